@@ -1,0 +1,220 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python oracle/gen_golden.py            # writes tests/golden/<scenario>.npz
+
+What is imported from the reference, unmodified: ``qpth.AL_mpc.MPC`` / ``qpth.al_utils`` (the whole
+hot path) and ``deqmpc/rex_quadrotor.py`` / ``deqmpc/flying_cartpole2d.py`` (TorchScript dynamics).
+Stubs needed to import them here: ``ipdb`` (empty module) and ``rexquad_utils`` (un-shipped; replaced
+by oracle/rexquad_standin.py — those helper formulas are therefore *unpinned*).
+Pendulum / cartpole dynamics are the reference's own CasADi C compiled into oracle/_ref
+(oracle/Makefile), wrapped as ``dx`` / ``dx_jac`` callables with the conventions of
+deqmpc/my_envs/dynamics.py:27-108.
+
+Hooks (no reference edits): ``al_utils.merit_grad_hessian`` (grad per Newton step),
+``al_utils.line_search_newton`` (20 merits, argmin, accept, incoming merit) and
+``al_utils.NewtonAL`` (fp64 iterate before the ``.float()`` cast of AL_mpc.py:337-338).
+"""
+import argparse
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("ALMPC_REFERENCE", "/root/reference")
+
+
+def import_reference():
+    sys.modules.setdefault("ipdb", types.ModuleType("ipdb"))
+    import oracle.rexquad_standin as standin
+
+    sys.modules["rexquad_utils"] = standin
+    for p in (REF, os.path.join(REF, "deqmpc")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch  # noqa: F401
+    from qpth import AL_mpc, al_utils
+    import rex_quadrotor
+    import flying_cartpole2d
+
+    return AL_mpc, al_utils, rex_quadrotor, flying_cartpole2d
+
+
+# --------------------------------------------------------------------------------------------------
+# dynamics callables for the reference solver
+# --------------------------------------------------------------------------------------------------
+class CasadiDx:
+    """dx / dx_jac built on the reference's generated C (oracle/_ref), fp64, one sample at a time."""
+
+    def __init__(self, pkg, nq, dt):
+        from oracle.dynamics_oracle import CasadiRef
+
+        self.ref, self.nq, self.dt = CasadiRef(pkg, nq), nq, dt
+
+    def dx(self, x, u):
+        import torch
+
+        xn = np.stack([self.ref.step(xi, float(ui[0]), self.dt) for xi, ui in zip(x.detach().double().numpy(), u.detach().double().numpy())])
+        return torch.from_numpy(xn).to(x.dtype)
+
+    def dx_jac(self, x, u):
+        import torch
+
+        xs, us = x.detach().double().numpy(), u.detach().double().numpy()
+        J = [self.ref.jac(xi, float(ui[0]), self.dt) for xi, ui in zip(xs, us)]
+        Jx = torch.from_numpy(np.stack([j[0] for j in J])).to(x.dtype)
+        Ju = torch.from_numpy(np.stack([j[1] for j in J])).to(x.dtype)
+        return self.dx(x, u), (Jx, Ju)
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic inputs — shared with tests/ and bench.py through oracle/problem_gen.py
+# --------------------------------------------------------------------------------------------------
+def run_scenario(name, model_name, T, B, dtype_name, calls, seed, stream_after=None, rho_init_max=1e4):
+    """calls = list of al_iter per MPC.forward call; state (lam, rho, warm start) carries across calls
+    exactly as in the DEQ loop (policies.py:147-171).  stream_after = index of the call before which
+    warm_start_initialize is invoked (policies.py:1305-1310)."""
+    import torch
+
+    AL_mpc, al_utils, rex_quadrotor, flying_cartpole2d = import_reference()
+    from oracle import problem_gen
+
+    dtype = torch.float64 if dtype_name == "f64" else torch.float32
+    om = problem_gen.make_oracle_model(model_name)
+    if model_name == "rex_quadrotor":
+        env = rex_quadrotor.RexQuadrotor(bsz=B)
+        dx, dx_jac = env.dynamics, env.dynamics_derivatives
+    elif model_name == "flying_cartpole":
+        env = flying_cartpole2d.FlyingCartpole(bsz=B)
+        dx, dx_jac = env.dynamics, env.dynamics_derivatives
+    else:
+        pkg, nq = {"pendulum": ("pendulum1l", 1), "cartpole1l": ("cartpole1l", 2), "cartpole2l": ("cartpole2l", 3)}[model_name]
+        cd = CasadiDx(pkg, nq, om.dt)
+        dx, dx_jac = cd.dx, cd.dx_jac
+    nx, nu, n = om.nx, om.nu, om.nx + om.nu
+
+    inp = problem_gen.make_inputs(model_name, T, B, seed)
+    x0, x_ref, u_ref = inp["x0"], inp["x_ref"], inp["u_ref"]
+    Qd1 = inp["Qd"].to(dtype)  # [n]
+    Qfull = torch.diag(Qd1).repeat(B, T, 1, 1)
+
+    ctrl = AL_mpc.MPC(nx, nu, T, u_lower=torch.tensor(om.u_lower), u_upper=torch.tensor(om.u_upper),
+                      n_batch=B, dtype=dtype)
+    ctrl.reinitialize(x_ref, None)
+
+    # ---- hooks
+    rec = {"grad": [], "dir": [], "merits": [], "idx": [], "accept": [], "merit_in": [], "xu64": [], "nsteps": []}
+    orig_mgh, orig_ls, orig_newton = al_utils.merit_grad_hessian, al_utils.line_search_newton, al_utils.NewtonAL
+
+    def mgh(*a, **k):
+        out = orig_mgh(*a, **k)
+        rec["grad"].append(out[0].detach().clone())
+        return out
+
+    def ls(update, x_est, meritfnQ, merit, x0_):
+        vals = {}
+
+        def spy(xn):
+            v = meritfnQ(xn)
+            vals["v"] = v.detach().reshape(20, -1).clone()
+            return v
+
+        out = orig_ls(update, x_est, spy, merit, x0_)
+        rec["dir"].append(update.detach().clone())
+        rec["merits"].append(vals["v"])
+        rec["idx"].append(torch.min(vals["v"], dim=0).indices.clone())
+        rec["accept"].append(out[3].detach().bool().clone())
+        rec["merit_in"].append(merit.detach().clone())
+        return out
+
+    class NewtonProxy:
+        @staticmethod
+        def apply(*a):
+            n0 = len(rec["dir"])
+            out = orig_newton.apply(*a)
+            rec["xu64"].append(out[0].detach().clone())
+            rec["nsteps"].append(len(rec["dir"]) - n0)
+            return out
+
+    al_utils.merit_grad_hessian, al_utils.line_search_newton, al_utils.NewtonAL = mgh, ls, NewtonProxy
+    out = {}
+    try:
+        g = torch.Generator().manual_seed(seed + 7)
+        for ci, al_iter in enumerate(calls):
+            if stream_after is not None and ci == stream_after:
+                # Tracking_MPC.warm_start_initialize (policies.py:1305-1310)
+                xi, ui = ctrl.x_init, ctrl.u_init
+                ui[:, -1:] = u_ref[:, -1:]
+                xi[:, -1:] = x_ref[:, -1:]
+                ctrl.warm_start_initialize(xi, ui, types.SimpleNamespace(rho_init_max=rho_init_max))
+            if ctrl.x_init is None:  # Tracking_MPC.forward, policies.py:1242-1244
+                ctrl.x_init, ctrl.u_init = x_ref.detach().clone(), u_ref.detach().clone()
+            xu_ref = torch.cat([x_ref, u_ref], -1)
+            Qleaf = Qfull.clone().requires_grad_(True)
+            p = (-(Qfull * xu_ref.unsqueeze(-2)).sum(-1)).detach().requires_grad_(True)  # policies.py:1295
+            f = 0.5 * (xu_ref * (Qfull * xu_ref.unsqueeze(-2)).sum(-1)).sum(-1)
+            ctrl.al_iter = al_iter
+            pre = dict(xu_init=torch.cat([ctrl.x_init, ctrl.u_init], -1).clone(), lam=ctrl.lamda_prev.clone(),
+                       rho=(ctrl.rho_prev.clone() if torch.is_tensor(ctrl.rho_prev) else torch.full((B, 1), ctrl.rho_prev)))
+            k0 = len(rec["dir"])
+            a0 = len(rec["xu64"])
+            x, u, status = ctrl(x0, al_utils.QuadCost(Qleaf, p, f), dx, dx_jac)
+            gx = torch.randn(x.shape, generator=g)
+            gu = torch.randn(u.shape, generator=g)
+            Qg, qg = torch.autograd.grad((x, u), (Qleaf, p), (gx, gu))
+            pfx = f"c{ci}_"
+            out.update({
+                pfx + "x_ref": x_ref, pfx + "u_ref": u_ref, pfx + "q": p.detach(), pfx + "xu_init": pre["xu_init"],
+                pfx + "lam_in": pre["lam"], pfx + "rho_in": pre["rho"], pfx + "al_iter": np.int64(al_iter),
+                pfx + "x": x.detach(), pfx + "u": u.detach(), pfx + "status": np.bool_(bool(status)),
+                pfx + "warm": np.bool_(bool(ctrl.warm_starting)),
+                pfx + "xu64": rec["xu64"][-1], pfx + "lam_out": ctrl.lamda_prev, pfx + "rho_out": ctrl.rho_prev,
+                pfx + "dyn_res": ctrl.dyn_res_prev, pfx + "nsteps": np.array(rec["nsteps"][a0:], dtype=np.int64),
+                pfx + "gx": gx, pfx + "gu": gu, pfx + "Q_grad": Qg.diagonal(dim1=-2, dim2=-1), pfx + "q_grad": qg,
+                pfx + "step_grad": torch.stack(rec["grad"][k0:]), pfx + "step_dir": torch.stack(rec["dir"][k0:]),
+                pfx + "step_merits": torch.stack(rec["merits"][k0:]), pfx + "step_idx": torch.stack(rec["idx"][k0:]),
+                pfx + "step_accept": torch.stack(rec["accept"][k0:]), pfx + "step_merit_in": torch.stack(rec["merit_in"][k0:]),
+                pfx + "xu_al": torch.stack(rec["xu64"][a0:]),
+            })
+            # synthetic "network": pull the reference trajectory towards the solution
+            x_ref = (0.7 * x_ref + 0.3 * x.detach()).clone()
+            x_ref[:, 0] = x0
+    finally:
+        al_utils.merit_grad_hessian, al_utils.line_search_newton, al_utils.NewtonAL = orig_mgh, orig_ls, orig_newton
+
+    out.update({"x0": x0, "Qd": Qd1, "u_lower": torch.tensor(om.u_lower), "u_upper": torch.tensor(om.u_upper),
+                "n_calls": np.int64(len(calls)), "T": np.int64(T), "B": np.int64(B), "seed": np.int64(seed),
+                "stream_after": np.int64(-1 if stream_after is None else stream_after),
+                "rho_init_max": np.float64(rho_init_max)})
+    meta = dict(model=model_name, dtype=dtype_name, torch=torch.__version__)
+    npz = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
+    npz["meta_model"] = np.array(meta["model"])
+    npz["meta_dtype"] = np.array(meta["dtype"])
+    npz["meta_torch"] = np.array(meta["torch"])
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **npz)
+    print(f"{name}: wrote {path} ({os.path.getsize(path)/1024:.0f} KB) newton steps per call:",
+          [out[f'c{c}_nsteps'].tolist() for c in range(len(calls))])
+
+
+SCENARIOS = {
+    # name: (model, T, B, dtype, calls(al_iter each), seed, stream_after)
+    "quad_T5_f64_cold": ("rex_quadrotor", 5, 8, "f64", [2], 1003, None),
+    "quad_T5_f64_chain": ("rex_quadrotor", 5, 6, "f64", [2, 2, 2, 2], 1013, None),
+    "quad_T5_f32_cold": ("rex_quadrotor", 5, 8, "f32", [2], 1023, None),
+    "pendulum_T5_f64_chain": ("pendulum", 5, 16, "f64", [2, 2, 2], 1000, None),
+    "cartpole1l_T5_f64_stream": ("cartpole1l", 5, 12, "f64", [2, 2, 2, 2, 2, 2, 2, 2, 2], 1001, 6),
+    "flying_T10_f64_cold": ("flying_cartpole", 10, 4, "f64", [2, 2], 1002, None),
+    "quad_T5_f64_lastqp": ("rex_quadrotor", 5, 4, "f64", [10], 1033, None),
+}
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("names", nargs="*", default=list(SCENARIOS))
+    args = ap.parse_args()
+    for nm in args.names:
+        run_scenario(nm, *SCENARIOS[nm])
