@@ -1,0 +1,182 @@
+"""Drop-in for ``qpth.AL_mpc.MPC`` (reference qpth/AL_mpc.py:53-592) on top of the fused CUDA solver.
+
+Same constructor keywords, same ``forward(x0, cost, dx, dx_jac, compute_Qq=None, u_init=None,
+x_init=None) -> (x, u, status)`` and the same mutable state the caller touches
+(``al_iter``, ``x_init`` / ``u_init``, ``lamda_prev`` / ``rho_prev``, ``warm_starting``,
+``reinitialize``, ``warm_start_initialize``) — see deqmpc/policies.py:1200-1216,1236-1310 for the
+call sites.  Differences, all deliberate:
+
+* the dynamics callable must resolve to a native CUDA functor (``dynamics.resolve``); there is no
+  CPU fallback and no generic-callable path yet — anything else raises;
+* the al_iter x Newton loop runs as one stream-ordered sequence of kernel launches with the
+  batch-global decisions taken on the device, so ``forward`` only synchronises with the host in
+  streaming mode, where the reference's own ``status`` is a Python bool (AL_mpc.py:420-423);
+* ``cost.C`` may be the reference's diag-embedded [B,T,n,n] tensor or already its diagonal [B,T,n].
+"""
+import torch
+from torch.nn import Module
+
+from . import _lib
+from .al_utils import LinDx, QuadCost  # noqa: F401  (re-exported like the reference module)
+from .dynamics import resolve
+from .solver import ALSolve, SolveConfig
+
+
+def _detach_maybe(x):
+    if x is None:
+        return None
+    return x.detach() if torch.is_tensor(x) and x.requires_grad else x
+
+
+class MPC(Module):
+    def __init__(self, n_state, n_ctrl, T, u_lower=None, u_upper=None, u_init=None, x_init=None, al_iter=2,
+                 verbose=0, eps=1e-7, back_eps=1e-7, n_batch=None, linesearch_decay=0.2, max_linesearch_iter=10,
+                 exit_unconverged=True, detach_unconverged=True, backprop=True, slew_rate_penalty=None,
+                 solver_type="dense", add_goal_constraint=False, x_goal=None, diag_cost=True, ineqG=None, ineqh=None,
+                 state_estimator=False, dtype=torch.float64):
+        super().__init__()
+        assert (u_lower is None) == (u_upper is None)
+        assert max_linesearch_iter > 0
+        if u_lower is None:
+            raise _lib.AlmpcError("MPC needs control bounds (the reference dereferences them unconditionally, AL_mpc.py:152)")
+        if state_estimator or add_goal_constraint or ineqG is not None or not diag_cost:
+            raise _lib.AlmpcError("state_estimator / goal constraint / ineqG / dense cost are outside the fused AL-MPC path")
+        self.dtype = dtype
+        self.n_state, self.n_ctrl, self.T = n_state, n_ctrl, T
+        self.u_lower = _detach_maybe(torch.as_tensor(u_lower).to(dtype))
+        self.u_upper = _detach_maybe(torch.as_tensor(u_upper).to(dtype))
+        if self.u_lower.dim() == 0:
+            self.u_lower = self.u_lower.repeat(n_ctrl)
+            self.u_upper = self.u_upper.repeat(n_ctrl)
+        self.x_lower = self.x_upper = None
+        self.u_init = _detach_maybe(u_init)
+        self.x_init = _detach_maybe(x_init)
+        self.verbose, self.eps, self.back_eps, self.n_batch = verbose, eps, back_eps, n_batch
+        self.linesearch_decay, self.max_linesearch_iter = linesearch_decay, max_linesearch_iter
+        self.exit_unconverged, self.detach_unconverged, self.backprop = exit_unconverged, detach_unconverged, backprop
+        self.slew_rate_penalty, self.solver_type = slew_rate_penalty, solver_type
+        self.state_estimator, self.diag_cost = state_estimator, diag_cost
+        self.al_iter = al_iter
+        self.neq = n_state * T
+        self.nineq = 2 * n_ctrl * T
+        self.rho_prev = 1.0
+        self.rho_max = 1e8
+        self.max_newton_steps = 4
+        self.lamda_prev = None if n_batch is None else torch.zeros(n_batch, self.neq + self.nineq, dtype=dtype)
+        self.dyn_res_prev = 1000000
+        self.warm_starting = False
+        self.just_initialized = True
+        self.cost_hist_stream = [[], []]
+        self.mask = None
+        self.last_info = None      # device int32[INFO_INTS] of the latest solve (no sync to keep it)
+        self.last_status = None    # device int32[B] per-problem status bits
+        self._bounds_host = (self.u_lower.double().cpu().tolist(), self.u_upper.double().cpu().tolist())
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, x0, cost, dx, dx_jac, compute_Qq=None, u_init=None, x_init=None):
+        n_batch = self.n_batch if self.n_batch is not None else cost.C.size(0)
+        assert x0.ndimension() == 2 and x0.size(0) == n_batch
+        _lib.require_cuda(x0, "MPC.forward(x0)")
+        dyn = resolve(dx)
+        if dyn.nx != self.n_state or dyn.nu != self.n_ctrl:
+            raise _lib.AlmpcError("dynamics dimensions do not match n_state / n_ctrl")
+        dev = x0.device
+
+        # ---- primal warm start (AL_mpc.py:222-246)
+        if u_init is not None:
+            u = u_init
+        elif self.u_init is None:
+            u = torch.zeros(n_batch, self.T, self.n_ctrl, dtype=x0.dtype, device=dev)
+        else:
+            u = self.u_init
+        if u.ndimension() == 2:
+            u = u.unsqueeze(0).expand(n_batch, self.T, -1).clone()
+        u = u.to(dev).type_as(x0.data)
+        if x_init is not None:
+            x = x_init
+        elif self.x_init is None:
+            x = self.rollout(x0, u, dyn)
+        else:
+            x = self.x_init
+        if x.ndimension() == 2:
+            x = x.unsqueeze(0).expand(n_batch, self.T, -1).clone()
+        x = x.to(dev).type_as(x0.data)
+
+        # ---- cost (AL_mpc.py:249-250): diagonal of C, linear term c
+        C = cost.C
+        assert C.ndimension() in (3, 4)
+        Qd = C.diagonal(dim1=-2, dim2=-1) if C.ndimension() == 4 else C
+        Qd = Qd.to(self.dtype)
+        q = cost.c.to(self.dtype)
+
+        # ---- dual warm start
+        m = self.neq + self.nineq
+        lam = self.lamda_prev
+        if lam is None or lam.shape != (n_batch, m):
+            lam = torch.zeros(n_batch, m, dtype=self.dtype, device=dev)
+        rho = self.rho_prev
+        if not torch.is_tensor(rho):
+            rho = torch.full((n_batch, 1), float(rho), dtype=self.dtype, device=dev)
+        rho_dtype = rho.dtype
+        cfg = SolveConfig(
+            dyn=dyn, T=self.T, u_lower=self._bounds_host[0], u_upper=self._bounds_host[1], al_iter=int(self.al_iter),
+            max_newton=self.max_newton_steps, stream_mode=bool(self.warm_starting),
+            rho_f32=(rho_dtype == torch.float32 and self.dtype == torch.float64), rho_max=self.rho_max)
+        xu0 = torch.cat([x.to(self.dtype), u.to(self.dtype)], dim=2)
+        xo, uo, xu, lam_new, rho_new, dyn_res, status, info, _ = ALSolve.apply(
+            Qd, q, x0.to(self.dtype), xu0, lam.to(dev).to(self.dtype), rho.to(dev).to(self.dtype).reshape(-1), cfg)
+
+        # ---- state kept for the next call (AL_mpc.py:333-336, 256-257)
+        self.lamda_prev = lam_new
+        self.rho_prev = rho_new.to(rho_dtype).reshape(n_batch, 1)
+        self.dyn_res_prev = dyn_res
+        self.just_initialized = False
+        self.last_info, self.last_status, self.last_xu = info, status, xu
+        self.x_init = xo.detach().clone()
+        self.u_init = uo.detach().clone()
+        flag = False
+        if self.warm_starting:
+            flag = bool(info[_lib.INFO_RHO_EXCEEDED].item())  # the reference syncs here too (AL_mpc.py:412,420)
+        return xo, uo, flag
+
+    # ------------------------------------------------------------------------------------------
+    def rollout(self, x, actions, dynamics):
+        """AL_mpc.py:521-534 with the native functor."""
+        dyn = resolve(dynamics)
+        xs = [x]
+        for t in range(self.T - 1):
+            xs.append(dyn(xs[t].contiguous(), actions[:, t].contiguous()))
+        return torch.stack(xs, 1)
+
+    def get_xu(self):
+        return torch.cat((self.x_init, self.u_init), dim=2)
+
+    def reinitialize(self, x, mask=None):
+        """AL_mpc.py:569-579: cold start — lam = 0, rho = 1 (in the dtype of ``x``), drop the warm start."""
+        self.u_init = None
+        self.x_init = None
+        self.n_batch = x.size(0)
+        self.rho_prev = torch.ones((self.n_batch, 1), device=x.device, dtype=x.dtype)
+        self.lamda_prev = torch.zeros(self.n_batch, self.neq + self.nineq, device=x.device, dtype=x.dtype)
+        self.cost_hist_stream = [[], []]
+        self.dyn_res_prev = 1000000
+        self.just_initialized = True
+        self.warm_starting = False
+        self.mask = mask
+
+    def warm_start_initialize(self, x, u, args):
+        """AL_mpc.py:581-592: keep the primal warm start, zero the duals, clamp rho, switch to streaming."""
+        self.u_init = u
+        self.x_init = x
+        self.lamda_prev = self.lamda_prev * 0
+        rho = self.rho_prev
+        if not torch.is_tensor(rho):
+            rho = torch.full((self.n_batch, 1), float(rho), dtype=self.dtype, device=x.device)
+        self.rho_prev = torch.clamp(rho, max=args.rho_init_max)
+        self.just_initialized = True
+        self.warm_starting = True
+
+    def newton_steps(self):
+        """Host copy of the realised Newton-step counts of the latest solve (synchronises)."""
+        info = self.last_info.cpu().tolist()
+        return info[_lib.INFO_NEWTON0:_lib.INFO_NEWTON0 + info[_lib.INFO_AL_DONE]]

@@ -1,0 +1,1076 @@
+// libalmpc: fused batched augmented-Lagrangian MPC solver for sm_100a (B200).
+//
+// One warp owns one problem.  One launch of k_newton_step performs ONE Gauss-Newton step of the
+// reference's NewtonAL.forward (qpth/al_utils.py:451-576) for every problem of the batch:
+//
+//   P1  dynamics + Jacobians G_t=[A_t B_t] (forward-mode duals, one tangent column per lane)   al_utils.py:233-265
+//   P2  residuals c, (optional) dual/penalty update of the previous AL iteration, merit        AL_mpc.py:315-325, al_utils.py:52-77
+//   P3  gradient g = Qd z + q + J^T lam + rho Jc^T c+                                           al_utils.py:113-117
+//   P4  block-tridiagonal Cholesky of H = diag(Qd) + rho Jc^T Jc and the two triangular sweeps  al_utils.py:119-120, 510-515
+//       (the reference factors the dense 80x80 matrix; H is exactly block tridiagonal)
+//   P5  20-point line search, first-argmin, strict-decrease accept                              al_utils.py:618-642
+//   P6  batch-global stop statistics -> device-side control block for the next launch           al_utils.py:551-564
+//
+// The batch-global decisions of the reference (stop rule on ||c+||_F over the WHOLE batch, the
+// rho_max exit of al_solve_stream) are taken on the device by the last CTA of every launch
+// (deterministic two-stage reduction), so a solve is a fixed sequence of launches without any host
+// synchronisation; launches that find the solve finished return immediately.
+//
+// The block factor streams to global memory as it is produced (it is the cached factor the
+// implicit backward needs, al_utils.py:572,590) and is read back for the backward sweep.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "almpc.h"
+#include "almpc_models.cuh"
+
+namespace almpc {
+
+constexpr int NLS = ALMPC_N_LS;
+constexpr unsigned FULL = 0xffffffffu;
+
+enum Mode { MODE_FIRST = 0, MODE_CONT = 1, MODE_DUAL_NEWTON = 2, MODE_DONE = 3 };
+
+struct Ctl {
+  int mode, a, k, total_newton;
+  unsigned ticket;
+  int pad;
+  double res_old;
+  double rho_final_max;
+};
+
+template <typename S>
+struct KParams {
+  S dyn[ALMPC_MAX_PARAMS];
+  S ulo[ALMPC_MAX_NU], uhi[ALMPC_MAX_NU];
+  double rho_mult, rho_max;
+  int B, T, al_iter, max_newton, stream_mode, rho_f32, flags;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rsqrt_(double x) { return rsqrt(x); }
+__device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+template <typename S> __device__ __forceinline__ S fmax0(S x) { return x > S(0) ? x : S(0); }
+template <typename S> __device__ __forceinline__ bool finite_(S x) { return (x - x) == S(0); }
+
+template <typename S>
+__device__ __forceinline__ S warp_sum(S v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+template <typename S>
+__device__ __forceinline__ S next_rho(S rho, double mult, int f32) {
+  double r = (double)rho * mult;
+  if (f32) r = (double)(float)r;
+  return (S)r;
+}
+
+// per-warp shared-memory layout, in units of S
+template <int NX, int NU>
+struct Layout {
+  static constexpr int NN = NX + NU;
+  int N, neq, nin, m;
+  int xu, dv, lam, c, w, x0, G, scr, total;
+  __host__ __device__ Layout(int T) {
+    N = T * NN; neq = T * NX; nin = 2 * T * NU; m = neq + nin;
+    int o = 0;
+    xu = o; o += N;
+    dv = o; o += N;
+    lam = o; o += m;
+    c = o; o += neq;
+    w = o; o += neq;
+    x0 = o; o += NX;
+    G = o; o += (T - 1) * NX * NN;
+    scr = o;
+    int s1 = NN * (NN + 1), s2 = NLS * (T - 1) * 3 + NLS * 4;
+    o += (s1 > s2 ? s1 : s2);
+    total = (o + 1) & ~1;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// right-looking elimination on "one row per lane".
+//   lanes 0..NN-1 : rows of the SPD block (lower part in a[0..lane])         -> rows of L (diag = 1/L_ii)
+//   lanes >= NN   : extra rows b (rhs, sub-diagonal block rows)               -> b L^{-T}
+// FUSED=true  : factor + solve in one pass.
+// FUSED=false : lanes 0..NN-1 already hold L (read-only); only lanes >= NN are transformed.
+// ------------------------------------------------------------------------------------------------
+template <int NN, bool FUSED, typename S>
+__device__ __forceinline__ bool eliminate(S (&a)[NN], int lane) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < NN; ++k) {
+    S lk;
+    if (FUSED) {
+      S d = __shfl_sync(FULL, a[k], k);
+      ok = ok && (d > S(0));
+      S inv = rsqrt_(d);
+      lk = a[k] * inv;
+      a[k] = (lane == k) ? inv : lk;
+#pragma unroll
+      for (int j = k + 1; j < NN; ++j) {
+        S ljk = __shfl_sync(FULL, lk, j);
+        a[j] -= lk * ljk;
+      }
+    } else {
+      S inv = __shfl_sync(FULL, a[k], k);
+      lk = a[k] * inv;
+      if (lane >= NN) a[k] = lk;
+#pragma unroll
+      for (int j = k + 1; j < NN; ++j) {
+        S ljk = __shfl_sync(FULL, a[k], j);
+        if (lane >= NN) a[j] -= lk * ljk;
+      }
+    }
+  }
+  return ok;
+}
+
+// factor storage per problem: T blocks [NN][NN] then (T-1) blocks [NX][NN]
+template <int NX, int NU>
+__host__ __device__ inline size_t factor_elems(int T) {
+  constexpr int NN = NX + NU;
+  return (size_t)T * NN * NN + (size_t)(T - 1) * NX * NN;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward sweep: factor H (block tridiagonal) and solve L y = g.  On entry dv = g, G = Jacobians.
+// On exit dv = y, G slots hold E_t = H_{t+1,t} L_tt^{-T}, factor (global) holds L_tt and E_t.
+// BUILD=true  : build D_t from G, Qd, rho and the active set, factor, stream to `fac`
+// BUILD=false : (backward pass) read L_tt / E_t from `fac` and only do the substitution.
+// ------------------------------------------------------------------------------------------------
+template <int NX, int NU, typename S>
+__device__ __forceinline__ bool forward_sweep_factor(S* sm, const Layout<NX, NU>& L, int T, int lane, S rho,
+                                                     const S* __restrict__ Qd_g, const S* ulo, const S* uhi,
+                                                     S* fac) {
+  constexpr int NN = NX + NU;
+  constexpr int LD = NN + 1;
+  constexpr int EX0 = 32 - NN - 1;  // sub-diagonal rows that fit next to L rows and the rhs row
+  constexpr int NTRI = NN * (NN + 1) / 2;
+  S* xu = sm + L.xu;
+  S* dv = sm + L.dv;
+  S* G = sm + L.G;
+  S* scr = sm + L.scr;
+  bool ok = true;
+  for (int t = 0; t < T; ++t) {
+    const S* Gt = G + (size_t)t * NX * NN;          // valid for t < T-1
+    const S* Ep = G + (size_t)(t - 1) * NX * NN;    // E_{t-1}, valid for t > 0
+    // ---- (a) D_t (lower triangle) into scr; rhs_t -= E_{t-1} y_{t-1}
+    for (int idx = lane; idx < NTRI; idx += 32) {
+      int r = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
+      while (r * (r + 1) / 2 > idx) --r;
+      while ((r + 1) * (r + 2) / 2 <= idx) ++r;
+      int c = idx - r * (r + 1) / 2;
+      S v = S(0);
+      if (t < T - 1) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) v += Gt[i * NN + r] * Gt[i * NN + c];
+      }
+      if (r == c) {
+        if (r < NX) {
+          v += S(1);
+        } else {
+          S u = xu[t * NN + r];
+          v += ((u - uhi[r - NX]) >= S(0) ? S(1) : S(0)) + ((ulo[r - NX] - u) >= S(0) ? S(1) : S(0));
+        }
+      }
+      v *= rho;
+      if (r == c) v += Qd_g[t * NN + r];
+      if (t > 0 && r < NX) {  // c <= r < NX
+        S s = S(0);
+#pragma unroll
+        for (int k = 0; k < NN; ++k) s += Ep[r * NN + k] * Ep[c * NN + k];
+        v -= s;
+      }
+      scr[r * LD + c] = v;
+    }
+    if (t > 0) {
+      for (int r = lane; r < NX; r += 32) {
+        S s = S(0);
+#pragma unroll
+        for (int k = 0; k < NN; ++k) s += Ep[r * NN + k] * dv[(t - 1) * NN + k];
+        dv[t * NN + r] -= s;
+      }
+    }
+    __syncwarp();
+    // ---- (b) rows into registers
+    S a[NN];
+    if (lane < NN) {
+#pragma unroll
+      for (int c = 0; c < NN; ++c) a[c] = (c <= lane) ? scr[lane * LD + c] : S(0);
+    } else if (lane == NN) {
+#pragma unroll
+      for (int c = 0; c < NN; ++c) a[c] = dv[t * NN + c];
+    } else {
+      int i = lane - NN - 1;
+      bool act = (i < NX) && (t < T - 1);
+#pragma unroll
+      for (int c = 0; c < NN; ++c) a[c] = act ? -rho * Gt[i * NN + c] : S(0);
+    }
+    // ---- (c) factor + forward substitution + trsm in one elimination
+    ok = eliminate<NN, true>(a, lane) && ok;
+    __syncwarp();
+    // ---- (d) write-outs
+    if (lane < NN) {
+#pragma unroll
+      for (int c = 0; c < NN; ++c) scr[lane * LD + c] = (c <= lane) ? a[c] : S(0);
+    } else if (lane == NN) {
+#pragma unroll
+      for (int c = 0; c < NN; ++c) dv[t * NN + c] = a[c];
+    } else {
+      int i = lane - NN - 1;
+      if (i < NX && t < T - 1) {
+        S* Et = G + (size_t)t * NX * NN;
+#pragma unroll
+        for (int c = 0; c < NN; ++c) Et[i * NN + c] = a[c];
+      }
+    }
+    if (NX > EX0 && t < T - 1) {  // sub-diagonal rows that did not fit (e.g. flying cartpole nx=14, n=18)
+      constexpr int PER = 32 - NN;
+      for (int base = EX0; base < NX; base += PER) {
+        int i = base + (lane - NN);
+        bool act = (lane >= NN) && (i < NX);
+        if (lane >= NN) {
+#pragma unroll
+          for (int c = 0; c < NN; ++c) a[c] = act ? -rho * Gt[i * NN + c] : S(0);
+        }
+        eliminate<NN, false>(a, lane);
+        if (act) {
+          S* Et = G + (size_t)t * NX * NN;
+#pragma unroll
+          for (int c = 0; c < NN; ++c) Et[i * NN + c] = a[c];
+        }
+      }
+    }
+    __syncwarp();
+    // stream L_tt (row-major NN x NN) and E_t to global
+    {
+      S* Lg = fac + (size_t)t * NN * NN;
+      for (int idx = lane; idx < NN * NN; idx += 32) {
+        int r = idx / NN, c = idx - r * NN;
+        Lg[idx] = scr[r * LD + c];
+      }
+      if (t < T - 1) {
+        S* Eg = fac + (size_t)T * NN * NN + (size_t)t * NX * NN;
+        const S* Et = G + (size_t)t * NX * NN;
+        for (int idx = lane; idx < NX * NN; idx += 32) Eg[idx] = Et[idx];
+      }
+    }
+    __syncwarp();
+  }
+  return ok;
+}
+
+// forward substitution only, from a stored factor (backward pass): dv = L^{-1} dv
+template <int NX, int NU, typename S>
+__device__ __forceinline__ void forward_sweep_stored(S* dv, S* Esm, int T, int lane, const S* fac) {
+  constexpr int NN = NX + NU;
+  for (int t = 0; t < T; ++t) {
+    if (t > 0) {
+      // dv_t[r] -= sum_k E_{t-1}[r][k] y_{t-1}[k]
+      const S* Eg = fac + (size_t)T * NN * NN + (size_t)(t - 1) * NX * NN;
+      for (int idx = lane; idx < NX * NN; idx += 32) Esm[idx] = Eg[idx];
+      __syncwarp();
+      for (int r = lane; r < NX; r += 32) {
+        S s = S(0);
+#pragma unroll
+        for (int k = 0; k < NN; ++k) s += Esm[r * NN + k] * dv[(t - 1) * NN + k];
+        dv[t * NN + r] -= s;
+      }
+      __syncwarp();
+    }
+    // row-per-lane substitution: y_k = b_k * inv_k ; b_r -= L[r][k] y_k
+    S a[NN];
+    const S* Lg = fac + (size_t)t * NN * NN;
+    if (lane < NN) {
+#pragma unroll
+      for (int c = 0; c < NN; ++c) a[c] = Lg[lane * NN + c];
+    }
+    S b = (lane < NN) ? dv[t * NN + lane] : S(0);
+#pragma unroll
+    for (int k = 0; k < NN; ++k) {
+      S yk = __shfl_sync(FULL, b * a[k], k);  // lane k: a[k] = 1/L_kk
+      if (lane == k) b = yk;
+      else if (lane > k) b -= a[k] * yk;
+    }
+    if (lane < NN) dv[t * NN + lane] = b;
+    __syncwarp();
+  }
+}
+
+// backward sweep: dv = L^{-T} dv, with L_tt read from global (column per lane) and E_t either from
+// shared memory (Esm_all != nullptr: all blocks resident, forward solve) or from global.
+template <int NX, int NU, typename S>
+__device__ __forceinline__ void backward_sweep(S* dv, const S* Esm_all, S* Etmp, int T, int lane,
+                                               const S* fac) {  // NOT restrict/nc: written earlier by this warp
+  constexpr int NN = NX + NU;
+  for (int t = T - 1; t >= 0; --t) {
+    S l[NN];
+    const S* Lg = fac + (size_t)t * NN * NN;
+    if (lane < NN) {
+#pragma unroll
+      for (int r = 0; r < NN; ++r) l[r] = (r >= lane) ? Lg[r * NN + lane] : S(0);
+    }
+    S b = (lane < NN) ? dv[t * NN + lane] : S(0);
+    if (t < T - 1) {
+      const S* Et;
+      if (Esm_all) {
+        Et = Esm_all + (size_t)t * NX * NN;
+      } else {
+        const S* Eg = fac + (size_t)T * NN * NN + (size_t)t * NX * NN;
+        for (int idx = lane; idx < NX * NN; idx += 32) Etmp[idx] = Eg[idx];
+        __syncwarp();
+        Et = Etmp;
+      }
+      if (lane < NN) {
+        S s = S(0);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) s += Et[i * NN + lane] * dv[(t + 1) * NN + i];
+        b -= s;
+      }
+    }
+#pragma unroll
+    for (int r = NN - 1; r >= 0; --r) {
+      S dr = __shfl_sync(FULL, b * l[r], r);  // lane r: l[r] = 1/L_rr
+      if (lane == r) b = dr;
+      else if (lane < r) b -= l[r] * dr;
+    }
+    if (lane < NN) dv[t * NN + lane] = b;
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the Newton-step kernel
+// ------------------------------------------------------------------------------------------------
+template <class M, typename S, int WPB>
+__global__ void __launch_bounds__(WPB * 32, 4)
+k_newton_step(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__ Qd_g, const S* __restrict__ q_g,
+              S* __restrict__ xu_g, S* __restrict__ lam_g, S* __restrict__ rho_g, S* __restrict__ fac_g,
+              int* __restrict__ status_g, int* __restrict__ info_g, S* __restrict__ debug_g, Ctl* ctl,
+              double* __restrict__ partials, S* __restrict__ merit_g) {
+  constexpr int NX = M::NX, NU = M::NU, NN = NX + NU;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[WPB][3];
+
+  const int mode = ctl->mode;
+  if (mode == MODE_DONE) return;
+  const int al_a = ctl->a, nk = ctl->k;
+
+  const int T = P.T;
+  const Layout<NX, NU> L(T);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int prob = blockIdx.x * WPB + warp;
+  S* sm = reinterpret_cast<S*>(smem_raw) + (size_t)warp * L.total;
+  S* xu = sm + L.xu;
+  S* dv = sm + L.dv;
+  S* lam = sm + L.lam;
+  S* cres = sm + L.c;
+  S* wv = sm + L.w;
+  S* x0 = sm + L.x0;
+  S* G = sm + L.G;
+  S* scr = sm + L.scr;
+  const S* dyn = P.dyn;
+
+  double r_entry = 0.0, r_exit = 0.0, rho_used = 0.0;
+
+  if (prob < P.B) {
+    const size_t pN = (size_t)prob * L.N;
+    const S* Qd = Qd_g + pN;
+    const S* qv = q_g + pN;
+    // ---------------------------------------------------------------- P0 load
+    for (int i = lane; i < L.N; i += 32) xu[i] = xu_g[pN + i];
+    for (int i = lane; i < L.m; i += 32) lam[i] = lam_g[(size_t)prob * L.m + i];
+    for (int i = lane; i < NX; i += 32) x0[i] = x0_g[(size_t)prob * NX + i];
+    S rho = rho_g[prob];
+    S merit_cur = (mode == MODE_CONT) ? merit_g[prob] : S(0);
+    int status = (mode == MODE_FIRST) ? (ALMPC_STATUS_FINITE | ALMPC_STATUS_CHOL_OK) : status_g[prob];
+    __syncwarp();
+
+    // ---------------------------------------------------------------- P1 dynamics + Jacobian columns
+    for (int it = lane; it < (T - 1) * NN; it += 32) {
+      const int t = it / NN, j = it - t * NN;
+      Dual<S> xd[NX], ud[NU], xn[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) xd[i] = Dual<S>(xu[t * NN + i], (i == j) ? S(1) : S(0));
+#pragma unroll
+      for (int i = 0; i < NU; ++i) ud[i] = Dual<S>(xu[t * NN + NX + i], (NX + i == j) ? S(1) : S(0));
+      rk4_step<M, S, Dual<S>>(xd, ud, xn, dyn);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) G[(size_t)t * NX * NN + i * NN + j] = xn[i].d;
+      if (j == 0) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) cres[t * NX + i] = xu[(t + 1) * NN + i] - xn[i].v;
+      }
+    }
+    for (int i = lane; i < NX; i += 32) cres[(T - 1) * NX + i] = xu[i] - x0[i];
+    __syncwarp();
+
+    // ---------------------------------------------------------------- P2 dual update / merit / entry residual
+    if (mode == MODE_DUAL_NEWTON) {
+      // lam <- lam + rho c ; lam_ineq <- max(0, .) ; rho <- 10 rho        (AL_mpc.py:316-317,325)
+      for (int i = lane; i < L.neq; i += 32) lam[i] += rho * cres[i];
+      for (int i = lane; i < L.nin; i += 32) {
+        int t = i / (2 * NU), s = i - t * 2 * NU;
+        S u = xu[t * NN + NX + (s < NU ? s : s - NU)];
+        S ci = (s < NU) ? (u - P.uhi[s]) : (P.ulo[s - NU] - u);
+        lam[L.neq + i] = fmax0(lam[L.neq + i] + rho * ci);
+      }
+      rho = next_rho(rho, P.rho_mult, P.rho_f32);
+      __syncwarp();
+      for (int i = lane; i < L.m; i += 32) lam_g[(size_t)prob * L.m + i] = lam[i];
+      if (lane == 0) rho_g[prob] = rho;
+    }
+    rho_used = (double)rho;
+    {
+      S s2 = S(0), sl = S(0), cost = S(0);
+      for (int i = lane; i < L.neq; i += 32) {
+        S ci = cres[i];
+        s2 += ci * ci;
+        sl += lam[i] * ci;
+        wv[i] = lam[i] + rho * ci;
+      }
+      for (int i = lane; i < L.nin; i += 32) {
+        int t = i / (2 * NU), s = i - t * 2 * NU;
+        S u = xu[t * NN + NX + (s < NU ? s : s - NU)];
+        S ci = (s < NU) ? (u - P.uhi[s]) : (P.ulo[s - NU] - u);
+        S cp = fmax0(ci);
+        s2 += cp * cp;
+        sl += lam[L.neq + i] * ci;
+      }
+      for (int i = lane; i < L.N; i += 32) {
+        S z = xu[i];
+        cost += S(0.5) * (z * Qd[i] * z) + qv[i] * z;
+      }
+      s2 = warp_sum(s2);
+      sl = warp_sum(sl);
+      cost = warp_sum(cost);
+      r_entry = (double)s2;
+      if (mode != MODE_CONT) merit_cur = cost + S(0.5) * rho * s2 + sl;
+    }
+    __syncwarp();
+
+    // ---------------------------------------------------------------- P3 gradient -> dv
+    for (int idx = lane; idx < L.N; idx += 32) {
+      const int t = idx / NN, j = idx - t * NN;
+      S g = Qd[idx] * xu[idx] + qv[idx];
+      if (t < T - 1) {
+        const S* Gt = G + (size_t)t * NX * NN;
+        S s = S(0);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) s += Gt[i * NN + j] * wv[t * NX + i];
+        g -= s;
+      }
+      if (j < NX) {
+        g += (t > 0) ? wv[(t - 1) * NX + j] : wv[(T - 1) * NX + j];
+      } else {
+        int s = j - NX;
+        S u = xu[idx];
+        S cu = u - P.uhi[s], cl = P.ulo[s] - u;
+        S lu = lam[L.neq + t * 2 * NU + s], ll = lam[L.neq + t * 2 * NU + NU + s];
+        g += (lu - ll) + rho * (fmax0(cu) - fmax0(cl));
+      }
+      dv[idx] = g;
+      if (debug_g) debug_g[(size_t)prob * (2 * L.N + 24) + idx] = g;
+    }
+    __syncwarp();
+
+    // ---------------------------------------------------------------- P4 factor + solve
+    S* fac = fac_g + (size_t)prob * factor_elems<NX, NU>(T);
+    bool ok = forward_sweep_factor<NX, NU, S>(sm, L, T, lane, rho, Qd, P.ulo, P.uhi, fac);
+    ok = __all_sync(FULL, ok);
+    if (!ok) status &= ~ALMPC_STATUS_CHOL_OK;
+    backward_sweep<NX, NU, S>(dv, G, nullptr, T, lane, fac);
+    for (int i = lane; i < L.N; i += 32) {
+      S d = -dv[i];
+      dv[i] = d;
+      if (debug_g) debug_g[(size_t)prob * (2 * L.N + 24) + L.N + i] = d;
+    }
+    __syncwarp();
+
+    // ---------------------------------------------------------------- P5 line search
+    S* part = scr;                       // [NLS][(T-1)][3]
+    S* cand = scr + NLS * (T - 1) * 3;   // [NLS][4]: merit, res2
+    for (int it = lane; it < NLS * (T - 1); it += 32) {
+      const int kk = it / (T - 1), t = it - kk * (T - 1);
+      const S alpha = (S)ldexpf(1.0f, -kk);
+      S xs[NX], us[NU], xn[NX];
+      S cost = S(0), s2 = S(0), sl = S(0);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        S z = xu[t * NN + i] + alpha * dv[t * NN + i];
+        xs[i] = z;
+        cost += S(0.5) * (z * Qd[t * NN + i] * z) + qv[t * NN + i] * z;
+      }
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        S z = xu[t * NN + NX + i] + alpha * dv[t * NN + NX + i];
+        us[i] = z;
+        cost += S(0.5) * (z * Qd[t * NN + NX + i] * z) + qv[t * NN + NX + i] * z;
+        S cu = z - P.uhi[i], cl = P.ulo[i] - z;
+        sl += lam[L.neq + t * 2 * NU + i] * cu + lam[L.neq + t * 2 * NU + NU + i] * cl;
+        S pu = fmax0(cu), pl = fmax0(cl);
+        s2 += pu * pu + pl * pl;
+      }
+      if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          S ci = xs[i] - x0[i];
+          s2 += ci * ci;
+          sl += lam[(T - 1) * NX + i] * ci;
+        }
+      }
+      rk4_step<M, S, S>(xs, us, xn, dyn);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        S z1 = xu[(t + 1) * NN + i] + alpha * dv[(t + 1) * NN + i];
+        S ci = z1 - xn[i];
+        s2 += ci * ci;
+        sl += lam[t * NX + i] * ci;
+        if (t == T - 2) cost += S(0.5) * (z1 * Qd[(t + 1) * NN + i] * z1) + qv[(t + 1) * NN + i] * z1;
+      }
+      if (t == T - 2) {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          const int e = (T - 1) * NN + NX + i;
+          S z = xu[e] + alpha * dv[e];
+          cost += S(0.5) * (z * Qd[e] * z) + qv[e] * z;
+          S cu = z - P.uhi[i], cl = P.ulo[i] - z;
+          sl += lam[L.neq + (T - 1) * 2 * NU + i] * cu + lam[L.neq + (T - 1) * 2 * NU + NU + i] * cl;
+          S pu = fmax0(cu), pl = fmax0(cl);
+          s2 += pu * pu + pl * pl;
+        }
+      }
+      part[it * 3 + 0] = cost;
+      part[it * 3 + 1] = s2;
+      part[it * 3 + 2] = sl;
+    }
+    __syncwarp();
+    S mk = S(0), r2k = S(0);
+    if (lane < NLS) {
+      S cost = S(0), s2 = S(0), sl = S(0);
+      for (int t = 0; t < T - 1; ++t) {
+        cost += part[(lane * (T - 1) + t) * 3 + 0];
+        s2 += part[(lane * (T - 1) + t) * 3 + 1];
+        sl += part[(lane * (T - 1) + t) * 3 + 2];
+      }
+      mk = cost + S(0.5) * rho * s2 + sl;
+      r2k = s2;
+      if (debug_g) debug_g[(size_t)prob * (2 * L.N + 24) + 2 * L.N + lane] = mk;
+    }
+    // first-argmin with torch.min NaN semantics (any NaN -> NaN, step rejected)
+    const bool isn = (lane < NLS) && (mk != mk);
+    const bool any_nan = __any_sync(FULL, isn);
+    S bv = (lane < NLS) ? mk : S(INFINITY);
+    int bi = (lane < NLS) ? lane : NLS;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      S ov = __shfl_xor_sync(FULL, bv, o);
+      int oi = __shfl_xor_sync(FULL, bi, o);
+      if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (bi >= NLS) bi = 0;  // all +inf
+    S r2_best = __shfl_sync(FULL, r2k, bi);
+    if (any_nan) bv = S(NAN);
+    const bool accept = bv < merit_cur;
+    const S alpha = (S)ldexpf(1.0f, -bi);
+    bool fin = true;
+    for (int i = lane; i < L.N; i += 32) {
+      S xo = xu[i];
+      S xnew = xo + alpha * dv[i];
+      S xr = accept ? xnew : (finite_(xnew) ? xo : S(NAN));  // status*x_next + (1-status)*x_est, al_utils.py:640-641
+      fin = fin && finite_(xr);
+      xu_g[pN + i] = xr;
+    }
+    fin = __all_sync(FULL, fin);
+    if (!fin) status &= ~ALMPC_STATUS_FINITE;
+    r_exit = accept ? (double)r2_best : (fin ? r_entry : (double)NAN);
+    if (lane == 0) {
+      merit_g[prob] = bv;  // merit <- new_merit even when the step was rejected (al_utils.py:569)
+      status_g[prob] = status;
+      if (debug_g) {
+        S* dbg = debug_g + (size_t)prob * (2 * L.N + 24) + 2 * L.N + NLS;
+        dbg[0] = (S)bi;
+        dbg[1] = accept ? S(1) : S(0);
+        dbg[2] = merit_cur;
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ P6 batch-global statistics
+  if (lane == 0) {
+    red[warp][0] = r_entry;
+    red[warp][1] = r_exit;
+    red[warp][2] = rho_used;
+  }
+  __syncthreads();
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int w = 0; w < WPB; ++w) { s0 += red[w][0]; s1 += red[w][1]; s2 = fmax(s2, red[w][2]); }
+    partials[blockIdx.x * 4 + 0] = s0;
+    partials[blockIdx.x * 4 + 1] = s1;
+    partials[blockIdx.x * 4 + 2] = s2;
+    __threadfence();
+    unsigned tk = atomicAdd(&ctl->ticket, 1u);
+    is_last = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // deterministic reduction over blocks by the last CTA: thread-strided partial sums, then a fixed tree
+  double (*fin_red)[3] = reinterpret_cast<double (*)[3]>(smem_raw);  // warp regions are dead by now
+  {
+    double s0 = 0, s1 = 0, s2 = 0;
+    const volatile double* pv = partials;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += WPB * 32) {
+      s0 += pv[b * 4 + 0];
+      s1 += pv[b * 4 + 1];
+      s2 = fmax(s2, pv[b * 4 + 2]);
+    }
+    fin_red[threadIdx.x][0] = s0;
+    fin_red[threadIdx.x][1] = s1;
+    fin_red[threadIdx.x][2] = s2;
+  }
+  __syncthreads();
+  for (int o = WPB * 16; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      fin_red[threadIdx.x][0] += fin_red[threadIdx.x + o][0];
+      fin_red[threadIdx.x][1] += fin_red[threadIdx.x + o][1];
+      fin_red[threadIdx.x][2] = fmax(fin_red[threadIdx.x][2], fin_red[threadIdx.x + o][2]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double R_entry = sqrt(fin_red[0][0]), R_exit = sqrt(fin_red[0][1]), rho_max_used = fin_red[0][2];
+    const double res_old = (nk == 0) ? R_entry : ctl->res_old;
+    // al_utils.py:560-564 — evaluated exactly as written there (NaN compares false -> no break)
+    bool stop = (fabs(res_old - R_exit) / R_exit < 1e-3) || (R_exit < 1e-3);
+    const int steps_done = nk + 1;
+    if (steps_done >= P.max_newton) stop = true;
+    ctl->ticket = 0;
+    ctl->total_newton += 1;
+    info_g[ALMPC_INFO_TOTAL_NEWTON] = ctl->total_newton;
+    if (!stop) {
+      ctl->k = steps_done;
+      ctl->mode = MODE_CONT;
+      ctl->res_old = R_exit;
+    } else {
+      info_g[ALMPC_INFO_NEWTON0 + al_a] = steps_done;
+      info_g[ALMPC_INFO_AL_DONE] = al_a + 1;
+      double rho_next = rho_max_used * P.rho_mult;
+      if (P.rho_f32) rho_next = (double)(float)rho_next;
+      ctl->rho_final_max = rho_next;
+      const bool exceed = P.stream_mode && (rho_next > P.rho_max);
+      if (al_a + 1 >= P.al_iter || exceed) {
+        ctl->mode = MODE_DONE;
+      } else {
+        ctl->a = al_a + 1;
+        ctl->k = 0;
+        ctl->mode = MODE_DUAL_NEWTON;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// final dual update + outputs (always runs once at the end of a forward solve)
+//   lam <- lam + rho c(xu), clamp ; rho <- 10 rho ; dyn_res = ||c+|| ; x,u -> fp32     AL_mpc.py:315-338
+// ------------------------------------------------------------------------------------------------
+template <class M, typename S, int WPB>
+__global__ void __launch_bounds__(WPB * 32)
+k_final_dual(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__ xu_g, S* __restrict__ lam_g,
+             S* __restrict__ rho_g, float* __restrict__ x_out, float* __restrict__ u_out, S* __restrict__ dyn_res_g,
+             int* __restrict__ info_g, Ctl* ctl) {
+  constexpr int NX = M::NX, NU = M::NU, NN = NX + NU;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int T = P.T;
+  const Layout<NX, NU> L(T);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int prob = blockIdx.x * WPB + warp;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    info_g[ALMPC_INFO_RHO_EXCEEDED] = (ctl->rho_final_max > P.rho_max) ? 1 : 0;
+  }
+  if (prob >= P.B) return;
+  S* sm = reinterpret_cast<S*>(smem_raw) + (size_t)warp * (L.N + L.neq);
+  S* xu = sm;
+  S* cres = sm + L.N;
+  const size_t pN = (size_t)prob * L.N;
+  for (int i = lane; i < L.N; i += 32) xu[i] = xu_g[pN + i];
+  __syncwarp();
+  for (int t = lane; t < T - 1; t += 32) {
+    S xs[NX], us[NU], xn[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xs[i] = xu[t * NN + i];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) us[i] = xu[t * NN + NX + i];
+    rk4_step<M, S, S>(xs, us, xn, P.dyn);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) cres[t * NX + i] = xu[(t + 1) * NN + i] - xn[i];
+  }
+  for (int i = lane; i < NX; i += 32) cres[(T - 1) * NX + i] = xu[i] - x0_g[(size_t)prob * NX + i];
+  __syncwarp();
+  const S rho = rho_g[prob];
+  S* lamp = lam_g + (size_t)prob * L.m;
+  const bool upd = !(P.flags & ALMPC_FLAG_SKIP_FINAL_DUAL);
+  S s2 = S(0);
+  for (int i = lane; i < L.neq; i += 32) {
+    S ci = cres[i];
+    if (upd) lamp[i] += rho * ci;
+    s2 += ci * ci;
+  }
+  for (int i = lane; i < L.nin; i += 32) {
+    int t = i / (2 * NU), s = i - t * 2 * NU;
+    S u = xu[t * NN + NX + (s < NU ? s : s - NU)];
+    S ci = (s < NU) ? (u - P.uhi[s]) : (P.ulo[s - NU] - u);
+    if (upd) lamp[L.neq + i] = fmax0(lamp[L.neq + i] + rho * ci);
+    S cp = fmax0(ci);
+    s2 += cp * cp;
+  }
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    if (upd) rho_g[prob] = next_rho(rho, P.rho_mult, P.rho_f32);
+    if (dyn_res_g) dyn_res_g[prob] = sqrt(s2);
+  }
+  if (x_out) {
+    for (int i = lane; i < T * NX; i += 32) {
+      int t = i / NX, j = i - t * NX;
+      x_out[(size_t)prob * T * NX + i] = (float)xu[t * NN + j];
+    }
+  }
+  if (u_out) {
+    for (int i = lane; i < T * NU; i += 32) {
+      int t = i / NU, j = i - t * NU;
+      u_out[(size_t)prob * T * NU + i] = (float)xu[t * NN + NX + j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// implicit backward: gbar = -H^{-1} grad ; grad_q = gbar ; grad_Q = gbar * xu     al_utils.py:578-615
+// ------------------------------------------------------------------------------------------------
+template <int NX, int NU, typename S, int WPB>
+__global__ void __launch_bounds__(WPB * 32)
+k_backward(int B, int T, const S* __restrict__ fac_g, const S* __restrict__ xu_g, const S* __restrict__ grad_g,
+           S* __restrict__ gQ_g, S* __restrict__ gq_g) {
+  constexpr int NN = NX + NU;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int prob = blockIdx.x * WPB + warp;
+  if (prob >= B) return;
+  const int N = T * NN;
+  S* sm = reinterpret_cast<S*>(smem_raw) + (size_t)warp * (N + NX * NN);
+  S* dv = sm;
+  S* Etmp = sm + N;
+  const size_t pN = (size_t)prob * N;
+  for (int i = lane; i < N; i += 32) dv[i] = grad_g[pN + i];
+  __syncwarp();
+  const S* fac = fac_g + (size_t)prob * factor_elems<NX, NU>(T);
+  forward_sweep_stored<NX, NU, S>(dv, Etmp, T, lane, fac);
+  backward_sweep<NX, NU, S>(dv, nullptr, Etmp, T, lane, fac);
+  for (int i = lane; i < N; i += 32) {
+    S g = -dv[i];
+    gq_g[pN + i] = g;
+    if (gQ_g) gQ_g[pN + i] = g * xu_g[pN + i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone dynamics (+ Jacobian): one thread per (row, tangent)
+// ------------------------------------------------------------------------------------------------
+template <class M, typename S>
+__global__ void k_dynamics(const KParams<S> P, int64_t R, const S* __restrict__ x, const S* __restrict__ u,
+                           S* __restrict__ xn_g, S* __restrict__ Jx, S* __restrict__ Ju) {
+  constexpr int NX = M::NX, NU = M::NU, NN = NX + NU;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (Jx == nullptr) {
+    if (gid >= R) return;
+    S xs[NX], us[NU], xn[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xs[i] = x[gid * NX + i];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) us[i] = u[gid * NU + i];
+    rk4_step<M, S, S>(xs, us, xn, P.dyn);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xn_g[gid * NX + i] = xn[i];
+    return;
+  }
+  if (gid >= R * NN) return;
+  const int64_t r = gid / NN;
+  const int j = (int)(gid - r * NN);
+  Dual<S> xd[NX], ud[NU], xn[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) xd[i] = Dual<S>(x[r * NX + i], (i == j) ? S(1) : S(0));
+#pragma unroll
+  for (int i = 0; i < NU; ++i) ud[i] = Dual<S>(u[r * NU + i], (NX + i == j) ? S(1) : S(0));
+  rk4_step<M, S, Dual<S>>(xd, ud, xn, P.dyn);
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    if (j < NX) Jx[(r * NX + i) * NX + j] = xn[i].d;
+    else Ju[(r * NX + i) * NU + (j - NX)] = xn[i].d;
+  }
+  if (j == 0 && xn_g) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xn_g[r * NX + i] = xn[i].v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FMA-pipe peak micro-benchmark (roofline denominator for bench.py)
+// ------------------------------------------------------------------------------------------------
+template <typename S>
+__global__ void k_fma_peak(int iters, S* sink) {
+  S a0 = S(1.0) + threadIdx.x * S(1e-6), a1 = a0 + S(0.1), a2 = a0 + S(0.2), a3 = a0 + S(0.3);
+  S a4 = a0 + S(0.4), a5 = a0 + S(0.5), a6 = a0 + S(0.6), a7 = a0 + S(0.7);
+  const S m = S(0.999999), c = S(1e-7);
+  for (int i = 0; i < iters; ++i) {
+    a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+    a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+  }
+  S s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == S(-1)) sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s", what);
+  return code;
+}
+static int cuda_err(cudaError_t e, const char* where) {
+  if (e == cudaSuccess) return 0;
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return (int)e;
+}
+
+template <typename S>
+static KParams<S> make_params(const almpc_desc* d) {
+  KParams<S> P;
+  for (int i = 0; i < ALMPC_MAX_PARAMS; ++i) P.dyn[i] = (S)d->dyn_params[i];
+  for (int i = 0; i < ALMPC_MAX_NU; ++i) { P.ulo[i] = (S)d->u_lower[i]; P.uhi[i] = (S)d->u_upper[i]; }
+  P.rho_mult = d->rho_mult;
+  P.rho_max = d->rho_max;
+  P.B = d->B; P.T = d->T; P.al_iter = d->al_iter; P.max_newton = d->max_newton;
+  P.stream_mode = d->stream_mode; P.rho_f32 = d->rho_f32; P.flags = d->flags;
+  return P;
+}
+
+static int check_desc(const almpc_desc* d) {
+  if (!d) return set_err(-1, "null descriptor");
+  if (d->dyn_id < 0 || d->dyn_id >= ALMPC_DYN_COUNT) return set_err(-2, "unknown dyn_id");
+  if (d->B < 0) return set_err(-3, "negative batch");
+  if (d->T < 2 || d->T > 64) return set_err(-4, "horizon T must be in [2,64]");
+  if (d->al_iter < 1 || d->al_iter > ALMPC_MAX_AL_ITER) return set_err(-5, "al_iter out of range");
+  if (d->max_newton < 1) return set_err(-6, "max_newton must be >= 1");
+  return 0;
+}
+
+constexpr int kWPB = 4;
+
+static size_t ws_ctl_bytes() { return 256; }
+static int n_blocks(int B) { return (B + kWPB - 1) / kWPB; }
+
+template <class M, typename S>
+static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* q, S* xu, S* lam, S* rho, S* factor,
+                        float* x_out, float* u_out, S* dyn_res_out, int32_t* status_out, int32_t* info_out,
+                        S* debug_out, void* workspace, cudaStream_t st) {
+  constexpr int NX = M::NX, NU = M::NU;
+  if (d->B == 0) return 0;
+  if (!x0 || !Qd || !q || !xu || !lam || !rho || !factor || !info_out || !workspace)
+    return set_err(-10, "null buffer");
+  const Layout<NX, NU> L(d->T);
+  const size_t smem = (size_t)kWPB * L.total * sizeof(S);
+  if (smem > 227 * 1024) return set_err(-11, "horizon too long for the shared-memory layout");
+  auto kern = k_newton_step<M, S, kWPB>;
+  auto kfin = k_final_dual<M, S, kWPB>;
+  cudaError_t e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(newton_step)");
+  e = cudaFuncSetAttribute(kfin, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(final_dual)");
+  const KParams<S> P = make_params<S>(d);
+  const int nb = n_blocks(d->B);
+  unsigned char* ws = (unsigned char*)workspace;
+  Ctl* ctl = (Ctl*)ws;
+  double* partials = (double*)(ws + ws_ctl_bytes());
+  S* merit = (S*)(ws + ws_ctl_bytes() + (size_t)nb * 4 * sizeof(double));
+  int32_t* status = status_out ? status_out : (int32_t*)(merit + d->B);
+  e = cudaMemsetAsync(ctl, 0, ws_ctl_bytes(), st);
+  if (e != cudaSuccess) return cuda_err(e, "cudaMemsetAsync(ctl)");
+  e = cudaMemsetAsync(info_out, 0, ALMPC_INFO_INTS * sizeof(int32_t), st);
+  if (e != cudaSuccess) return cuda_err(e, "cudaMemsetAsync(info)");
+  const int launches = d->al_iter * d->max_newton;
+  for (int i = 0; i < launches; ++i) {
+    kern<<<nb, kWPB * 32, smem, st>>>(P, x0, Qd, q, xu, lam, rho, factor, status, info_out, debug_out, ctl, partials,
+                                      merit);
+  }
+  const size_t smem_fin = (size_t)kWPB * (L.N + L.neq) * sizeof(S);
+  kfin<<<nb, kWPB * 32, smem_fin, st>>>(P, x0, xu, lam, rho, x_out, u_out, dyn_res_out, info_out, ctl);
+  return cuda_err(cudaGetLastError(), "almpc_forward launch");
+}
+
+template <int NX, int NU, typename S>
+static int backward_impl(const almpc_desc* d, const S* factor, const S* xu, const S* grad_xu, S* grad_Q, S* grad_q,
+                         cudaStream_t st) {
+  if (d->B == 0) return 0;
+  if (!factor || !xu || !grad_xu || !grad_q) return set_err(-10, "null buffer");
+  constexpr int NN = NX + NU;
+  const size_t smem = (size_t)kWPB * (d->T * NN + NX * NN) * sizeof(S);
+  auto kern = k_backward<NX, NU, S, kWPB>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(backward)");
+  }
+  kern<<<n_blocks(d->B), kWPB * 32, smem, st>>>(d->B, d->T, factor, xu, grad_xu, grad_Q, grad_q);
+  return cuda_err(cudaGetLastError(), "almpc_backward launch");
+}
+
+template <class M, typename S>
+static int dynamics_impl(const almpc_desc* d, int64_t R, const S* x, const S* u, S* xn, S* Jx, S* Ju, cudaStream_t st) {
+  if (R == 0) return 0;
+  if (!x || !u) return set_err(-10, "null buffer");
+  if ((Jx == nullptr) != (Ju == nullptr)) return set_err(-12, "Jx and Ju must both be given or both be NULL");
+  if (!Jx && !xn) return set_err(-10, "null output");
+  const KParams<S> P = make_params<S>(d);
+  const int64_t threads = Jx ? R * (M::NX + M::NU) : R;
+  const int bs = 128;
+  k_dynamics<M, S><<<(unsigned)((threads + bs - 1) / bs), bs, 0, st>>>(P, R, x, u, xn, Jx, Ju);
+  return cuda_err(cudaGetLastError(), "almpc_dynamics launch");
+}
+
+#define ALMPC_DISPATCH(dyn_id, CALL)                                    \
+  switch (dyn_id) {                                                     \
+    case ALMPC_DYN_PENDULUM: { using M = Pendulum; return CALL; }       \
+    case ALMPC_DYN_CARTPOLE1L: { using M = Cartpole1L; return CALL; }   \
+    case ALMPC_DYN_REX_QUADROTOR: { using M = RexQuad; return CALL; }   \
+    case ALMPC_DYN_FLYING_CARTPOLE: { using M = FlyingCartpole; return CALL; } \
+    case ALMPC_DYN_CARTPOLE2L: { using M = Cartpole2L; return CALL; }   \
+    default: return set_err(-2, "unknown dyn_id");                      \
+  }
+
+template <typename S>
+static int forward_any(const almpc_desc* d, const S* x0, const S* Qd, const S* q, S* xu, S* lam, S* rho, S* factor,
+                       float* x_out, float* u_out, S* dyn_res_out, int32_t* status_out, int32_t* info_out,
+                       S* debug_out, void* workspace, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  ALMPC_DISPATCH(d->dyn_id, (forward_impl<M, S>(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out,
+                                                status_out, info_out, debug_out, workspace, st)))
+}
+
+template <typename S>
+static int backward_any(const almpc_desc* d, const S* factor, const S* xu, const S* grad_xu, S* grad_Q, S* grad_q,
+                        void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  ALMPC_DISPATCH(d->dyn_id, (backward_impl<M::NX, M::NU, S>(d, factor, xu, grad_xu, grad_Q, grad_q, st)))
+}
+
+template <typename S>
+static int dynamics_any(const almpc_desc* d, int64_t R, const S* x, const S* u, S* xn, S* Jx, S* Ju, void* stream) {
+  if (!d) return set_err(-1, "null descriptor");
+  if (R < 0) return set_err(-3, "negative row count");
+  cudaStream_t st = (cudaStream_t)stream;
+  ALMPC_DISPATCH(d->dyn_id, (dynamics_impl<M, S>(d, R, x, u, xn, Jx, Ju, st)))
+}
+
+template <typename S>
+static int fma_peak(int blocks, int iters, S* sink, double* flops, void* stream) {
+  if (blocks <= 0 || iters <= 0 || !sink) return set_err(-1, "bad fma_peak arguments");
+  k_fma_peak<S><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+  if (flops) *flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+  return cuda_err(cudaGetLastError(), "almpc_fma_peak launch");
+}
+
+}  // namespace almpc
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using namespace almpc;
+
+extern "C" {
+
+int almpc_model_dims(int32_t dyn_id, int32_t* nx, int32_t* nu) {
+  int x, u;
+  switch (dyn_id) {
+    case ALMPC_DYN_PENDULUM: x = Pendulum::NX; u = Pendulum::NU; break;
+    case ALMPC_DYN_CARTPOLE1L: x = Cartpole1L::NX; u = Cartpole1L::NU; break;
+    case ALMPC_DYN_REX_QUADROTOR: x = RexQuad::NX; u = RexQuad::NU; break;
+    case ALMPC_DYN_FLYING_CARTPOLE: x = FlyingCartpole::NX; u = FlyingCartpole::NU; break;
+    case ALMPC_DYN_CARTPOLE2L: x = Cartpole2L::NX; u = Cartpole2L::NU; break;
+    default: return set_err(-2, "unknown dyn_id");
+  }
+  if (nx) *nx = x;
+  if (nu) *nu = u;
+  return 0;
+}
+
+size_t almpc_factor_elems(const almpc_desc* d) {
+  int32_t nx, nu;
+  if (!d || almpc_model_dims(d->dyn_id, &nx, &nu)) return 0;
+  const size_t n = (size_t)nx + nu;
+  return (size_t)d->T * n * n + (size_t)(d->T - 1) * nx * n;
+}
+
+size_t almpc_workspace_bytes(const almpc_desc* d) {
+  if (!d) return 0;
+  const size_t nb = (size_t)n_blocks(d->B);
+  return ws_ctl_bytes() + nb * 4 * sizeof(double) + (size_t)d->B * sizeof(double) + (size_t)d->B * sizeof(int32_t) + 64;
+}
+
+size_t almpc_debug_elems(const almpc_desc* d) {
+  int32_t nx, nu;
+  if (!d || almpc_model_dims(d->dyn_id, &nx, &nu)) return 0;
+  return 2 * (size_t)d->T * (nx + nu) + 24;
+}
+
+int almpc_forward_f64(const almpc_desc* d, const double* x0, const double* Qd, const double* q, double* xu,
+                      double* lam, double* rho, double* factor, float* x_out, float* u_out, double* dyn_res_out,
+                      int32_t* status_out, int32_t* info_out, double* debug_out, void* workspace, void* stream) {
+  return forward_any<double>(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out, status_out, info_out,
+                             debug_out, workspace, stream);
+}
+int almpc_forward_f32(const almpc_desc* d, const float* x0, const float* Qd, const float* q, float* xu, float* lam,
+                      float* rho, float* factor, float* x_out, float* u_out, float* dyn_res_out, int32_t* status_out,
+                      int32_t* info_out, float* debug_out, void* workspace, void* stream) {
+  return forward_any<float>(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out, status_out, info_out,
+                            debug_out, workspace, stream);
+}
+int almpc_backward_f64(const almpc_desc* d, const double* factor, const double* xu, const double* grad_xu,
+                       double* grad_Q, double* grad_q, void* stream) {
+  return backward_any<double>(d, factor, xu, grad_xu, grad_Q, grad_q, stream);
+}
+int almpc_backward_f32(const almpc_desc* d, const float* factor, const float* xu, const float* grad_xu,
+                       float* grad_Q, float* grad_q, void* stream) {
+  return backward_any<float>(d, factor, xu, grad_xu, grad_Q, grad_q, stream);
+}
+int almpc_dynamics_f64(const almpc_desc* d, int64_t R, const double* x, const double* u, double* xn, double* Jx,
+                       double* Ju, void* stream) {
+  return dynamics_any<double>(d, R, x, u, xn, Jx, Ju, stream);
+}
+int almpc_dynamics_f32(const almpc_desc* d, int64_t R, const float* x, const float* u, float* xn, float* Jx,
+                       float* Ju, void* stream) {
+  return dynamics_any<float>(d, R, x, u, xn, Jx, Ju, stream);
+}
+int almpc_fma_peak_f64(int32_t blocks, int32_t iters, double* sink, double* flops, void* stream) {
+  return fma_peak<double>(blocks, iters, sink, flops, stream);
+}
+int almpc_fma_peak_f32(int32_t blocks, int32_t iters, float* sink, double* flops, void* stream) {
+  return fma_peak<float>(blocks, iters, sink, flops, stream);
+}
+const char* almpc_last_error(void) { return g_err; }
+const char* almpc_version(void) { return "almpc 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+"""Fused AL-MPC solve as one torch.autograd.Function over the C ABI.
+
+``ALSolve.apply`` replaces the whole loop of ``MPC.al_solve`` / ``al_solve_stream``
+(qpth/AL_mpc.py:260-423): every ``NewtonAL.apply`` (qpth/al_utils.py:451-576), the dual / penalty
+update (AL_mpc.py:315-325) and the fp32 output cast (AL_mpc.py:337-338) happen inside
+``almpc_forward_*``; the backward is ``NewtonAL.backward`` (al_utils.py:578-615) via
+``almpc_backward_*``.  No host synchronisation happens here.
+"""
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from .dynamics import NativeDynamics
+
+
+@dataclass
+class SolveConfig:
+    dyn: NativeDynamics
+    T: int
+    u_lower: list
+    u_upper: list
+    al_iter: int = 2
+    max_newton: int = 4
+    stream_mode: bool = False
+    rho_f32: bool = False
+    rho_mult: float = 10.0
+    rho_max: float = 1e8
+    skip_final_dual: bool = False
+    debug: bool = False
+
+    def desc(self, B):
+        d = _lib.Desc()
+        d.B, d.T, d.dyn_id = B, self.T, self.dyn.dyn_id
+        d.al_iter, d.max_newton = self.al_iter, self.max_newton
+        d.stream_mode, d.rho_f32 = int(self.stream_mode), int(self.rho_f32)
+        d.flags = _lib.FLAG_SKIP_FINAL_DUAL if self.skip_final_dual else 0
+        d.rho_mult, d.rho_max = self.rho_mult, self.rho_max
+        for i, v in enumerate(self.dyn.param_block()):
+            d.dyn_params[i] = v
+        if len(self.u_lower) != self.dyn.nu or len(self.u_upper) != self.dyn.nu:
+            raise _lib.AlmpcError("u_lower / u_upper must have n_ctrl entries")
+        for i in range(self.dyn.nu):
+            d.u_lower[i] = float(self.u_lower[i])
+            d.u_upper[i] = float(self.u_upper[i])
+        return d
+
+
+def raw_forward(cfg: SolveConfig, x0, Qd, q, xu, lam, rho):
+    """In-place forward on caller-owned buffers (xu, lam, rho are updated).  Returns a dict of the
+    freshly allocated outputs.  All tensors: CUDA, contiguous, solver dtype."""
+    lib = _lib.load()
+    for t, name in ((x0, "x0"), (Qd, "Qd"), (q, "q"), (xu, "xu"), (lam, "lam"), (rho, "rho")):
+        _lib.require_cuda(t, name)
+        if not t.is_contiguous():
+            raise _lib.AlmpcError(f"{name} must be contiguous")
+        if t.dtype != xu.dtype:
+            raise _lib.AlmpcError(f"{name} has dtype {t.dtype}, expected {xu.dtype}")
+    B, T, n = xu.shape
+    nx, nu = cfg.dyn.nx, cfg.dyn.nu
+    if T != cfg.T or n != nx + nu:
+        raise _lib.AlmpcError(f"xu has shape {tuple(xu.shape)}, expected [B,{cfg.T},{nx + nu}]")
+    m = T * nx + 2 * T * nu
+    if x0.shape != (B, nx) or Qd.shape != (B, T, n) or q.shape != (B, T, n) or lam.shape != (B, m) or rho.numel() != B:
+        raise _lib.AlmpcError("inconsistent AL-MPC buffer shapes")
+    dev, dt = xu.device, xu.dtype
+    d = cfg.desc(B)
+    out = dict(
+        factor=torch.empty(B, lib.almpc_factor_elems(ctypes.byref(d)), dtype=dt, device=dev),
+        x=torch.empty(B, T, nx, dtype=torch.float32, device=dev),
+        u=torch.empty(B, T, nu, dtype=torch.float32, device=dev),
+        dyn_res=torch.empty(B, dtype=dt, device=dev),
+        status=torch.empty(B, dtype=torch.int32, device=dev),
+        info=torch.empty(_lib.INFO_INTS, dtype=torch.int32, device=dev),
+        debug=(torch.zeros(B, lib.almpc_debug_elems(ctypes.byref(d)), dtype=dt, device=dev) if cfg.debug else None),
+    )
+    ws = torch.empty(lib.almpc_workspace_bytes(ctypes.byref(d)), dtype=torch.uint8, device=dev)
+    if B > 0:
+        with torch.cuda.device(dev):
+            rc = getattr(lib, "almpc_forward_" + _lib.suffix(dt))(
+                ctypes.byref(d), _lib.ptr(x0), _lib.ptr(Qd), _lib.ptr(q), _lib.ptr(xu), _lib.ptr(lam), _lib.ptr(rho),
+                _lib.ptr(out["factor"]), _lib.ptr(out["x"]), _lib.ptr(out["u"]), _lib.ptr(out["dyn_res"]),
+                _lib.ptr(out["status"]), _lib.ptr(out["info"]), _lib.ptr(out["debug"]), _lib.ptr(ws), _lib.stream_ptr())
+        _lib.check(rc, "almpc_forward")
+    else:
+        out["info"].zero_()
+    return out
+
+
+def raw_backward(cfg: SolveConfig, factor, xu, grad_xu, need_Q=True):
+    lib = _lib.load()
+    _lib.require_cuda(grad_xu, "grad_xu")
+    B = xu.shape[0]
+    d = cfg.desc(B)
+    grad_xu = grad_xu.to(xu.dtype).contiguous()
+    gq = torch.empty_like(xu)
+    gQ = torch.empty_like(xu) if need_Q else None
+    if B > 0:
+        with torch.cuda.device(xu.device):
+            rc = getattr(lib, "almpc_backward_" + _lib.suffix(xu.dtype))(
+                ctypes.byref(d), _lib.ptr(factor), _lib.ptr(xu), _lib.ptr(grad_xu), _lib.ptr(gQ), _lib.ptr(gq),
+                _lib.stream_ptr())
+        _lib.check(rc, "almpc_backward")
+    return gQ, gq
+
+
+class ALSolve(torch.autograd.Function):
+    """(Qd, q, x0, xu_init, lam, rho, cfg) -> (x f32, u f32, xu, lam_new, rho_new, dyn_res, status, info, debug).
+    Gradients flow to Qd and q only (al_utils.py:599-615)."""
+
+    @staticmethod
+    def forward(ctx, Qd, q, x0, xu_init, lam, rho, cfg):
+        xu = xu_init.detach().clone().contiguous()
+        lam = lam.detach().clone().contiguous()
+        rho = rho.detach().clone().contiguous()
+        out = raw_forward(cfg, x0.detach().contiguous(), Qd.detach().contiguous(), q.detach().contiguous(), xu, lam, rho)
+        ctx.cfg = cfg
+        ctx.save_for_backward(out["factor"], xu)
+        dbg = out["debug"] if out["debug"] is not None else torch.empty(0, device=xu.device)
+        ctx.mark_non_differentiable(xu, lam, rho, out["dyn_res"], out["status"], out["info"], dbg)
+        return out["x"], out["u"], xu, lam, rho, out["dyn_res"], out["status"], out["info"], dbg
+
+    @staticmethod
+    def backward(ctx, gx, gu, *unused):
+        factor, xu = ctx.saved_tensors
+        nx = ctx.cfg.dyn.nx
+        if gx is None:
+            gx = torch.zeros(xu.shape[0], xu.shape[1], nx, dtype=xu.dtype, device=xu.device)
+        if gu is None:
+            gu = torch.zeros(xu.shape[0], xu.shape[1], xu.shape[2] - nx, dtype=xu.dtype, device=xu.device)
+        grad_xu = torch.cat([gx.to(xu.dtype), gu.to(xu.dtype)], dim=2)
+        need_Q = ctx.needs_input_grad[0]
+        gQ, gq = raw_backward(ctx.cfg, factor, xu, grad_xu, need_Q=need_Q)
+        return gQ, (gq if ctx.needs_input_grad[1] else None), None, None, None, None, None

@@ -1,0 +1,134 @@
+/*
+ * libalmpc — C ABI of the B200-native batched augmented-Lagrangian MPC solver.
+ *
+ * This is the drop-in boundary for the reference's AL-MPC hot path.  Every entry point takes plain
+ * device pointers + sizes + a CUDA stream; there are no torch types, no allocations and no host
+ * synchronisation inside the library (all calls are CUDA-graph capturable).  Return value: 0 = ok,
+ * <0 = bad argument, >0 = cudaError_t of the failing runtime call; almpc_last_error() gives text.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference repo):
+ *
+ *   almpc_forward_{f64,f32}   qpth/AL_mpc.py:260-339 (MPC.al_solve) and :342-423 (al_solve_stream):
+ *                             the whole al_iter x (<=4 Newton steps) loop, i.e. every
+ *                             al_utils.NewtonAL.apply call (qpth/al_utils.py:451-576) with its
+ *                             merit_grad_hessian (:80-123), cholesky/cholesky_solve (:510-515),
+ *                             line_search_newton (:618-642) and the dual / penalty update
+ *                             (AL_mpc.py:315-325), plus the fp32 output cast (AL_mpc.py:337-338).
+ *   almpc_backward_{f64,f32}  al_utils.NewtonAL.backward (qpth/al_utils.py:578-615).
+ *   almpc_dynamics_{f64,f32}  the dx / dx_jac plug-ins: RexQuadrotor_dynamics(_jac).forward
+ *                             (deqmpc/rex_quadrotor.py:109-110,136-144), FlyingCartpole_dynamics(_jac)
+ *                             (deqmpc/flying_cartpole2d.py:93-94,139-148) and the native
+ *                             pkg.dynamics / pkg.derivatives extensions
+ *                             (deqmpc/my_envs/<pkg>/src/dynamics.cpp:13-54).
+ *
+ * Layouts (all contiguous, row-major, S = double or float):
+ *   n = nx+nu, N = T*n, neq = T*nx, nineq = 2*T*nu, m = neq+nineq
+ *   x0[B][nx]   Qd[B][T][n]   q[B][T][n]   xu[B][T][n] (x_t then u_t per stage)
+ *   lam[B][m]   eq rows first: (T-1) dynamics blocks of nx, then the x_0 - x0 block (al_utils.py:224);
+ *               then per stage t: nu upper-bound rows, nu lower-bound rows (al_utils.py:293)
+ *   rho[B]      penalty per problem, stored in S
+ *   factor[B][almpc_factor_elems]  block-tridiagonal Cholesky factor of the last Newton Hessian:
+ *               T lower-triangular blocks L_tt[n][n] (diagonal holds 1/L_ii) followed by
+ *               (T-1) sub-diagonal blocks E_t[nx][n] (rows = x_{t+1}, the only non-zero rows)
+ */
+#ifndef ALMPC_H_
+#define ALMPC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* native dynamics models (device functors fused into the solver) */
+enum almpc_dyn_id {
+  ALMPC_DYN_PENDULUM = 0,        /* my_envs/pendulum1l   nx=2  nu=1 */
+  ALMPC_DYN_CARTPOLE1L = 1,      /* my_envs/cartpole1l   nx=4  nu=1 */
+  ALMPC_DYN_REX_QUADROTOR = 2,   /* rex_quadrotor.py     nx=12 nu=4 */
+  ALMPC_DYN_FLYING_CARTPOLE = 3, /* flying_cartpole2d.py nx=14 nu=4 */
+  ALMPC_DYN_CARTPOLE2L = 4,      /* my_envs/cartpole2l   nx=6  nu=1 */
+  ALMPC_DYN_COUNT = 5
+};
+
+#define ALMPC_MAX_PARAMS 48
+#define ALMPC_MAX_NU 8
+#define ALMPC_MAX_AL_ITER 32
+#define ALMPC_N_LS 20 /* line-search candidates 2^-k, k=0..19 (al_utils.py:619) */
+
+/* desc.flags: leave lam/rho untouched at the end (NewtonAL-only use: al_utils.py:449 has no dual update) */
+#define ALMPC_FLAG_SKIP_FINAL_DUAL 1
+
+typedef struct almpc_desc {
+  int32_t B;          /* problems in the batch */
+  int32_t T;          /* horizon */
+  int32_t dyn_id;     /* enum almpc_dyn_id */
+  int32_t al_iter;    /* AL iterations (MPC.al_iter, AL_mpc.py:290) */
+  int32_t max_newton; /* Newton steps per AL iteration, reference value 4 (al_utils.py:485) */
+  int32_t stream_mode;/* 1 = al_solve_stream semantics: stop when max(rho) > rho_max (AL_mpc.py:412) */
+  int32_t rho_f32;    /* 1 = round rho to fp32 after each x10 (rho_prev is an fp32 tensor, AL_mpc.py:573) */
+  int32_t flags;      /* ALMPC_FLAG_* */
+  double rho_mult;    /* 10 (AL_mpc.py:325) */
+  double rho_max;     /* 1e8 (AL_mpc.py:193) */
+  double dyn_params[ALMPC_MAX_PARAMS]; /* model parameters, layout in DESIGN.md / dynamics.py */
+  double u_lower[ALMPC_MAX_NU];
+  double u_upper[ALMPC_MAX_NU];
+} almpc_desc;
+
+/* info_out layout (int32, device memory, ALMPC_INFO_INTS entries) */
+#define ALMPC_INFO_AL_DONE 0       /* AL iterations executed */
+#define ALMPC_INFO_RHO_EXCEEDED 1  /* final max(rho) > rho_max (stream-mode status flag, AL_mpc.py:420) */
+#define ALMPC_INFO_TOTAL_NEWTON 2  /* Newton steps executed in total */
+#define ALMPC_INFO_NEWTON0 4       /* [4 + a] = Newton steps of AL iteration a */
+#define ALMPC_INFO_INTS (4 + ALMPC_MAX_AL_ITER)
+
+/* per-problem status bits written to status_out */
+#define ALMPC_STATUS_FINITE 1   /* iterate stayed finite (al_utils.py:545-549) */
+#define ALMPC_STATUS_CHOL_OK 2  /* every pivot of every factorisation was positive */
+
+int almpc_model_dims(int32_t dyn_id, int32_t* nx, int32_t* nu);
+size_t almpc_factor_elems(const almpc_desc* d);          /* scalars per problem in `factor` */
+size_t almpc_workspace_bytes(const almpc_desc* d);       /* device scratch the caller must provide */
+size_t almpc_debug_elems(const almpc_desc* d);           /* scalars per problem in `debug_out` */
+
+/* Forward solve.  In/out: xu (warm start -> solution), lam, rho (dual warm start -> updated duals).
+ * Out: factor (for backward), x_out/u_out fp32 (may be NULL), dyn_res_out[B] = ||c+|| per problem
+ * (may be NULL), status_out[B] (may be NULL), info_out[ALMPC_INFO_INTS] (device),
+ * debug_out (may be NULL): per problem [grad N | direction N | merits 20 | argmin | accept | merit_in]
+ * of the last executed Newton step. */
+int almpc_forward_f64(const almpc_desc* d, const double* x0, const double* Qd, const double* q,
+                      double* xu, double* lam, double* rho, double* factor, float* x_out, float* u_out,
+                      double* dyn_res_out, int32_t* status_out, int32_t* info_out, double* debug_out,
+                      void* workspace, void* stream);
+int almpc_forward_f32(const almpc_desc* d, const float* x0, const float* Qd, const float* q,
+                      float* xu, float* lam, float* rho, float* factor, float* x_out, float* u_out,
+                      float* dyn_res_out, int32_t* status_out, int32_t* info_out, float* debug_out,
+                      void* workspace, void* stream);
+
+/* Implicit backward: gbar = -H^{-1} grad_xu with the cached factor; grad_q = gbar,
+ * grad_Q = gbar * xu (grad_Q may be NULL when Q needs no gradient). */
+int almpc_backward_f64(const almpc_desc* d, const double* factor, const double* xu, const double* grad_xu,
+                       double* grad_Q, double* grad_q, void* stream);
+int almpc_backward_f32(const almpc_desc* d, const float* factor, const float* xu, const float* grad_xu,
+                       float* grad_Q, float* grad_q, void* stream);
+
+/* Stand-alone dynamics: xn[R][nx] = f(x[R][nx], u[R][nu]); optional Jx[R][nx][nx], Ju[R][nx][nu]
+ * (Jx[r][i][j] = d xn_i / d x_j, al_utils.py:237-248).  Uses d->dyn_id / d->dyn_params only. */
+int almpc_dynamics_f64(const almpc_desc* d, int64_t R, const double* x, const double* u, double* xn,
+                       double* Jx, double* Ju, void* stream);
+int almpc_dynamics_f32(const almpc_desc* d, int64_t R, const float* x, const float* u, float* xn,
+                       float* Jx, float* Ju, void* stream);
+
+/* FMA-pipe micro-benchmark used by bench.py to measure the FP64 / FP32 roofline denominators:
+ * launches `blocks` x 256 threads, each doing `iters` x 8 independent FMAs; returns via *flops the
+ * number of floating-point operations performed (2 per FMA). */
+int almpc_fma_peak_f64(int32_t blocks, int32_t iters, double* sink, double* flops, void* stream);
+int almpc_fma_peak_f32(int32_t blocks, int32_t iters, float* sink, double* flops, void* stream);
+
+const char* almpc_last_error(void);
+const char* almpc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALMPC_H_ */

@@ -162,7 +162,8 @@ def line_search(pb, d, xu, x0, Qd, q, lam, rho, merit_in):
     return acc * chosen + (1 - acc) * xu, best.values, best.indices, accept, vals
 
 
-def newton_al(pb: Problem, xu, x0, lam, rho, Qd, q, trace: Optional[SolveTrace] = None, keep_H=False):
+def newton_al(pb: Problem, xu, x0, lam, rho, Qd, q, trace: Optional[SolveTrace] = None, keep_H=False,
+              force_steps: Optional[int] = None):
     """NewtonAL.forward, al_utils.py:451-576.  Returns (xu, status[B], saved) where saved holds the
     factor of the LAST iteration's pre-step Hessian for the implicit backward."""
     B = xu.shape[0]
@@ -196,7 +197,12 @@ def newton_al(pb: Problem, xu, x0, lam, rho, Qd, q, trace: Optional[SolveTrace] 
                           H.clone() if keep_H else None)
             )
         xu = xu1
-        if abs(res_old - res_new) / res_new < 1e-3 or res_new < 1e-3:
+        if force_steps is not None:
+            # test hook: replay the step count another (larger) batch realised — the reference's stop
+            # rule is a whole-batch statistic (al_utils.py:486,552), so a sub-batch cannot reproduce it
+            if nstep >= force_steps:
+                break
+        elif abs(res_old - res_new) / res_new < 1e-3 or res_new < 1e-3:
             break
         res_old = res_new
         m_cur = m_new
@@ -239,6 +245,7 @@ class OracleMPC:
         self.rho_prev = 1.0
         self.saved = None
         self.trace = None
+        self.force_steps = None  # optional list: Newton steps per AL iteration (see newton_al)
 
     def reinitialize(self, x, mask=None):  # AL_mpc.py:569-579
         self.x_init = self.u_init = None
@@ -264,9 +271,10 @@ class OracleMPC:
         rho = self.rho_prev
         xu = torch.cat([x, u], 2)
         exceeded = False
-        for _ in range(self.al_iter):
+        for a in range(self.al_iter):
             xu = xu.detach().clone()
-            xu, status, saved = newton_al(pb, xu, x0, lam, rho, Qd, q, trace, keep_H)
+            force = None if self.force_steps is None else self.force_steps[a]
+            xu, status, saved = newton_al(pb, xu, x0, lam, rho, Qd, q, trace, keep_H, force)
             c, c_plus = residuals(pb, xu, x0)
             lam = lam + rho * c
             lam = torch.cat([lam[:, : pb.neq], lam[:, pb.neq :].clamp(min=0)], 1)

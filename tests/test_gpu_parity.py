@@ -1,0 +1,326 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, reached through the product API / C ABI,
+against (1) golden outputs of the unmodified reference, (2) the CPU oracle on seeded inputs, and
+(3) size-independent properties at BASELINE.json's full batch size.
+
+Tolerances (north_star): 1e-6 relative in fp64, 1e-4 in fp32 *where the problem is well enough
+conditioned for two correct implementations to agree that closely*; cond(H) ~ rho/R, so the fp64
+budget is widened with the largest penalty used in the call exactly as for the oracle-vs-reference
+check (tests/test_oracle_golden.py::tolerances), and fp32 is only asserted in the rho <= 1e2 regime
+(SURVEY.md A.5)."""
+import types
+
+import pytest
+import torch
+
+from golden_util import Golden, list_golden, max_rel_err_rows, rel_err
+
+pytestmark = pytest.mark.gpu
+
+cuda = torch.cuda.is_available()
+if cuda:
+    import deq_mpc_corl_b200 as pkg
+    from deq_mpc_corl_b200 import _lib
+    from deq_mpc_corl_b200.al_mpc import MPC
+    from deq_mpc_corl_b200.al_utils import QuadCost
+    from deq_mpc_corl_b200.dynamics import make as make_dyn
+    from deq_mpc_corl_b200.problems import MODEL_SPECS, make_inputs, tracking_cost
+
+DEV = "cuda:0"
+
+
+def tolerances(rho_out_max, dtype):
+    if dtype != torch.float64:
+        return dict(xu=2e-3, lam=1e-2, grad=1e-2)
+    rho_used = rho_out_max / 10.0
+    return dict(xu=max(1e-6, 1e-14 * rho_used), lam=max(1e-6, 1e-12 * rho_used), grad=max(1e-6, 1e-11 * rho_used))
+
+
+# --------------------------------------------------------------------------------------------------
+# dynamics functors vs the oracle models
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model", ["pendulum", "cartpole1l", "cartpole2l", "rex_quadrotor", "flying_cartpole"])
+def test_dynamics_matches_oracle(model):
+    from oracle.problem_gen import make_oracle_model
+
+    om = make_oracle_model(model)
+    dyn = make_dyn(model, dt=om.dt)
+    g = torch.Generator().manual_seed(5)
+    R = 257
+    x = (torch.rand(R, om.nx, generator=g, dtype=torch.float64) * 2 - 1) * 0.8
+    lo, hi = torch.tensor(om.u_lower), torch.tensor(om.u_upper)
+    u = lo + (hi - lo) * torch.rand(R, om.nu, generator=g, dtype=torch.float64)
+    xn_ref, (jx_ref, ju_ref) = om.step_jac(x, u)
+    xn, (jx, ju) = dyn.jacobian(x.to(DEV), u.to(DEV))
+    xn2 = dyn(x.to(DEV), u.to(DEV))
+    assert torch.equal(xn, xn2)
+    assert rel_err(xn.cpu(), xn_ref) < 1e-13
+    assert rel_err(jx.cpu(), jx_ref) < 1e-12
+    assert rel_err(ju.cpu(), ju_ref) < 1e-12
+    # fp32 functor
+    xn32 = dyn(x.float().to(DEV), u.float().to(DEV))
+    assert rel_err(xn32.cpu(), xn_ref) < 5e-6
+
+
+def test_cartpole2l_known_answer_traj():
+    """my_envs/traj.npz (the only on-disk fixture of the reference): X[k+1] = f(X[k], U[k]) at dt=0.03
+    to 1e-6.  A copy of the arrays lives in tests/golden/cartpole2l_traj.npz."""
+    import numpy as np
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "cartpole2l_traj.npz"))
+    X, U = torch.from_numpy(z["X_np"]), torch.from_numpy(z["U_np"])
+    dyn = make_dyn("cartpole2l", dt=0.03)
+    xn = dyn(X[:-1].contiguous().to(DEV), U.contiguous().to(DEV)).cpu()
+    assert (xn - X[1:]).abs().max().item() < 2e-6
+
+
+# --------------------------------------------------------------------------------------------------
+# full solves vs golden outputs of the unmodified reference
+# --------------------------------------------------------------------------------------------------
+def make_ctrl(gold):
+    spec = MODEL_SPECS[gold.model]
+    dyn = make_dyn(gold.model, dt=spec["dt"])
+    ctrl = MPC(spec["nx"], spec["nu"], gold.T, u_lower=gold.t("u_lower"), u_upper=gold.t("u_upper"),
+               n_batch=gold.B, dtype=gold.dtype)
+    return ctrl, dyn, spec
+
+
+@pytest.mark.parametrize("name", list_golden() if cuda else [])
+def test_solve_matches_reference_golden(name):
+    gold = Golden(name)
+    ctrl, dyn, spec = make_ctrl(gold)
+    nx = spec["nx"]
+    x0 = gold.t("x0").to(DEV)
+    Qd1 = gold.t("Qd").to(gold.dtype)
+    Qfull0 = torch.diag(Qd1).repeat(gold.B, gold.T, 1, 1).to(DEV)
+    for ci in range(gold.n_calls):
+        c = gold.call(ci)
+        if ci == 0:
+            ctrl.reinitialize(c["x_ref"].to(DEV))
+        if gold.stream_after == ci:
+            ctrl.warm_start_initialize(ctrl.x_init, ctrl.u_init, types.SimpleNamespace(rho_init_max=gold.rho_init_max))
+        # call-level parity: start from the reference's own state
+        assert bool(c["warm"]) == ctrl.warm_starting
+        ctrl.x_init = c["xu_init"][..., :nx].to(DEV)
+        ctrl.u_init = c["xu_init"][..., nx:].to(DEV)
+        ctrl.lamda_prev = c["lam_in"].to(DEV)
+        ctrl.rho_prev = c["rho_in"].to(DEV)
+        ctrl.al_iter = int(c["al_iter"])
+        Qleaf = Qfull0.clone().requires_grad_(True)
+        q = c["q"].to(DEV).requires_grad_(True)
+        x, u, status = ctrl(x0, QuadCost(Qleaf, q, None), dyn, dyn)
+        Qg, qg = torch.autograd.grad((x, u), (Qleaf, q), (c["gx"].to(DEV), c["gu"].to(DEV)))
+        Qg = Qg.diagonal(dim1=-2, dim2=-1)
+        tol = tolerances(float(c["rho_out"].double().max()), gold.dtype)
+        assert ctrl.newton_steps() == c["nsteps"].tolist(), f"{name} call {ci}: Newton-step counts"
+        assert bool(status) == bool(c["status"])
+        assert (ctrl.last_status.cpu() == 3).all()
+        assert torch.equal(ctrl.rho_prev.cpu().double(), c["rho_out"].double())
+        assert ctrl.rho_prev.dtype == c["rho_out"].dtype
+        e_xu = rel_err(ctrl.last_xu.cpu(), c["xu64"])
+        e_lam = rel_err(ctrl.lamda_prev.cpu(), c["lam_out"])
+        e_q = rel_err(qg.cpu(), c["q_grad"])
+        e_Q = rel_err(Qg.cpu(), c["Q_grad"])
+        print(f"{name} c{ci}: xu {e_xu:.1e} lam {e_lam:.1e} q_grad {e_q:.1e} Q_grad {e_Q:.1e} (tol {tol})")
+        assert e_xu < tol["xu"], f"{name} call {ci}: xu {e_xu}"
+        assert e_lam < tol["lam"], f"{name} call {ci}: lam {e_lam}"
+        assert e_q < tol["grad"] and e_Q < tol["grad"], f"{name} call {ci}: grads {e_q} {e_Q}"
+        assert rel_err(x.detach().cpu(), c["x"]) < max(tol["xu"], 1e-6)
+        assert rel_err(u.detach().cpu(), c["u"]) < max(tol["xu"] * 10, 1e-6)
+        assert x.dtype == torch.float32 and u.dtype == torch.float32
+        assert rel_err(ctrl.dyn_res_prev.cpu(), c["dyn_res"]) < max(tol["lam"] * 100, 1e-5)
+
+
+@pytest.mark.parametrize("name", ["quad_T5_f64_cold", "pendulum_T5_f64_chain", "flying_T10_f64_cold", "cartpole1l_T5_f64_stream"] if cuda else [])
+def test_first_newton_step_trace(name):
+    """Step-level parity: gradient, Newton direction, the 20 merits, argmin and accept of the first
+    Newton step against the reference's own intermediate values."""
+    from deq_mpc_corl_b200.solver import SolveConfig, raw_forward
+
+    gold = Golden(name)
+    c = gold.call(0)
+    spec = MODEL_SPECS[gold.model]
+    dyn = make_dyn(gold.model, dt=spec["dt"])
+    cfg = SolveConfig(dyn=dyn, T=gold.T, u_lower=gold.t("u_lower").tolist(), u_upper=gold.t("u_upper").tolist(),
+                      al_iter=1, max_newton=1, debug=True, skip_final_dual=True)
+    dt = gold.dtype
+    B, T, n = gold.B, gold.T, spec["nx"] + spec["nu"]
+    xu = c["xu_init"].to(dt).to(DEV).contiguous()
+    Qd = gold.t("Qd").to(dt).expand(B, T, n).contiguous().to(DEV)
+    out = raw_forward(cfg, gold.t("x0").to(dt).to(DEV), Qd, c["q"].to(dt).to(DEV).contiguous(), xu,
+                      c["lam_in"].to(dt).to(DEV).contiguous(), c["rho_in"].to(dt).reshape(-1).to(DEV).contiguous())
+    dbg = out["debug"].cpu()
+    N = T * n
+    assert rel_err(dbg[:, :N], c["step_grad"][0]) < 1e-12
+    assert max_rel_err_rows(dbg[:, N:2 * N], c["step_dir"][0].reshape(B, -1)) < 1e-9
+    assert rel_err(dbg[:, 2 * N:2 * N + 20].T, c["step_merits"][0]) < 1e-12
+    assert torch.equal(dbg[:, 2 * N + 20].long(), c["step_idx"][0])
+    assert torch.equal(dbg[:, 2 * N + 21].bool(), c["step_accept"][0])
+    assert rel_err(dbg[:, 2 * N + 22], c["step_merit_in"][0]) < 1e-12
+
+
+# --------------------------------------------------------------------------------------------------
+# CUDA vs the CPU oracle on seeded synthetic batches
+# --------------------------------------------------------------------------------------------------
+def solve_both(model, T, B, seed, dtype, al_iter=2):
+    from oracle import almpc_oracle as orc
+    from oracle.problem_gen import make_oracle_model
+
+    inp = make_inputs(model, T, B, seed)
+    spec = MODEL_SPECS[model]
+    Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"], dtype)
+    # oracle
+    om = make_oracle_model(model)
+    ompc = orc.OracleMPC(om, T, inp["u_lower"], inp["u_upper"], B, dtype=dtype, al_iter=al_iter)
+    ompc.reinitialize(inp["x_ref"])
+    ompc.x_init, ompc.u_init = inp["x_ref"].clone(), inp["u_ref"].clone()
+    tr = orc.SolveTrace()
+    xo, uo, _, xuo = ompc.solve(inp["x0"], Qd, q, trace=tr)
+    g = torch.Generator().manual_seed(seed + 1)
+    gx, gu = torch.randn(xo.shape, generator=g), torch.randn(uo.shape, generator=g)
+    Qg_o, qg_o = ompc.backward(gx, gu)
+    # CUDA
+    dyn = make_dyn(model, dt=spec["dt"])
+    ctrl = MPC(spec["nx"], spec["nu"], T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B, dtype=dtype)
+    ctrl.reinitialize(inp["x_ref"].to(DEV))
+    ctrl.x_init, ctrl.u_init = inp["x_ref"].to(DEV), inp["u_ref"].to(DEV)
+    ctrl.al_iter = al_iter
+    Qdl = Qd.to(DEV).requires_grad_(True)
+    ql = q.to(DEV).requires_grad_(True)
+    x, u, _ = ctrl(inp["x0"].to(DEV), QuadCost(Qdl, ql, None), dyn, dyn)
+    Qg, qg = torch.autograd.grad((x, u), (Qdl, ql), (gx.to(DEV), gu.to(DEV)))
+    return dict(o=dict(xu=xuo, lam=ompc.lamda_prev, Qg=Qg_o, qg=qg_o, steps=tr.newton_steps),
+                c=dict(xu=ctrl.last_xu.cpu(), lam=ctrl.lamda_prev.cpu(), Qg=Qg.cpu(), qg=qg.cpu(), steps=ctrl.newton_steps()))
+
+
+@pytest.mark.parametrize("model,T,B", [("rex_quadrotor", 5, 192), ("pendulum", 5, 200), ("cartpole1l", 5, 256),
+                                       ("cartpole1l", 10, 64), ("pendulum", 20, 33), ("flying_cartpole", 10, 48),
+                                       ("rex_quadrotor", 10, 32), ("cartpole2l", 5, 40)])
+def test_cuda_matches_oracle_f64(model, T, B):
+    r = solve_both(model, T, B, 4242 + T, torch.float64)
+    assert r["c"]["steps"] == r["o"]["steps"]
+    assert rel_err(r["c"]["xu"], r["o"]["xu"]) < 1e-6
+    assert max_rel_err_rows(r["c"]["xu"], r["o"]["xu"]) < 1e-5
+    assert rel_err(r["c"]["lam"], r["o"]["lam"]) < 1e-6
+    assert rel_err(r["c"]["qg"], r["o"]["qg"]) < 1e-6
+    assert rel_err(r["c"]["Qg"], r["o"]["Qg"]) < 1e-6
+
+
+@pytest.mark.parametrize("model,T,B", [("rex_quadrotor", 5, 128), ("cartpole1l", 5, 128)])
+def test_cuda_matches_oracle_f32(model, T, B):
+    """fp32 solver vs the fp32 oracle: both sit on the fp32 noise floor of the algorithm
+    (SURVEY.md §7.3 item 2), so the budget is the measured oracle-vs-reference fp32 gap, not 1e-4."""
+    r = solve_both(model, T, B, 777, torch.float32)
+    assert abs(sum(r["c"]["steps"]) - sum(r["o"]["steps"])) <= 1
+    assert rel_err(r["c"]["xu"], r["o"]["xu"]) < 5e-3
+
+
+# --------------------------------------------------------------------------------------------------
+# edge cases + full-size properties
+# --------------------------------------------------------------------------------------------------
+def test_empty_and_ragged_batches():
+    spec = MODEL_SPECS["rex_quadrotor"]
+    dyn = make_dyn("rex_quadrotor")
+    for B in (0, 1, 3, 5):  # not a multiple of the 4 problems per CTA
+        inp = make_inputs("rex_quadrotor", 5, max(B, 1), 11)
+        inp = {k: (v[:B] if v.dim() > 1 else v) for k, v in inp.items()}
+        Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"])
+        ctrl = MPC(12, 4, 5, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B)
+        ctrl.reinitialize(inp["x_ref"].to(DEV))
+        ctrl.x_init, ctrl.u_init = inp["x_ref"].to(DEV), inp["u_ref"].to(DEV)
+        x, u, st = ctrl(inp["x0"].to(DEV), QuadCost(Qd.to(DEV), q.to(DEV), None), dyn, dyn)
+        assert x.shape == (B, 5, 12) and u.shape == (B, 5, 4) and st is False
+        assert torch.isfinite(x).all() and torch.isfinite(u).all()
+
+
+def test_unregistered_dynamics_and_cpu_tensors_fail_loudly():
+    inp = make_inputs("pendulum", 5, 4, 3)
+    Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"])
+    ctrl = MPC(2, 1, 5, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=4)
+    ctrl.reinitialize(inp["x_ref"])
+    ctrl.x_init, ctrl.u_init = inp["x_ref"], inp["u_ref"]
+    with pytest.raises(_lib.AlmpcError):
+        ctrl(inp["x0"], QuadCost(Qd, q, None), make_dyn("pendulum"), None)  # CPU tensors
+    with pytest.raises(_lib.AlmpcError):
+        ctrl(inp["x0"].to(DEV), QuadCost(Qd.to(DEV), q.to(DEV), None), lambda x, u: x, None)
+
+
+def test_full_size_properties_quadrotor_64k():
+    """BASELINE.json headline size (quadrotor T=5, B=65536, fp64): properties that do not need the
+    oracle — determinism, replicated problems give bit-identical rows, KKT residual of the adjoint
+    solve, linearity of the backward — plus an oracle check on a sample of rows with the Newton-step
+    counts forced to the ones the GPU batch realised (the stop rule is batch-global)."""
+    model, T, B = "rex_quadrotor", 5, 65536
+    spec = MODEL_SPECS[model]
+    base = make_inputs(model, T, 4096, 99)
+    rep = B // 4096
+    inp = {k: (v.repeat(rep, *([1] * (v.dim() - 1))) if v.dim() > 1 else v) for k, v in base.items()}
+    Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"])
+    dyn = make_dyn(model)
+
+    def run():
+        ctrl = MPC(12, 4, T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B)
+        ctrl.reinitialize(inp["x_ref"].to(DEV))
+        ctrl.x_init, ctrl.u_init = inp["x_ref"].to(DEV), inp["u_ref"].to(DEV)
+        ql = q.to(DEV).requires_grad_(True)
+        x, u, _ = ctrl(inp["x0"].to(DEV), QuadCost(Qd.to(DEV), ql, None), dyn, dyn)
+        return ctrl, x, u, ql
+
+    ctrl, x, u, ql = run()
+    ctrl2, x2, u2, _ = run()
+    assert torch.equal(x, x2) and torch.equal(u, u2) and torch.equal(ctrl.lamda_prev, ctrl2.lamda_prev)  # deterministic
+    xu = ctrl.last_xu.view(rep, 4096, T, 16)
+    assert (xu == xu[0:1]).all()  # replicas bit-identical
+    assert (ctrl.last_status == 3).all()
+    steps = ctrl.newton_steps()
+    # backward linearity
+    g = torch.Generator().manual_seed(1)
+    v1 = torch.randn(B, T, 12, generator=g).to(DEV), torch.randn(B, T, 4, generator=g).to(DEV)
+    v2 = torch.randn(B, T, 12, generator=g).to(DEV), torch.randn(B, T, 4, generator=g).to(DEV)
+    g1, = torch.autograd.grad((x, u), ql, v1, retain_graph=True)
+    g2, = torch.autograd.grad((x, u), ql, v2, retain_graph=True)
+    g12, = torch.autograd.grad((x, u), ql, (2 * v1[0] - 3 * v2[0], 2 * v1[1] - 3 * v2[1]), retain_graph=True)
+    assert rel_err(g12, 2 * g1 - 3 * g2) < 1e-9
+    # oracle on a sample of rows, forcing the realised step counts
+    from oracle import almpc_oracle as orc
+    from oracle.problem_gen import make_oracle_model
+
+    rows = torch.arange(0, 4096, 37)[:96]
+    om = make_oracle_model(model)
+    ompc = orc.OracleMPC(om, T, inp["u_lower"], inp["u_upper"], len(rows), al_iter=2)
+    ompc.reinitialize(inp["x_ref"][rows])
+    ompc.x_init, ompc.u_init = inp["x_ref"][rows].clone(), inp["u_ref"][rows].clone()
+    ompc.force_steps = list(steps)
+    _, _, _, xuo = ompc.solve(inp["x0"][rows], Qd[rows], q[rows])
+    assert rel_err(ctrl.last_xu[rows.to(DEV)].cpu(), xuo) < 1e-6
+    Qg_o, qg_o = ompc.backward(v1[0][rows.to(DEV)].cpu(), v1[1][rows.to(DEV)].cpu())
+    assert rel_err(g1[rows.to(DEV)].cpu(), qg_o) < 1e-6
+
+
+def test_newton_al_function_signature():
+    """al_utils.NewtonAL.apply with the reference's 15-argument order (al_utils.py:451-468)."""
+    from deq_mpc_corl_b200.al_utils import NewtonAL, NewtonContext
+    from oracle import almpc_oracle as orc
+    from oracle.problem_gen import make_oracle_model
+
+    model, T, B = "cartpole1l", 5, 64
+    inp = make_inputs(model, T, B, 21)
+    Qd, q, f = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"])
+    dyn = make_dyn(model)
+    xu0 = torch.cat([inp["x_ref"], inp["u_ref"]], -1).double()
+    lam = torch.zeros(B, T * 4 + 2 * T, dtype=torch.float64)
+    rho = torch.ones(B, 1, dtype=torch.float64)
+
+    def meritfn(*a, **k):
+        raise AssertionError("callables are not evaluated by the fused path")
+
+    meritfn.almpc_context = NewtonContext(dyn, inp["u_lower"], inp["u_upper"])
+    Ql, ql = Qd.to(DEV).requires_grad_(True), q.to(DEV).requires_grad_(True)
+    x_est, status = NewtonAL.apply(meritfn, None, None, None, xu0.to(DEV), inp["x0"].double().to(DEV), lam.to(DEV),
+                                   rho.to(DEV), Ql, ql, f.to(DEV), 1e-3, 1e-6, True, 0)
+    gQ, gq = torch.autograd.grad(x_est, (Ql, ql), torch.ones_like(x_est))
+    pb = orc.Problem(make_oracle_model(model), T, inp["u_lower"], inp["u_upper"])
+    xo, st, saved = orc.newton_al(pb, xu0.clone(), inp["x0"].double(), lam, rho, Qd, q)
+    Qg_o, qg_o = orc.newton_backward(saved, xo, torch.ones_like(xo))
+    assert status.all() and rel_err(x_est.detach().cpu(), xo) < 1e-8
+    assert rel_err(gq.cpu(), qg_o) < 1e-7 and rel_err(gQ.cpu(), Qg_o) < 1e-7
