@@ -11,7 +11,9 @@
 // code runs on plain scalars (line search, residuals) and on dual numbers (forward-mode Jacobian
 // columns, one tangent per thread).
 #pragma once
+#ifndef ALMPC_MODELS_NO_CUDA
 #include <cuda_runtime.h>
+#endif
 
 namespace almpc {
 

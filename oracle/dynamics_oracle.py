@@ -280,7 +280,17 @@ class Cartpole2L(_Model):
         q, qd = x[..., :3], x[..., 3:]
         M, b = self._mass_bias(q, qd)
         tau = torch.cat([u, torch.zeros_like(qd[..., :2])], -1)
-        qdd = torch.linalg.solve(M, (tau - b).unsqueeze(-1)).squeeze(-1)
+        # explicit 3x3 solve by Cramer's rule (torch.linalg.solve under vmap(jacfwd) returned wrong
+        # tangents for batches > 1 with torch 2.11 — caught by the finite-difference self-check)
+        r = tau - b
+        a, bb, c = M[..., 0, 0], M[..., 0, 1], M[..., 0, 2]
+        d, e, f_ = M[..., 1, 1], M[..., 1, 2], M[..., 2, 2]
+        c00, c01, c02 = d * f_ - e * e, c * e - bb * f_, bb * e - c * d
+        c11, c12, c22 = a * f_ - c * c, bb * c - a * e, a * d - bb * bb
+        det = a * c00 + bb * c01 + c * c02
+        r0, r1, r2 = r[..., 0], r[..., 1], r[..., 2]
+        qdd = torch.stack([c00 * r0 + c01 * r1 + c02 * r2, c01 * r0 + c11 * r1 + c12 * r2,
+                           c02 * r0 + c12 * r1 + c22 * r2], -1) / det.unsqueeze(-1)
         return torch.cat([qd, qdd], -1)
 
 
