@@ -889,13 +889,14 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
     return set_err(-10, "null buffer");
   const Layout<NX, NU> L(d->T);
   const size_t smem = (size_t)kWPB * L.total * sizeof(S);
-  if (smem > 227 * 1024) return set_err(-11, "horizon too long for the shared-memory layout");
+  if (smem + 1024 > 227 * 1024) return set_err(-11, "horizon too long for the shared-memory layout");
   auto kern = k_newton_step<M, S, kWPB>;
   auto kfin = k_final_dual<M, S, kWPB>;
   cudaError_t e;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  const size_t smem_fin = (size_t)kWPB * (L.N + L.neq) * sizeof(S);
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(newton_step)");
-  e = cudaFuncSetAttribute(kfin, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(kfin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fin);
   if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(final_dual)");
   const KParams<S> P = make_params<S>(d);
   const int nb = n_blocks(d->B);
@@ -913,7 +914,6 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
     kern<<<nb, kWPB * 32, smem, st>>>(P, x0, Qd, q, xu, lam, rho, factor, status, info_out, debug_out, ctl, partials,
                                       merit);
   }
-  const size_t smem_fin = (size_t)kWPB * (L.N + L.neq) * sizeof(S);
   kfin<<<nb, kWPB * 32, smem_fin, st>>>(P, x0, xu, lam, rho, x_out, u_out, dyn_res_out, info_out, ctl);
   return cuda_err(cudaGetLastError(), "almpc_forward launch");
 }
@@ -927,7 +927,7 @@ static int backward_impl(const almpc_desc* d, const S* factor, const S* xu, cons
   const size_t smem = (size_t)kWPB * (d->T * NN + NX * NN) * sizeof(S);
   auto kern = k_backward<NX, NU, S, kWPB>;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(backward)");
   }
   kern<<<n_blocks(d->B), kWPB * 32, smem, st>>>(d->B, d->T, factor, xu, grad_xu, grad_Q, grad_q);
