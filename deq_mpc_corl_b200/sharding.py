@@ -1,0 +1,113 @@
+"""Multi-GPU plumbing for the AL-MPC path: one process per GPU, the problem batch split contiguously.
+
+The solve is embarrassingly parallel over problems, so the data path has NO
+collective: every rank runs the fused solver on its own shard.  Collectives appear in exactly two
+places, both here:
+
+* ``allreduce_gradients`` — the policy-gradient all-reduce of DEQ-MPC training (the only trainable
+  tensors are the network parameters, deqmpc/train.py:265); NCCL over NVLink on GPUs, gloo on CPU.
+* ``gather_batch`` — optional re-assembly of per-shard outputs (evaluation / tests).
+
+Stop-rule semantics under sharding: the reference's Newton stop test is a statistic of the WHOLE
+batch (qpth/al_utils.py:486,552,560-564).  Each rank applies the same rule to ITS shard
+("per-shard stopping"); realised Newton-step counts are reported per rank.  A sharded run is
+therefore bit-identical to the reference run on each shard, not to the reference run on the
+concatenated batch.
+"""
+from typing import Callable, Dict, Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous [lo, hi) of rank's shard; the first n % world ranks get one extra problem."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard(t: torch.Tensor, world: int, rank: int) -> torch.Tensor:
+    lo, hi = shard_bounds(t.shape[0], world, rank)
+    return t[lo:hi]
+
+
+def _world(group=None):
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def gather_batch(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All-gather shards of unequal length back into the [n_total, ...] batch (every rank gets it)."""
+    world, rank = _world(group)
+    if world == 1:
+        return local
+    sizes = [shard_bounds(n_total, world, r) for r in range(world)]
+    max_len = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((max_len,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], 0)
+
+
+def run_sharded(fn: Callable[..., Sequence[torch.Tensor]], batch_inputs: Dict[str, torch.Tensor], group=None,
+                gather: bool = True):
+    """Slice every [B, ...] input to this rank's shard, call ``fn(**shard)`` and (optionally) gather
+    every output back to the full batch.  ``fn`` is the per-GPU solve (e.g. a closure over ``MPC``)."""
+    world, rank = _world(group)
+    n = next(iter(batch_inputs.values())).shape[0]
+    local = {k: shard(v, world, rank) for k, v in batch_inputs.items()}
+    outs = fn(**local)
+    if not gather:
+        return outs
+    return tuple(gather_batch(o, n, group) for o in outs)
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, average: bool = True,
+                        bucket_bytes: int = 32 << 20) -> int:
+    """Sum (or average) ``p.grad`` over the ranks with flat buckets sized for launch latency, not link
+    count (NVSwitch: every peer at full bandwidth).  Returns the number of collectives issued."""
+    world, _ = _world(group)
+    grads = [p.grad for p in params if p.grad is not None]
+    if world == 1 or not grads:
+        return 0
+    n_coll = 0
+    bucket: List[torch.Tensor] = []
+    size = 0
+
+    def flush():
+        nonlocal bucket, size, n_coll
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat /= world
+        off = 0
+        for g in bucket:
+            g.copy_(flat[off: off + g.numel()].view_as(g))
+            off += g.numel()
+        bucket, size = [], 0
+        n_coll += 1
+
+    for g in grads:
+        if bucket and (g.dtype != bucket[0].dtype or size + g.numel() * g.element_size() > bucket_bytes):
+            flush()
+        bucket.append(g)
+        size += g.numel() * g.element_size()
+    flush()
+    return n_coll
+
+
+def allreduce_stop_statistic(sum_sq: torch.Tensor, group=None) -> torch.Tensor:
+    """Helper for callers that want the reference's batch-GLOBAL stop statistic across shards:
+    sqrt(sum over ranks of per-shard sum of squares).  8 bytes, latency-only over NVLink."""
+    world, _ = _world(group)
+    t = sum_sq.clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.sqrt()
