@@ -81,17 +81,17 @@ struct Layout {
   __host__ __device__ Layout(int T) {
     N = T * NN; neq = T * NX; nin = 2 * T * NU; m = neq + nin;
     int o = 0;
-    xu = o; o += N;
-    dv = o; o += N;
-    lam = o; o += m;
-    c = o; o += neq;
-    w = o; o += neq;
-    x0 = o; o += NX;
-    G = o; o += (T - 1) * NX * NN;
-    scr = o;
-    int s1 = NN * (NN + 1), s2 = NLS * (T - 1) * 3 + NLS * 4;
-    o += (s1 > s2 ? s1 : s2);
-    total = (o + 1) & ~1;
+    auto take = [&](int cnt) { int at = o; o += (cnt + 1) & ~1; return at; };  // every region 16-byte aligned
+    xu = take(N);
+    dv = take(N);
+    lam = take(m);
+    c = take(neq);
+    w = take(neq);
+    x0 = take(NX);
+    G = take((T - 1) * NX * NN);
+    int s1 = NN * ((NN % 2 == 0) ? NN + 2 : NN + 1), s2 = NLS * (T - 1) * 3;
+    scr = take(s1 > s2 ? s1 : s2);
+    total = o;
   }
 };
 
@@ -146,14 +146,145 @@ __host__ __device__ inline size_t factor_elems(int T) {
 // BUILD=true  : build D_t from G, Qd, rho and the active set, factor, stream to `fac`
 // BUILD=false : (backward pass) read L_tt / E_t from `fac` and only do the substitution.
 // ------------------------------------------------------------------------------------------------
+// D(8x8) += A(8x4) B(4x8), FP64 tensor-core MMA (legacy mma.sync path; on B200 it runs at the DFMA rate
+// but replaces 8 DFMA + their shared-memory operand loads per lane by one instruction).
+// Fragment layout (PTX ISA, m8n8k4 .f64): g = lane>>2, q = lane&3:  a = A[g][q], b = B[q][g],
+// c0 = C[g][2q], c1 = C[g][2q+1].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int NN>
+struct ScrLd {
+  static constexpr int LD = (NN % 2 == 0) ? NN + 2 : NN + 1;  // even: rows start 16-byte aligned
+};
+
+// D_t = diag(Qd_t) + rho (G_t^T G_t + I_x + active bounds) - E_{t-1} E_{t-1}^T   (lower tiles) -> scr
+template <int NX, int NU, typename S>
+__device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, const S* Ep, bool has_G, bool has_E,
+                                            int lane, S rho, const S* __restrict__ Qd_t, const S* ulo, const S* uhi) {
+  constexpr int NN = NX + NU;
+  constexpr int LD = ScrLd<NN>::LD;
+  if constexpr (sizeof(S) == 8) {
+    constexpr int NT = (NN + 7) / 8, KG = (NX + 3) / 4, NTX = (NX + 7) / 8, KE = (NN + 3) / 4;
+    const int g = lane >> 2, q4 = lane & 3;
+    double acc[NT][NT][2];
+#pragma unroll
+    for (int rt = 0; rt < NT; ++rt)
+#pragma unroll
+      for (int ct = 0; ct < NT; ++ct) acc[rt][ct][0] = acc[rt][ct][1] = 0.0;
+    if (has_G) {
+      double f[NT][KG];
+#pragma unroll
+      for (int tl = 0; tl < NT; ++tl)
+#pragma unroll
+        for (int ch = 0; ch < KG; ++ch) {
+          const int col = tl * 8 + g, row = 4 * ch + q4;
+          f[tl][ch] = (col < NN && row < NX) ? (double)Gt[row * NN + col] : 0.0;
+        }
+#pragma unroll
+      for (int rt = 0; rt < NT; ++rt)
+#pragma unroll
+        for (int ct = 0; ct <= rt; ++ct)
+#pragma unroll
+          for (int ch = 0; ch < KG; ++ch) dmma884(acc[rt][ct][0], acc[rt][ct][1], f[rt][ch], f[ct][ch]);
+    }
+    double sy[NTX][NTX][2];
+#pragma unroll
+    for (int rt = 0; rt < NTX; ++rt)
+#pragma unroll
+      for (int ct = 0; ct < NTX; ++ct) sy[rt][ct][0] = sy[rt][ct][1] = 0.0;
+    if (has_E) {
+      double f[NTX][KE];
+#pragma unroll
+      for (int tl = 0; tl < NTX; ++tl)
+#pragma unroll
+        for (int ch = 0; ch < KE; ++ch) {
+          const int row = tl * 8 + g, k = 4 * ch + q4;
+          f[tl][ch] = (row < NX && k < NN) ? (double)Ep[row * NN + k] : 0.0;
+        }
+#pragma unroll
+      for (int rt = 0; rt < NTX; ++rt)
+#pragma unroll
+        for (int ct = 0; ct <= rt; ++ct)
+#pragma unroll
+          for (int ch = 0; ch < KE; ++ch) dmma884(sy[rt][ct][0], sy[rt][ct][1], f[rt][ch], f[ct][ch]);
+    }
+#pragma unroll
+    for (int rt = 0; rt < NT; ++rt) {
+      const int r = rt * 8 + g;
+#pragma unroll
+      for (int ct = 0; ct <= rt; ++ct) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = ct * 8 + 2 * q4 + e;
+          double v = acc[rt][ct][e];
+          if (r == c) {
+            if (r < NX) {
+              v += 1.0;
+            } else if (r < NN) {
+              const double u = xu_t[r];
+              v += ((u - uhi[r - NX]) >= 0.0 ? 1.0 : 0.0) + ((ulo[r - NX] - u) >= 0.0 ? 1.0 : 0.0);
+            }
+          }
+          v *= rho;
+          if (r == c && r < NN) v += Qd_t[r];
+          if (rt < NTX && ct < NTX) v -= sy[rt][ct][e];
+          if (r < NN && c < NN) scr[r * LD + c] = v;
+        }
+      }
+    }
+  } else {
+    constexpr int NTRI = NN * (NN + 1) / 2;
+    for (int idx = lane; idx < NTRI; idx += 32) {
+      int r = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
+      while (r * (r + 1) / 2 > idx) --r;
+      while ((r + 1) * (r + 2) / 2 <= idx) ++r;
+      const int c = idx - r * (r + 1) / 2;
+      S v0 = S(0), v1 = S(0);
+      if (has_G) {
+#pragma unroll
+        for (int i = 0; i + 1 < NX; i += 2) {
+          v0 += Gt[i * NN + r] * Gt[i * NN + c];
+          v1 += Gt[(i + 1) * NN + r] * Gt[(i + 1) * NN + c];
+        }
+        if (NX & 1) v0 += Gt[(NX - 1) * NN + r] * Gt[(NX - 1) * NN + c];
+      }
+      S v = v0 + v1;
+      if (r == c) {
+        if (r < NX) {
+          v += S(1);
+        } else {
+          const S u = xu_t[r];
+          v += ((u - uhi[r - NX]) >= S(0) ? S(1) : S(0)) + ((ulo[r - NX] - u) >= S(0) ? S(1) : S(0));
+        }
+      }
+      v *= rho;
+      if (r == c) v += Qd_t[r];
+      if (has_E && r < NX) {
+        S s0 = S(0), s1 = S(0);
+#pragma unroll
+        for (int k = 0; k + 1 < NN; k += 2) {
+          s0 += Ep[r * NN + k] * Ep[c * NN + k];
+          s1 += Ep[r * NN + k + 1] * Ep[c * NN + k + 1];
+        }
+        if (NN & 1) s0 += Ep[r * NN + NN - 1] * Ep[c * NN + NN - 1];
+        v -= s0 + s1;
+      }
+      scr[r * LD + c] = v;
+    }
+  }
+}
+
 template <int NX, int NU, typename S>
 __device__ __forceinline__ bool forward_sweep_factor(S* sm, const Layout<NX, NU>& L, int T, int lane, S rho,
                                                      const S* __restrict__ Qd_g, const S* ulo, const S* uhi,
                                                      S* fac) {
   constexpr int NN = NX + NU;
-  constexpr int LD = NN + 1;
+  constexpr int LD = ScrLd<NN>::LD;
   constexpr int EX0 = 32 - NN - 1;  // sub-diagonal rows that fit next to L rows and the rhs row
-  constexpr int NTRI = NN * (NN + 1) / 2;
   S* xu = sm + L.xu;
   S* dv = sm + L.dv;
   S* G = sm + L.G;
@@ -162,41 +293,20 @@ __device__ __forceinline__ bool forward_sweep_factor(S* sm, const Layout<NX, NU>
   for (int t = 0; t < T; ++t) {
     const S* Gt = G + (size_t)t * NX * NN;          // valid for t < T-1
     const S* Ep = G + (size_t)(t - 1) * NX * NN;    // E_{t-1}, valid for t > 0
-    // ---- (a) D_t (lower triangle) into scr; rhs_t -= E_{t-1} y_{t-1}
-    for (int idx = lane; idx < NTRI; idx += 32) {
-      int r = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
-      while (r * (r + 1) / 2 > idx) --r;
-      while ((r + 1) * (r + 2) / 2 <= idx) ++r;
-      int c = idx - r * (r + 1) / 2;
-      S v = S(0);
-      if (t < T - 1) {
-#pragma unroll
-        for (int i = 0; i < NX; ++i) v += Gt[i * NN + r] * Gt[i * NN + c];
-      }
-      if (r == c) {
-        if (r < NX) {
-          v += S(1);
-        } else {
-          S u = xu[t * NN + r];
-          v += ((u - uhi[r - NX]) >= S(0) ? S(1) : S(0)) + ((ulo[r - NX] - u) >= S(0) ? S(1) : S(0));
-        }
-      }
-      v *= rho;
-      if (r == c) v += Qd_g[t * NN + r];
-      if (t > 0 && r < NX) {  // c <= r < NX
-        S s = S(0);
-#pragma unroll
-        for (int k = 0; k < NN; ++k) s += Ep[r * NN + k] * Ep[c * NN + k];
-        v -= s;
-      }
-      scr[r * LD + c] = v;
-    }
+    S* Lg = fac + (size_t)t * NN * NN;
+    S* Eg = fac + (size_t)T * NN * NN + (size_t)t * NX * NN;
+    // ---- (a) D_t (lower part) into scr; rhs_t -= E_{t-1} y_{t-1}
+    build_block<NX, NU, S>(scr, xu + t * NN, Gt, Ep, t < T - 1, t > 0, lane, rho, Qd_g + t * NN, ulo, uhi);
     if (t > 0) {
       for (int r = lane; r < NX; r += 32) {
-        S s = S(0);
+        S s0 = S(0), s1 = S(0);
 #pragma unroll
-        for (int k = 0; k < NN; ++k) s += Ep[r * NN + k] * dv[(t - 1) * NN + k];
-        dv[t * NN + r] -= s;
+        for (int k = 0; k + 1 < NN; k += 2) {
+          s0 += Ep[r * NN + k] * dv[(t - 1) * NN + k];
+          s1 += Ep[r * NN + k + 1] * dv[(t - 1) * NN + k + 1];
+        }
+        if (NN & 1) s0 += Ep[r * NN + NN - 1] * dv[(t - 1) * NN + NN - 1];
+        dv[t * NN + r] -= s0 + s1;
       }
     }
     __syncwarp();
@@ -209,34 +319,37 @@ __device__ __forceinline__ bool forward_sweep_factor(S* sm, const Layout<NX, NU>
 #pragma unroll
       for (int c = 0; c < NN; ++c) a[c] = dv[t * NN + c];
     } else {
-      int i = lane - NN - 1;
-      bool act = (i < NX) && (t < T - 1);
+      const int i = lane - NN - 1;
+      const bool act = (i < NX) && (t < T - 1);
 #pragma unroll
       for (int c = 0; c < NN; ++c) a[c] = act ? -rho * Gt[i * NN + c] : S(0);
     }
     // ---- (c) factor + forward substitution + trsm in one elimination
     ok = eliminate<NN, true>(a, lane) && ok;
     __syncwarp();
-    // ---- (d) write-outs
+    // ---- (d) write-outs straight from registers: L rows -> global, y -> dv, E rows -> smem + global
     if (lane < NN) {
 #pragma unroll
-      for (int c = 0; c < NN; ++c) scr[lane * LD + c] = (c <= lane) ? a[c] : S(0);
+      for (int c = 0; c < NN; ++c) Lg[lane * NN + c] = (c <= lane) ? a[c] : S(0);
     } else if (lane == NN) {
 #pragma unroll
       for (int c = 0; c < NN; ++c) dv[t * NN + c] = a[c];
     } else {
-      int i = lane - NN - 1;
+      const int i = lane - NN - 1;
       if (i < NX && t < T - 1) {
         S* Et = G + (size_t)t * NX * NN;
 #pragma unroll
-        for (int c = 0; c < NN; ++c) Et[i * NN + c] = a[c];
+        for (int c = 0; c < NN; ++c) {
+          Et[i * NN + c] = a[c];
+          Eg[i * NN + c] = a[c];
+        }
       }
     }
     if (NX > EX0 && t < T - 1) {  // sub-diagonal rows that did not fit (e.g. flying cartpole nx=14, n=18)
       constexpr int PER = 32 - NN;
       for (int base = EX0; base < NX; base += PER) {
-        int i = base + (lane - NN);
-        bool act = (lane >= NN) && (i < NX);
+        const int i = base + (lane - NN);
+        const bool act = (lane >= NN) && (i < NX);
         if (lane >= NN) {
 #pragma unroll
           for (int c = 0; c < NN; ++c) a[c] = act ? -rho * Gt[i * NN + c] : S(0);
@@ -245,22 +358,11 @@ __device__ __forceinline__ bool forward_sweep_factor(S* sm, const Layout<NX, NU>
         if (act) {
           S* Et = G + (size_t)t * NX * NN;
 #pragma unroll
-          for (int c = 0; c < NN; ++c) Et[i * NN + c] = a[c];
+          for (int c = 0; c < NN; ++c) {
+            Et[i * NN + c] = a[c];
+            Eg[i * NN + c] = a[c];
+          }
         }
-      }
-    }
-    __syncwarp();
-    // stream L_tt (row-major NN x NN) and E_t to global
-    {
-      S* Lg = fac + (size_t)t * NN * NN;
-      for (int idx = lane; idx < NN * NN; idx += 32) {
-        int r = idx / NN, c = idx - r * NN;
-        Lg[idx] = scr[r * LD + c];
-      }
-      if (t < T - 1) {
-        S* Eg = fac + (size_t)T * NN * NN + (size_t)t * NX * NN;
-        const S* Et = G + (size_t)t * NX * NN;
-        for (int idx = lane; idx < NX * NN; idx += 32) Eg[idx] = Et[idx];
       }
     }
     __syncwarp();
@@ -497,7 +599,6 @@ k_newton_step(const KParams<S> P, const S* __restrict__ x0_g, const S* __restric
 
     // ---------------------------------------------------------------- P5 line search
     S* part = scr;                       // [NLS][(T-1)][3]
-    S* cand = scr + NLS * (T - 1) * 3;   // [NLS][4]: merit, res2
     for (int it = lane; it < NLS * (T - 1); it += 32) {
       const int kk = it / (T - 1), t = it - kk * (T - 1);
       const S alpha = (S)ldexpf(1.0f, -kk);
