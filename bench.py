@@ -363,7 +363,7 @@ def main():
             "e2e": {"value": k_e2e * B * world / (e2e_ms * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / k_e2e,
                     "api": "deq_mpc_corl_b200.al_mpc.MPC.forward + autograd backward, pinned host buffers"},
-            "gpu_launches": args.steps * (cfg.al_iter * cfg.max_newton + 2),
+            "gpu_launches": args.steps * (cfg.al_iter * cfg.max_newton * 3 + 2),
             "roofline": {
                 "bound": "fp64_fma" if dtype == torch.float64 else "fp32_fma", "kernel": "k_newton_step",
                 "achieved": ach_tflops, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach_tflops / peak_tflops,

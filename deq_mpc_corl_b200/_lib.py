@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libalmpc.so")
+LIB_PATH = os.environ.get("ALMPC_LIB", os.path.join(_HERE, "libalmpc.so"))
 
 MAX_PARAMS = 48
 MAX_NU = 8

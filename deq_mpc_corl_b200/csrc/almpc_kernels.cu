@@ -1,23 +1,29 @@
-// libalmpc: fused batched augmented-Lagrangian MPC solver for sm_100a (B200).
+// libalmpc: batched augmented-Lagrangian MPC solver for sm_100a (B200).
 //
-// One warp owns one problem.  One launch of k_newton_step performs ONE Gauss-Newton step of the
-// reference's NewtonAL.forward (qpth/al_utils.py:451-576) for every problem of the batch:
+// One Gauss-Newton step of the reference's NewtonAL.forward (qpth/al_utils.py:451-576) for every problem
+// of the batch is THREE stream-ordered launches, each with the thread mapping / register budget / occupancy
+// its phase wants (the first version fused them into one warp-per-problem kernel and was latency-bound at
+// 16 warps/SM because the register-hungry dynamics and the pivot-chain-bound factorisation shared one
+// register allocation; profiles/r01_v1_*):
 //
-//   P1  dynamics + Jacobians G_t=[A_t B_t] (forward-mode duals, one tangent column per lane)   al_utils.py:233-265
-//   P2  residuals c, (optional) dual/penalty update of the previous AL iteration, merit        AL_mpc.py:315-325, al_utils.py:52-77
-//   P3  gradient g = Qd z + q + J^T lam + rho Jc^T c+                                           al_utils.py:113-117
-//   P4  block-tridiagonal Cholesky of H = diag(Qd) + rho Jc^T Jc and the two triangular sweeps  al_utils.py:119-120, 510-515
-//       (the reference factors the dense 80x80 matrix; H is exactly block tridiagonal)
-//   P5  20-point line search, first-argmin, strict-decrease accept                              al_utils.py:618-642
-//   P6  batch-global stop statistics -> device-side control block for the next launch           al_utils.py:551-564
+//   k_jacobian      1 thread = 1 (problem, stage t, tangent column j): dynamics + Jacobians G_t=[A_t B_t]
+//                   by forward-mode duals, residuals c_t                                       al_utils.py:233-265
+//   k_factor_solve  1 warp = 1 problem (~28 warps/SM): residual statistics, (optional) dual/penalty update of
+//                   the previous AL iteration (AL_mpc.py:315-325), merit (al_utils.py:52-77), gradient
+//                   (:113-117), block-tridiagonal Cholesky of H = diag(Qd) + rho Jc^T Jc and both triangular
+//                   sweeps (:119-120, 510-515; the reference factors the dense matrix, H is exactly block
+//                   tridiagonal) -> Newton direction
+//   k_line_search   1 thread = 1 (problem, candidate 2^-k, stage t): 20-point line search, first-argmin,
+//                   strict-decrease accept (al_utils.py:618-642), iterate update, and the batch-global stop
+//                   statistics -> device-side control block for the next launches           al_utils.py:551-564
 //
-// The batch-global decisions of the reference (stop rule on ||c+||_F over the WHOLE batch, the
-// rho_max exit of al_solve_stream) are taken on the device by the last CTA of every launch
-// (deterministic two-stage reduction), so a solve is a fixed sequence of launches without any host
-// synchronisation; launches that find the solve finished return immediately.
+// The batch-global decisions of the reference (stop rule on ||c+||_F over the WHOLE batch, the rho_max
+// exit of al_solve_stream) are taken on the device by the last CTA of k_line_search (deterministic two-stage
+// reduction), so a solve is a fixed sequence of launches without any host synchronisation; launches that
+// find the solve finished return immediately.
 //
-// The block factor streams to global memory as it is produced (it is the cached factor the
-// implicit backward needs, al_utils.py:572,590) and is read back for the backward sweep.
+// The block factor streams to global memory as it is produced (it is the cached factor the implicit
+// backward needs, al_utils.py:572,590) and is read back (L2) for the backward sweep.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -26,6 +32,13 @@
 
 #include "almpc.h"
 #include "almpc_models.cuh"
+
+#ifndef ALMPC_NO_VEC2
+#define ALMPC_NO_VEC2 0
+#endif
+#ifndef ALMPC_NO_CP16
+#define ALMPC_NO_CP16 0
+#endif
 
 namespace almpc {
 
@@ -53,10 +66,55 @@ struct KParams {
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double rsqrt_(double x) { return rsqrt(x); }
+// 1/sqrt(x): fp32 MUFU seed (2^-22) + one cubically convergent correction in fp64 (~1 ulp):
+//   r = 1 - x y^2 ;  x^-1/2 = y (1 + r/2 + 3 r^2/8 + O(r^3)).  Pivots outside the fp32 range are flagged by
+// the caller (d < 1e30) and never occur for rho <= 1e12.
+__device__ __forceinline__ double rsqrt_(double x) {
+  const double y = (double)rsqrtf((float)x);
+  const double r = fma(-x * y, y, 1.0);
+  const double p = fma(0.375, r, 0.5);
+  return fma(y * r, p, y);
+}
 __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
 template <typename S> __device__ __forceinline__ S fmax0(S x) { return x > S(0) ? x : S(0); }
 template <typename S> __device__ __forceinline__ bool finite_(S x) { return (x - x) == S(0); }
+
+template <typename S> struct alignas(2 * sizeof(S)) Vec2 { S x, y; };
+
+// Ampere-style asynchronous global->shared copies (LDGSTS): the factor kernel prefetches the next stage's
+// blocks while the pivot chain of the current stage runs.
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// copy COUNT scalars with copy width W bytes (W = widest size dividing EVERY block size of the problem, so
+// that all block offsets are W-aligned)
+template <int COUNT, int W, typename S>
+__device__ __forceinline__ void warp_copy_async(S* dst, const S* src, int lane) {
+  constexpr int BYTES = COUNT * (int)sizeof(S);
+  static_assert(BYTES % W == 0, "copy width must divide the block");
+  for (int o = lane * W; o < BYTES; o += 32 * W) {
+    if constexpr (W == 16) cp_async16((char*)dst + o, (const char*)src + o);
+    else if constexpr (W == 8) cp_async8((char*)dst + o, (const char*)src + o);
+    else cp_async4((char*)dst + o, (const char*)src + o);
+  }
+}
+template <int NX, int NU, typename S>
+struct CopyWidth {
+  static constexpr int NN = NX + NU;
+  static constexpr int b1 = NN * NN * (int)sizeof(S), b2 = NX * NN * (int)sizeof(S);
+  static constexpr int W = (b1 % 16 == 0 && b2 % 16 == 0 && !ALMPC_NO_CP16) ? 16 : ((b1 % 8 == 0 && b2 % 8 == 0) ? 8 : 4);
+};
 
 template <typename S>
 __device__ __forceinline__ S warp_sum(S v) {
@@ -72,25 +130,43 @@ __device__ __forceinline__ S next_rho(S rho, double mult, int f32) {
   return (S)r;
 }
 
-// per-warp shared-memory layout, in units of S
+// per-warp shared-memory layout of k_factor_solve, in units of S (every region 16-byte aligned)
 template <int NX, int NU>
 struct Layout {
   static constexpr int NN = NX + NU;
   int N, neq, nin, m;
-  int xu, dv, lam, c, w, x0, G, scr, total;
+  int xu, dv, w, Gt, Ep, scr, total;
   __host__ __device__ Layout(int T) {
     N = T * NN; neq = T * NX; nin = 2 * T * NU; m = neq + nin;
     int o = 0;
-    auto take = [&](int cnt) { int at = o; o += (cnt + 1) & ~1; return at; };  // every region 16-byte aligned
+    auto take = [&](int cnt) { int at = o; o += (cnt + 3) & ~3; return at; };  // regions 16-byte aligned for float and double
     xu = take(N);
     dv = take(N);
-    lam = take(m);
-    c = take(neq);
     w = take(neq);
+    Gt = take(NX * NN);
+    Ep = take(NX * NN);
+    scr = take(64 + NN * ((NN % 2 == 0) ? NN + 2 : NN + 1));
+    total = o;
+  }
+};
+
+// per-problem shared-memory layout of k_line_search, in units of S
+template <int NX, int NU>
+struct LsLayout {
+  static constexpr int NN = NX + NU;
+  int N, neq, nin, m;
+  int xu, d, lam, Qd, q, x0, part, total;
+  __host__ __device__ LsLayout(int T) {
+    N = T * NN; neq = T * NX; nin = 2 * T * NU; m = neq + nin;
+    int o = 0;
+    auto take = [&](int cnt) { int at = o; o += (cnt + 3) & ~3; return at; };  // regions 16-byte aligned for float and double
+    xu = take(N);
+    d = take(N);
+    lam = take(m);
+    Qd = take(N);
+    q = take(N);
     x0 = take(NX);
-    G = take((T - 1) * NX * NN);
-    int s1 = NN * ((NN % 2 == 0) ? NN + 2 : NN + 1), s2 = NLS * (T - 1) * 3;
-    scr = take(s1 > s2 ? s1 : s2);
+    part = take(NLS * (T - 1) * 3);
     total = o;
   }
 };
@@ -102,31 +178,51 @@ struct Layout {
 // FUSED=true  : factor + solve in one pass.
 // FUSED=false : lanes 0..NN-1 already hold L (read-only); only lanes >= NN are transformed.
 // ------------------------------------------------------------------------------------------------
+// The pivot column travels through shared memory (one STS per lane, then 16-byte broadcast loads) instead
+// of one shuffle pair per entry: the first version was bound by the SM's shuffle throughput.
+//   colbuf : FUSED: 2 x 32 scalars (double-buffered pivot column).  !FUSED: the L rows, [NN][LDL].
 template <int NN, bool FUSED, typename S>
-__device__ __forceinline__ bool eliminate(S (&a)[NN], int lane) {
+__device__ __forceinline__ bool eliminate(S (&a)[NN], int lane, S* colbuf, int LDL = 0) {
   bool ok = true;
 #pragma unroll
   for (int k = 0; k < NN; ++k) {
-    S lk;
     if (FUSED) {
-      S d = __shfl_sync(FULL, a[k], k);
-      ok = ok && (d > S(0));
-      S inv = rsqrt_(d);
-      lk = a[k] * inv;
+      const S d = __shfl_sync(FULL, a[k], k);
+      ok = ok && (d > S(0)) && (d < S(1e30));
+      const S inv = rsqrt_(d);
+      const S lk = a[k] * inv;
       a[k] = (lane == k) ? inv : lk;
+      if (k + 1 < NN) {
+        S* col = colbuf + (k & 1) * 32;
+        col[lane] = lk;
+        __syncwarp();
+        // pivot column: one scalar head (odd start), 16-byte pairs, one scalar tail (odd NN)
+        constexpr bool kVec = !ALMPC_NO_VEC2;
+        const int j0 = k + 1;
+        const int js = kVec ? ((j0 + 1) & ~1) : NN;  // first even index >= j0
+        if (kVec && (j0 & 1) && j0 < NN) a[j0] -= lk * col[j0];
 #pragma unroll
-      for (int j = k + 1; j < NN; ++j) {
-        S ljk = __shfl_sync(FULL, lk, j);
-        a[j] -= lk * ljk;
+        for (int j = 0; j < NN; j += 2) {
+          if (kVec && j >= js && j + 1 < NN) {
+            const Vec2<S> v = *reinterpret_cast<const Vec2<S>*>(col + j);
+            a[j] -= lk * v.x;
+            a[j + 1] -= lk * v.y;
+          }
+        }
+        if (kVec && (NN & 1) && (NN - 1) >= js) a[NN - 1] -= lk * col[NN - 1];
+        if (!kVec) {
+#pragma unroll
+          for (int j = 0; j < NN; ++j)
+            if (j >= j0) a[j] -= lk * col[j];
+        }
       }
     } else {
-      S inv = __shfl_sync(FULL, a[k], k);
-      lk = a[k] * inv;
+      const S inv = colbuf[k * LDL + k];
+      const S lk = a[k] * inv;
       if (lane >= NN) a[k] = lk;
 #pragma unroll
       for (int j = k + 1; j < NN; ++j) {
-        S ljk = __shfl_sync(FULL, a[k], j);
-        if (lane >= NN) a[j] -= lk * ljk;
+        if (lane >= NN) a[j] -= lk * colbuf[j * LDL + k];
       }
     }
   }
@@ -278,98 +374,6 @@ __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, 
   }
 }
 
-template <int NX, int NU, typename S>
-__device__ __forceinline__ bool forward_sweep_factor(S* sm, const Layout<NX, NU>& L, int T, int lane, S rho,
-                                                     const S* __restrict__ Qd_g, const S* ulo, const S* uhi,
-                                                     S* fac) {
-  constexpr int NN = NX + NU;
-  constexpr int LD = ScrLd<NN>::LD;
-  constexpr int EX0 = 32 - NN - 1;  // sub-diagonal rows that fit next to L rows and the rhs row
-  S* xu = sm + L.xu;
-  S* dv = sm + L.dv;
-  S* G = sm + L.G;
-  S* scr = sm + L.scr;
-  bool ok = true;
-  for (int t = 0; t < T; ++t) {
-    const S* Gt = G + (size_t)t * NX * NN;          // valid for t < T-1
-    const S* Ep = G + (size_t)(t - 1) * NX * NN;    // E_{t-1}, valid for t > 0
-    S* Lg = fac + (size_t)t * NN * NN;
-    S* Eg = fac + (size_t)T * NN * NN + (size_t)t * NX * NN;
-    // ---- (a) D_t (lower part) into scr; rhs_t -= E_{t-1} y_{t-1}
-    build_block<NX, NU, S>(scr, xu + t * NN, Gt, Ep, t < T - 1, t > 0, lane, rho, Qd_g + t * NN, ulo, uhi);
-    if (t > 0) {
-      for (int r = lane; r < NX; r += 32) {
-        S s0 = S(0), s1 = S(0);
-#pragma unroll
-        for (int k = 0; k + 1 < NN; k += 2) {
-          s0 += Ep[r * NN + k] * dv[(t - 1) * NN + k];
-          s1 += Ep[r * NN + k + 1] * dv[(t - 1) * NN + k + 1];
-        }
-        if (NN & 1) s0 += Ep[r * NN + NN - 1] * dv[(t - 1) * NN + NN - 1];
-        dv[t * NN + r] -= s0 + s1;
-      }
-    }
-    __syncwarp();
-    // ---- (b) rows into registers
-    S a[NN];
-    if (lane < NN) {
-#pragma unroll
-      for (int c = 0; c < NN; ++c) a[c] = (c <= lane) ? scr[lane * LD + c] : S(0);
-    } else if (lane == NN) {
-#pragma unroll
-      for (int c = 0; c < NN; ++c) a[c] = dv[t * NN + c];
-    } else {
-      const int i = lane - NN - 1;
-      const bool act = (i < NX) && (t < T - 1);
-#pragma unroll
-      for (int c = 0; c < NN; ++c) a[c] = act ? -rho * Gt[i * NN + c] : S(0);
-    }
-    // ---- (c) factor + forward substitution + trsm in one elimination
-    ok = eliminate<NN, true>(a, lane) && ok;
-    __syncwarp();
-    // ---- (d) write-outs straight from registers: L rows -> global, y -> dv, E rows -> smem + global
-    if (lane < NN) {
-#pragma unroll
-      for (int c = 0; c < NN; ++c) Lg[lane * NN + c] = (c <= lane) ? a[c] : S(0);
-    } else if (lane == NN) {
-#pragma unroll
-      for (int c = 0; c < NN; ++c) dv[t * NN + c] = a[c];
-    } else {
-      const int i = lane - NN - 1;
-      if (i < NX && t < T - 1) {
-        S* Et = G + (size_t)t * NX * NN;
-#pragma unroll
-        for (int c = 0; c < NN; ++c) {
-          Et[i * NN + c] = a[c];
-          Eg[i * NN + c] = a[c];
-        }
-      }
-    }
-    if (NX > EX0 && t < T - 1) {  // sub-diagonal rows that did not fit (e.g. flying cartpole nx=14, n=18)
-      constexpr int PER = 32 - NN;
-      for (int base = EX0; base < NX; base += PER) {
-        const int i = base + (lane - NN);
-        const bool act = (lane >= NN) && (i < NX);
-        if (lane >= NN) {
-#pragma unroll
-          for (int c = 0; c < NN; ++c) a[c] = act ? -rho * Gt[i * NN + c] : S(0);
-        }
-        eliminate<NN, false>(a, lane);
-        if (act) {
-          S* Et = G + (size_t)t * NX * NN;
-#pragma unroll
-          for (int c = 0; c < NN; ++c) {
-            Et[i * NN + c] = a[c];
-            Eg[i * NN + c] = a[c];
-          }
-        }
-      }
-    }
-    __syncwarp();
-  }
-  return ok;
-}
-
 // forward substitution only, from a stored factor (backward pass): dv = L^{-1} dv
 template <int NX, int NU, typename S>
 __device__ __forceinline__ void forward_sweep_stored(S* dv, S* Esm, int T, int lane, const S* fac) {
@@ -450,307 +454,526 @@ __device__ __forceinline__ void backward_sweep(S* dv, const S* Esm_all, S* Etmp,
 }
 
 // ------------------------------------------------------------------------------------------------
-// the Newton-step kernel
+// kernel 1/3: dynamics + Jacobian columns.  1 thread = 1 (problem, stage t, column j of G_t = [A_t B_t]).
+//   G_g[prob][t][i][j] = d f_i / d z_j at (x_t,u_t) ; c_g[prob][t*nx+i] = x_{t+1,i} - f_i ; last block: x_0 - x0
 // ------------------------------------------------------------------------------------------------
-template <class M, typename S, int WPB>
-__global__ void __launch_bounds__(WPB * 32, 4)
-k_newton_step(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__ Qd_g, const S* __restrict__ q_g,
-              S* __restrict__ xu_g, S* __restrict__ lam_g, S* __restrict__ rho_g, S* __restrict__ fac_g,
-              int* __restrict__ status_g, int* __restrict__ info_g, S* __restrict__ debug_g, Ctl* ctl,
-              double* __restrict__ partials, S* __restrict__ merit_g) {
+template <class M, typename S>
+__global__ void __launch_bounds__(128)
+k_jacobian(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__ xu_g, S* __restrict__ G_g,
+           S* __restrict__ c_g, const Ctl* __restrict__ ctl) {
   constexpr int NX = M::NX, NU = M::NU, NN = NX + NU;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double red[WPB][3];
+  if (ctl->mode == MODE_DONE) return;
+  const int T = P.T;
+  const int IT = (T - 1) * NN;
+  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long)P.B * IT) return;
+  const int prob = (int)(gid / IT);
+  const int it = (int)(gid - (long)prob * IT);
+  const int t = it / NN, j = it - t * NN;
+  const S* xz = xu_g + (size_t)prob * T * NN + (size_t)t * NN;
+  Dual<S> xd[NX], ud[NU], xn[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) xd[i] = Dual<S>(xz[i], (i == j) ? S(1) : S(0));
+#pragma unroll
+  for (int i = 0; i < NU; ++i) ud[i] = Dual<S>(xz[NX + i], (NX + i == j) ? S(1) : S(0));
+  rk4_step<M, S, Dual<S>>(xd, ud, xn, P.dyn);
+  S* Gp = G_g + ((size_t)prob * (T - 1) + t) * NX * NN;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) Gp[i * NN + j] = xn[i].d;
+  S* cp = c_g + (size_t)prob * T * NX;
+  if (j == 0) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) cp[t * NX + i] = xz[NN + i] - xn[i].v;
+  }
+  if (it == IT - 1) {  // the x_0 - x0 block (al_utils.py:219)
+    const S* z0 = xu_g + (size_t)prob * T * NN;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) cp[(T - 1) * NX + i] = z0[i] - x0_g[(size_t)prob * NX + i];
+  }
+}
 
+// ------------------------------------------------------------------------------------------------
+// kernel 2/3: residual statistics, dual update, merit, gradient, block-tridiagonal factor + solve.
+// 1 warp = 1 problem.
+// ------------------------------------------------------------------------------------------------
+template <int NX, int NU, typename S, int WPB>
+__global__ void __launch_bounds__(WPB * 32, 7)
+k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restrict__ q_g, const S* __restrict__ xu_g,
+               S* __restrict__ lam_g, S* __restrict__ rho_g, S* fac_g, const S* __restrict__ G_g,
+               const S* __restrict__ c_g, S* __restrict__ d_g, S* __restrict__ merit_g, double* __restrict__ rentry_g,
+               int* __restrict__ status_g, S* __restrict__ debug_g, const Ctl* __restrict__ ctl) {
+  constexpr int NN = NX + NU;
+  constexpr int LD = ScrLd<NN>::LD;
+  constexpr int EX0 = 32 - NN - 1;  // sub-diagonal rows that fit next to the L rows and the rhs row
+  constexpr int CW = CopyWidth<NX, NU, S>::W;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int mode = ctl->mode;
   if (mode == MODE_DONE) return;
-  const int al_a = ctl->a, nk = ctl->k;
-
   const int T = P.T;
   const Layout<NX, NU> L(T);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int prob = blockIdx.x * WPB + warp;
+  if (prob >= P.B) return;
   S* sm = reinterpret_cast<S*>(smem_raw) + (size_t)warp * L.total;
   S* xu = sm + L.xu;
   S* dv = sm + L.dv;
-  S* lam = sm + L.lam;
-  S* cres = sm + L.c;
   S* wv = sm + L.w;
-  S* x0 = sm + L.x0;
-  S* G = sm + L.G;
+  S* Gt = sm + L.Gt;
+  S* Ep = sm + L.Ep;
   S* scr = sm + L.scr;
-  const S* dyn = P.dyn;
+  const size_t pN = (size_t)prob * L.N;
+  const S* Qd = Qd_g + pN;
+  const S* qv = q_g + pN;
+  S* lam = lam_g + (size_t)prob * L.m;
+  const S* cres = c_g + (size_t)prob * L.neq;
+  const S* Gp = G_g + (size_t)prob * (T - 1) * NX * NN;
+  S* fac = fac_g + (size_t)prob * factor_elems<NX, NU>(T);
+  S* dbg = debug_g ? debug_g + (size_t)prob * (2 * L.N + 24) : nullptr;
 
-  double r_entry = 0.0, r_exit = 0.0, rho_used = 0.0;
+  if (T > 1) warp_copy_async<NX * NN, CW>(Gt, Gp, lane);  // G_0, consumed after the residual statistics
+  cp_async_commit();
+  for (int i = lane; i < L.N; i += 32) xu[i] = xu_g[pN + i];
+  S rho = rho_g[prob];
+  __syncwarp();
 
-  if (prob < P.B) {
-    const size_t pN = (size_t)prob * L.N;
-    const S* Qd = Qd_g + pN;
-    const S* qv = q_g + pN;
-    // ---------------------------------------------------------------- P0 load
-    for (int i = lane; i < L.N; i += 32) xu[i] = xu_g[pN + i];
-    for (int i = lane; i < L.m; i += 32) lam[i] = lam_g[(size_t)prob * L.m + i];
-    for (int i = lane; i < NX; i += 32) x0[i] = x0_g[(size_t)prob * NX + i];
-    S rho = rho_g[prob];
-    S merit_cur = (mode == MODE_CONT) ? merit_g[prob] : S(0);
-    int status = (mode == MODE_FIRST) ? (ALMPC_STATUS_FINITE | ALMPC_STATUS_CHOL_OK) : status_g[prob];
-    __syncwarp();
-
-    // ---------------------------------------------------------------- P1 dynamics + Jacobian columns
-    for (int it = lane; it < (T - 1) * NN; it += 32) {
-      const int t = it / NN, j = it - t * NN;
-      Dual<S> xd[NX], ud[NU], xn[NX];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) xd[i] = Dual<S>(xu[t * NN + i], (i == j) ? S(1) : S(0));
-#pragma unroll
-      for (int i = 0; i < NU; ++i) ud[i] = Dual<S>(xu[t * NN + NX + i], (NX + i == j) ? S(1) : S(0));
-      rk4_step<M, S, Dual<S>>(xd, ud, xn, dyn);
-#pragma unroll
-      for (int i = 0; i < NX; ++i) G[(size_t)t * NX * NN + i * NN + j] = xn[i].d;
-      if (j == 0) {
-#pragma unroll
-        for (int i = 0; i < NX; ++i) cres[t * NX + i] = xu[(t + 1) * NN + i] - xn[i].v;
-      }
+  // ---- dual / penalty update of the previous AL iteration (AL_mpc.py:316-317,325)
+  if (mode == MODE_DUAL_NEWTON) {
+    for (int i = lane; i < L.neq; i += 32) lam[i] += rho * cres[i];
+    for (int i = lane; i < L.nin; i += 32) {
+      const int t = i / (2 * NU), s = i - t * 2 * NU;
+      const S u = xu[t * NN + NX + (s < NU ? s : s - NU)];
+      const S ci = (s < NU) ? (u - P.uhi[s]) : (P.ulo[s - NU] - u);
+      lam[L.neq + i] = fmax0(lam[L.neq + i] + rho * ci);
     }
-    for (int i = lane; i < NX; i += 32) cres[(T - 1) * NX + i] = xu[i] - x0[i];
+    rho = next_rho(rho, P.rho_mult, P.rho_f32);
+    if (lane == 0) rho_g[prob] = rho;
     __syncwarp();
+  }
+  // ---- entry residual ||c+||^2, merit at the entry point, w = lam_eq + rho c
+  {
+    S s2 = S(0), sl = S(0), cost = S(0);
+    for (int i = lane; i < L.neq; i += 32) {
+      const S ci = cres[i], li = lam[i];
+      s2 += ci * ci;
+      sl += li * ci;
+      wv[i] = li + rho * ci;
+    }
+    for (int i = lane; i < L.nin; i += 32) {
+      const int t = i / (2 * NU), s = i - t * 2 * NU;
+      const S u = xu[t * NN + NX + (s < NU ? s : s - NU)];
+      const S ci = (s < NU) ? (u - P.uhi[s]) : (P.ulo[s - NU] - u);
+      const S cp = fmax0(ci);
+      s2 += cp * cp;
+      sl += lam[L.neq + i] * ci;
+    }
+    for (int i = lane; i < L.N; i += 32) {
+      const S z = xu[i];
+      cost += S(0.5) * (z * Qd[i] * z) + qv[i] * z;
+    }
+    s2 = warp_sum(s2);
+    sl = warp_sum(sl);
+    cost = warp_sum(cost);
+    if (lane == 0) {
+      rentry_g[prob] = (double)s2;
+      if (mode != MODE_CONT) merit_g[prob] = cost + S(0.5) * rho * s2 + sl;
+    }
+  }
+  __syncwarp();
 
-    // ---------------------------------------------------------------- P2 dual update / merit / entry residual
-    if (mode == MODE_DUAL_NEWTON) {
-      // lam <- lam + rho c ; lam_ineq <- max(0, .) ; rho <- 10 rho        (AL_mpc.py:316-317,325)
-      for (int i = lane; i < L.neq; i += 32) lam[i] += rho * cres[i];
-      for (int i = lane; i < L.nin; i += 32) {
-        int t = i / (2 * NU), s = i - t * 2 * NU;
-        S u = xu[t * NN + NX + (s < NU ? s : s - NU)];
-        S ci = (s < NU) ? (u - P.uhi[s]) : (P.ulo[s - NU] - u);
-        lam[L.neq + i] = fmax0(lam[L.neq + i] + rho * ci);
-      }
-      rho = next_rho(rho, P.rho_mult, P.rho_f32);
-      __syncwarp();
-      for (int i = lane; i < L.m; i += 32) lam_g[(size_t)prob * L.m + i] = lam[i];
-      if (lane == 0) rho_g[prob] = rho;
-    }
-    rho_used = (double)rho;
-    {
-      S s2 = S(0), sl = S(0), cost = S(0);
-      for (int i = lane; i < L.neq; i += 32) {
-        S ci = cres[i];
-        s2 += ci * ci;
-        sl += lam[i] * ci;
-        wv[i] = lam[i] + rho * ci;
-      }
-      for (int i = lane; i < L.nin; i += 32) {
-        int t = i / (2 * NU), s = i - t * 2 * NU;
-        S u = xu[t * NN + NX + (s < NU ? s : s - NU)];
-        S ci = (s < NU) ? (u - P.uhi[s]) : (P.ulo[s - NU] - u);
-        S cp = fmax0(ci);
-        s2 += cp * cp;
-        sl += lam[L.neq + i] * ci;
-      }
-      for (int i = lane; i < L.N; i += 32) {
-        S z = xu[i];
-        cost += S(0.5) * (z * Qd[i] * z) + qv[i] * z;
-      }
-      s2 = warp_sum(s2);
-      sl = warp_sum(sl);
-      cost = warp_sum(cost);
-      r_entry = (double)s2;
-      if (mode != MODE_CONT) merit_cur = cost + S(0.5) * rho * s2 + sl;
-    }
+  // ---- forward sweep over the stages: gradient, Hessian block, fused elimination.
+  // Two block buffers ping-pong: X holds G_t (prefetched) and is overwritten by E_t; Y holds E_{t-1} and,
+  // once its last reader is done, receives the prefetch of G_{t+1}.
+  bool ok = true;
+  S* X = Gt;
+  S* Y = Ep;
+  for (int t = 0; t < T; ++t) {
+    S* Lg = fac + (size_t)t * NN * NN;
+    S* Eg = fac + (size_t)T * NN * NN + (size_t)t * NX * NN;
+    const bool has_G = t < T - 1, has_E = t > 0;
+    cp_async_wait_all();  // G_t (issued one stage ago / in the prologue)
     __syncwarp();
-
-    // ---------------------------------------------------------------- P3 gradient -> dv
-    for (int idx = lane; idx < L.N; idx += 32) {
-      const int t = idx / NN, j = idx - t * NN;
+    // gradient of stage t (al_utils.py:113-117) minus the coupling E_{t-1} y_{t-1}
+    if (lane < NN) {
+      const int j = lane, idx = t * NN + j;
       S g = Qd[idx] * xu[idx] + qv[idx];
-      if (t < T - 1) {
-        const S* Gt = G + (size_t)t * NX * NN;
-        S s = S(0);
+      if (has_G) {
+        S s0 = S(0), s1 = S(0);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) s += Gt[i * NN + j] * wv[t * NX + i];
-        g -= s;
+        for (int i = 0; i + 1 < NX; i += 2) {
+          s0 += X[i * NN + j] * wv[t * NX + i];
+          s1 += X[(i + 1) * NN + j] * wv[t * NX + i + 1];
+        }
+        if (NX & 1) s0 += X[(NX - 1) * NN + j] * wv[t * NX + NX - 1];
+        g -= s0 + s1;
       }
       if (j < NX) {
-        g += (t > 0) ? wv[(t - 1) * NX + j] : wv[(T - 1) * NX + j];
+        g += has_E ? wv[(t - 1) * NX + j] : wv[(T - 1) * NX + j];
       } else {
-        int s = j - NX;
-        S u = xu[idx];
-        S cu = u - P.uhi[s], cl = P.ulo[s] - u;
-        S lu = lam[L.neq + t * 2 * NU + s], ll = lam[L.neq + t * 2 * NU + NU + s];
+        const int sidx = j - NX;
+        const S u = xu[idx];
+        const S cu = u - P.uhi[sidx], cl = P.ulo[sidx] - u;
+        const S lu = lam[L.neq + t * 2 * NU + sidx], ll = lam[L.neq + t * 2 * NU + NU + sidx];
         g += (lu - ll) + rho * (fmax0(cu) - fmax0(cl));
       }
+      if (dbg) dbg[idx] = g;
+      if (has_E && j < NX) {
+        S s0 = S(0), s1 = S(0);
+#pragma unroll
+        for (int k = 0; k + 1 < NN; k += 2) {
+          s0 += Y[j * NN + k] * dv[(t - 1) * NN + k];
+          s1 += Y[j * NN + k + 1] * dv[(t - 1) * NN + k + 1];
+        }
+        if (NN & 1) s0 += Y[j * NN + NN - 1] * dv[(t - 1) * NN + NN - 1];
+        g -= s0 + s1;
+      }
       dv[idx] = g;
-      if (debug_g) debug_g[(size_t)prob * (2 * L.N + 24) + idx] = g;
     }
+    build_block<NX, NU, S>(scr + 64, xu + t * NN, X, Y, has_G, has_E, lane, rho, Qd + t * NN, P.ulo, P.uhi);
     __syncwarp();
-
-    // ---------------------------------------------------------------- P4 factor + solve
-    S* fac = fac_g + (size_t)prob * factor_elems<NX, NU>(T);
-    bool ok = forward_sweep_factor<NX, NU, S>(sm, L, T, lane, rho, Qd, P.ulo, P.uhi, fac);
-    ok = __all_sync(FULL, ok);
-    if (!ok) status &= ~ALMPC_STATUS_CHOL_OK;
-    backward_sweep<NX, NU, S>(dv, G, nullptr, T, lane, fac);
-    for (int i = lane; i < L.N; i += 32) {
-      S d = -dv[i];
-      dv[i] = d;
-      if (debug_g) debug_g[(size_t)prob * (2 * L.N + 24) + L.N + i] = d;
+    // rows into registers: L rows | rhs | -rho G_t rows
+    S a[NN];
+    if (lane < NN) {
+#pragma unroll
+      for (int c = 0; c < NN; ++c) a[c] = (c <= lane) ? scr[64 + lane * LD + c] : S(0);
+    } else if (lane == NN) {
+#pragma unroll
+      for (int c = 0; c < NN; ++c) a[c] = dv[t * NN + c];
+    } else {
+      const int i = lane - NN - 1;
+      const bool act = (i < NX) && has_G;
+#pragma unroll
+      for (int c = 0; c < NN; ++c) a[c] = act ? -rho * X[i * NN + c] : S(0);
     }
+    __syncwarp();  // Y (E_{t-1}) has no reader left: prefetch G_{t+1} into it behind the pivot chain
+    if (t + 1 < T - 1) warp_copy_async<NX * NN, CW>(Y, Gp + (size_t)(t + 1) * NX * NN, lane);
+    cp_async_commit();
+    ok = eliminate<NN, true>(a, lane, scr) && ok;
     __syncwarp();
-
-    // ---------------------------------------------------------------- P5 line search
-    S* part = scr;                       // [NLS][(T-1)][3]
-    for (int it = lane; it < NLS * (T - 1); it += 32) {
-      const int kk = it / (T - 1), t = it - kk * (T - 1);
-      const S alpha = (S)ldexpf(1.0f, -kk);
-      S xs[NX], us[NU], xn[NX];
-      S cost = S(0), s2 = S(0), sl = S(0);
+    if (lane < NN) {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) {
-        S z = xu[t * NN + i] + alpha * dv[t * NN + i];
-        xs[i] = z;
-        cost += S(0.5) * (z * Qd[t * NN + i] * z) + qv[t * NN + i] * z;
+      for (int c = 0; c < NN; ++c) Lg[lane * NN + c] = (c <= lane) ? a[c] : S(0);
+      if (NX > EX0 && has_G) {  // publish L for the second elimination pass
+#pragma unroll
+        for (int c = 0; c < NN; ++c) scr[64 + lane * LD + c] = a[c];
       }
+    } else if (lane == NN) {
 #pragma unroll
-      for (int i = 0; i < NU; ++i) {
-        S z = xu[t * NN + NX + i] + alpha * dv[t * NN + NX + i];
-        us[i] = z;
-        cost += S(0.5) * (z * Qd[t * NN + NX + i] * z) + qv[t * NN + NX + i] * z;
-        S cu = z - P.uhi[i], cl = P.ulo[i] - z;
-        sl += lam[L.neq + t * 2 * NU + i] * cu + lam[L.neq + t * 2 * NU + NU + i] * cl;
-        S pu = fmax0(cu), pl = fmax0(cl);
-        s2 += pu * pu + pl * pl;
-      }
-      if (t == 0) {
+      for (int c = 0; c < NN; ++c) dv[t * NN + c] = a[c];
+    } else {
+      const int i = lane - NN - 1;
+      if (i < NX && has_G && NX <= EX0) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) {
-          S ci = xs[i] - x0[i];
-          s2 += ci * ci;
-          sl += lam[(T - 1) * NX + i] * ci;
+        for (int c = 0; c < NN; ++c) {
+          X[i * NN + c] = a[c];
+          Eg[i * NN + c] = a[c];
         }
       }
-      rk4_step<M, S, S>(xs, us, xn, dyn);
+    }
+    if (NX > EX0 && has_G) {  // sub-diagonal rows that did not fit (flying cartpole: nx=14, n=18)
+      // rows of the first pass are parked in registers until every row of -rho G_t has been read from X
+      S keep[NN];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) {
-        S z1 = xu[(t + 1) * NN + i] + alpha * dv[(t + 1) * NN + i];
-        S ci = z1 - xn[i];
-        s2 += ci * ci;
-        sl += lam[t * NX + i] * ci;
-        if (t == T - 2) cost += S(0.5) * (z1 * Qd[(t + 1) * NN + i] * z1) + qv[(t + 1) * NN + i] * z1;
-      }
-      if (t == T - 2) {
+      for (int c = 0; c < NN; ++c) keep[c] = a[c];
+      const int i0 = lane - NN - 1;
+      constexpr int PER = 32 - NN;
+      for (int base = EX0; base < NX; base += PER) {
+        const int i = base + (lane - NN);
+        const bool act = (lane >= NN) && (i < NX);
+        if (lane >= NN) {
 #pragma unroll
-        for (int i = 0; i < NU; ++i) {
-          const int e = (T - 1) * NN + NX + i;
-          S z = xu[e] + alpha * dv[e];
-          cost += S(0.5) * (z * Qd[e] * z) + qv[e] * z;
-          S cu = z - P.uhi[i], cl = P.ulo[i] - z;
-          sl += lam[L.neq + (T - 1) * 2 * NU + i] * cu + lam[L.neq + (T - 1) * 2 * NU + NU + i] * cl;
-          S pu = fmax0(cu), pl = fmax0(cl);
-          s2 += pu * pu + pl * pl;
+          for (int c = 0; c < NN; ++c) a[c] = act ? -rho * X[i * NN + c] : S(0);
+        }
+        __syncwarp();
+        eliminate<NN, false>(a, lane, scr + 64, LD);
+        __syncwarp();
+        if (act) {
+#pragma unroll
+          for (int c = 0; c < NN; ++c) {
+            X[i * NN + c] = a[c];
+            Eg[i * NN + c] = a[c];
+          }
         }
       }
-      part[it * 3 + 0] = cost;
-      part[it * 3 + 1] = s2;
-      part[it * 3 + 2] = sl;
+      if (lane > NN && i0 < NX) {
+#pragma unroll
+        for (int c = 0; c < NN; ++c) {
+          X[i0 * NN + c] = keep[c];
+          Eg[i0 * NN + c] = keep[c];
+        }
+      }
     }
     __syncwarp();
-    S mk = S(0), r2k = S(0);
-    if (lane < NLS) {
-      S cost = S(0), s2 = S(0), sl = S(0);
-      for (int t = 0; t < T - 1; ++t) {
-        cost += part[(lane * (T - 1) + t) * 3 + 0];
-        s2 += part[(lane * (T - 1) + t) * 3 + 1];
-        sl += part[(lane * (T - 1) + t) * 3 + 2];
-      }
-      mk = cost + S(0.5) * rho * s2 + sl;
-      r2k = s2;
-      if (debug_g) debug_g[(size_t)prob * (2 * L.N + 24) + 2 * L.N + lane] = mk;
-    }
-    // first-argmin with torch.min NaN semantics (any NaN -> NaN, step rejected)
-    const bool isn = (lane < NLS) && (mk != mk);
-    const bool any_nan = __any_sync(FULL, isn);
-    S bv = (lane < NLS) ? mk : S(INFINITY);
-    int bi = (lane < NLS) ? lane : NLS;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      S ov = __shfl_xor_sync(FULL, bv, o);
-      int oi = __shfl_xor_sync(FULL, bi, o);
-      if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    if (bi >= NLS) bi = 0;  // all +inf
-    S r2_best = __shfl_sync(FULL, r2k, bi);
-    if (any_nan) bv = S(NAN);
-    const bool accept = bv < merit_cur;
-    const S alpha = (S)ldexpf(1.0f, -bi);
-    bool fin = true;
-    for (int i = lane; i < L.N; i += 32) {
-      S xo = xu[i];
-      S xnew = xo + alpha * dv[i];
-      S xr = accept ? xnew : (finite_(xnew) ? xo : S(NAN));  // status*x_next + (1-status)*x_est, al_utils.py:640-641
-      fin = fin && finite_(xr);
-      xu_g[pN + i] = xr;
-    }
-    fin = __all_sync(FULL, fin);
-    if (!fin) status &= ~ALMPC_STATUS_FINITE;
-    r_exit = accept ? (double)r2_best : (fin ? r_entry : (double)NAN);
-    if (lane == 0) {
-      merit_g[prob] = bv;  // merit <- new_merit even when the step was rejected (al_utils.py:569)
-      status_g[prob] = status;
-      if (debug_g) {
-        S* dbg = debug_g + (size_t)prob * (2 * L.N + 24) + 2 * L.N + NLS;
-        dbg[0] = (S)bi;
-        dbg[1] = accept ? S(1) : S(0);
-        dbg[2] = merit_cur;
-      }
-    }
+    S* tmp = X; X = Y; Y = tmp;  // Y := E_t, X := G_{t+1}
   }
-
-  // ------------------------------------------------------------------ P6 batch-global statistics
+  ok = __all_sync(FULL, ok);
+  // ---- backward sweep, d = -H^{-1} g.  L_tt / E_t come back from the streamed factor (L2) through
+  // cp.async: the blocks of stage t-1 are in flight while the substitution of stage t runs.
+  cp_async_wait_all();
+  __syncwarp();
+  S* Lsm = scr + 64;                    // [NN][NN] row-major copy of L_tt
+  S* Ecur = X;                          // E_t
+  S* Enext = Y;
+  warp_copy_async<NN * NN, CW>(Lsm, fac + (size_t)(T - 1) * NN * NN, lane);
+  cp_async_commit();
+  for (int t = T - 1; t >= 0; --t) {
+    cp_async_wait_all();
+    __syncwarp();
+    S l[NN];
+    if (lane < NN) {
+#pragma unroll
+      for (int r = 0; r < NN; ++r) l[r] = (r >= lane) ? Lsm[r * NN + lane] : S(0);
+    }
+    S b = (lane < NN) ? dv[t * NN + lane] : S(0);
+    if (t < T - 1 && lane < NN) {
+      S s0 = S(0), s1 = S(0);
+#pragma unroll
+      for (int i = 0; i + 1 < NX; i += 2) {
+        s0 += Ecur[i * NN + lane] * dv[(t + 1) * NN + i];
+        s1 += Ecur[(i + 1) * NN + lane] * dv[(t + 1) * NN + i + 1];
+      }
+      if (NX & 1) s0 += Ecur[(NX - 1) * NN + lane] * dv[(t + 1) * NN + NX - 1];
+      b -= s0 + s1;
+    }
+    __syncwarp();
+    if (t > 0) {
+      warp_copy_async<NN * NN, CW>(Lsm, fac + (size_t)(t - 1) * NN * NN, lane);
+      warp_copy_async<NX * NN, CW>(Enext, fac + (size_t)T * NN * NN + (size_t)(t - 1) * NX * NN, lane);
+    }
+    cp_async_commit();
+#pragma unroll
+    for (int r = NN - 1; r >= 0; --r) {
+      const S dr = __shfl_sync(FULL, b * l[r], r);  // lane r: l[r] = 1/L_rr
+      if (lane == r) b = dr;
+      else if (lane < r) b -= l[r] * dr;
+    }
+    if (lane < NN) dv[t * NN + lane] = b;
+    S* tmp = Ecur; Ecur = Enext; Enext = tmp;
+  }
+  __syncwarp();
+  for (int i = lane; i < L.N; i += 32) {
+    const S d = -dv[i];
+    d_g[pN + i] = d;
+    if (dbg) dbg[L.N + i] = d;
+  }
   if (lane == 0) {
-    red[warp][0] = r_entry;
-    red[warp][1] = r_exit;
-    red[warp][2] = rho_used;
+    int status = (mode == MODE_FIRST) ? (ALMPC_STATUS_FINITE | ALMPC_STATUS_CHOL_OK) : status_g[prob];
+    if (!ok) status &= ~ALMPC_STATUS_CHOL_OK;
+    status_g[prob] = status;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 3/3: 20-point line search + iterate update + batch-global stop statistics / control block.
+// 1 thread = 1 (problem, candidate k, stage t); `pls` problems per CTA.
+// ------------------------------------------------------------------------------------------------
+template <class M, typename S>
+__global__ void __launch_bounds__(256, 2)
+k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, const S* __restrict__ Qd_g,
+              const S* __restrict__ q_g, S* __restrict__ xu_g, const S* __restrict__ lam_g,
+              const S* __restrict__ rho_g, const S* __restrict__ d_g, S* __restrict__ merit_g,
+              const double* __restrict__ rentry_g, int* __restrict__ status_g, int* __restrict__ info_g,
+              S* __restrict__ debug_g, Ctl* ctl, double* __restrict__ partials) {
+  constexpr int NX = M::NX, NU = M::NU, NN = NX + NU;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[8][3];
+  __shared__ bool is_last;
+  const int mode = ctl->mode;
+  if (mode == MODE_DONE) return;
+  const int al_a = ctl->a, nk = ctl->k;
+  const int T = P.T;
+  const LsLayout<NX, NU> L(T);
+  const int IT = NLS * (T - 1);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int prob0 = blockIdx.x * pls;
+  S* smem = reinterpret_cast<S*>(smem_raw);
+
+  // cooperative, coalesced staging of the CTA's problems
+  for (int p = 0; p < pls; ++p) {
+    const int prob = prob0 + p;
+    if (prob >= P.B) break;
+    S* sp = smem + (size_t)p * L.total;
+    const size_t pN = (size_t)prob * L.N;
+    for (int i = tid; i < L.N; i += nthr) {
+      sp[L.xu + i] = xu_g[pN + i];
+      sp[L.d + i] = d_g[pN + i];
+      sp[L.Qd + i] = Qd_g[pN + i];
+      sp[L.q + i] = q_g[pN + i];
+    }
+    for (int i = tid; i < L.m; i += nthr) sp[L.lam + i] = lam_g[(size_t)prob * L.m + i];
+    for (int i = tid; i < NX; i += nthr) sp[L.x0 + i] = x0_g[(size_t)prob * NX + i];
   }
   __syncthreads();
-  __shared__ bool is_last;
-  if (threadIdx.x == 0) {
+
+  for (int wi = tid; wi < pls * IT; wi += nthr) {
+    const int p = wi / IT, it = wi - p * IT;
+    if (prob0 + p >= P.B) continue;
+    const S* sp = smem + (size_t)p * L.total;
+    const S* xu = sp + L.xu;
+    const S* dv = sp + L.d;
+    const S* lam = sp + L.lam;
+    const S* Qd = sp + L.Qd;
+    const S* qv = sp + L.q;
+    const S* x0 = sp + L.x0;
+    S* part = const_cast<S*>(sp) + L.part;
+    const int kk = it / (T - 1), t = it - kk * (T - 1);
+    const S alpha = (S)ldexpf(1.0f, -kk);
+    S xs[NX], us[NU], xn[NX];
+    S cost = S(0), s2 = S(0), sl = S(0);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      const S z = xu[t * NN + i] + alpha * dv[t * NN + i];
+      xs[i] = z;
+      cost += S(0.5) * (z * Qd[t * NN + i] * z) + qv[t * NN + i] * z;
+    }
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      const S z = xu[t * NN + NX + i] + alpha * dv[t * NN + NX + i];
+      us[i] = z;
+      cost += S(0.5) * (z * Qd[t * NN + NX + i] * z) + qv[t * NN + NX + i] * z;
+      const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
+      sl += lam[L.neq + t * 2 * NU + i] * cu + lam[L.neq + t * 2 * NU + NU + i] * cl;
+      const S pu = fmax0(cu), pl = fmax0(cl);
+      s2 += pu * pu + pl * pl;
+    }
+    if (t == 0) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        const S ci = xs[i] - x0[i];
+        s2 += ci * ci;
+        sl += lam[(T - 1) * NX + i] * ci;
+      }
+    }
+    rk4_step<M, S, S>(xs, us, xn, P.dyn);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      const S z1 = xu[(t + 1) * NN + i] + alpha * dv[(t + 1) * NN + i];
+      const S ci = z1 - xn[i];
+      s2 += ci * ci;
+      sl += lam[t * NX + i] * ci;
+      if (t == T - 2) cost += S(0.5) * (z1 * Qd[(t + 1) * NN + i] * z1) + qv[(t + 1) * NN + i] * z1;
+    }
+    if (t == T - 2) {
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        const int e = (T - 1) * NN + NX + i;
+        const S z = xu[e] + alpha * dv[e];
+        cost += S(0.5) * (z * Qd[e] * z) + qv[e] * z;
+        const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
+        sl += lam[L.neq + (T - 1) * 2 * NU + i] * cu + lam[L.neq + (T - 1) * 2 * NU + NU + i] * cl;
+        const S pu = fmax0(cu), pl = fmax0(cl);
+        s2 += pu * pu + pl * pl;
+      }
+    }
+    part[it * 3 + 0] = cost;
+    part[it * 3 + 1] = s2;
+    part[it * 3 + 2] = sl;
+  }
+  __syncthreads();
+
+  // one warp per problem: candidate sums, first-argmin, accept, iterate update
+  for (int p = warp; p < pls; p += (nthr >> 5)) {
+    const int prob = prob0 + p;
+    double r_entry = 0.0, r_exit = 0.0, rho_used = 0.0;
+    if (prob < P.B) {
+      const S* sp = smem + (size_t)p * L.total;
+      const S* xu = sp + L.xu;
+      const S* dv = sp + L.d;
+      const S* part = sp + L.part;
+      const S rho = rho_g[prob];
+      const S merit_cur = merit_g[prob];
+      S* dbg = debug_g ? debug_g + (size_t)prob * (2 * L.N + 24) + 2 * L.N : nullptr;
+      r_entry = rentry_g[prob];
+      rho_used = (double)rho;
+      S mk = S(0), r2k = S(0);
+      if (lane < NLS) {
+        S cost = S(0), s2 = S(0), sl = S(0);
+        for (int t = 0; t < T - 1; ++t) {
+          cost += part[(lane * (T - 1) + t) * 3 + 0];
+          s2 += part[(lane * (T - 1) + t) * 3 + 1];
+          sl += part[(lane * (T - 1) + t) * 3 + 2];
+        }
+        mk = cost + S(0.5) * rho * s2 + sl;
+        r2k = s2;
+        if (dbg) dbg[lane] = mk;
+      }
+      // first-argmin with torch.min NaN semantics (any NaN -> NaN, step rejected)
+      const bool isn = (lane < NLS) && (mk != mk);
+      const bool any_nan = __any_sync(FULL, isn);
+      S bv = (lane < NLS) ? mk : S(INFINITY);
+      int bi = (lane < NLS) ? lane : NLS;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const S ov = __shfl_xor_sync(FULL, bv, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (bi >= NLS) bi = 0;  // all +inf
+      const S r2_best = __shfl_sync(FULL, r2k, bi);
+      if (any_nan) bv = S(NAN);
+      const bool accept = bv < merit_cur;
+      const S alpha = (S)ldexpf(1.0f, -bi);
+      bool fin = true;
+      const size_t pN = (size_t)prob * L.N;
+      for (int i = lane; i < L.N; i += 32) {
+        const S xo = xu[i];
+        const S xnew = xo + alpha * dv[i];
+        // status*x_next + (1-status)*x_est (al_utils.py:640-641): a non-finite rejected candidate poisons the element
+        const S xr = accept ? xnew : (finite_(xnew) ? xo : S(NAN));
+        fin = fin && finite_(xr);
+        if (accept || !finite_(xnew)) xu_g[pN + i] = xr;
+      }
+      fin = __all_sync(FULL, fin);
+      r_exit = accept ? (double)r2_best : (fin ? r_entry : (double)NAN);
+      if (lane == 0) {
+        merit_g[prob] = bv;  // merit <- new_merit even when the step was rejected (al_utils.py:569)
+        if (!fin) status_g[prob] &= ~ALMPC_STATUS_FINITE;
+        if (dbg) {
+          dbg[NLS + 0] = (S)bi;
+          dbg[NLS + 1] = accept ? S(1) : S(0);
+          dbg[NLS + 2] = merit_cur;
+        }
+      }
+    }
+    if (lane == 0) {
+      red[p][0] = r_entry;
+      red[p][1] = r_exit;
+      red[p][2] = rho_used;
+    }
+  }
+  __syncthreads();
+  // ---- batch-global statistics: per-CTA partials, last CTA reduces in a fixed order and steers the solve
+  if (tid == 0) {
     double s0 = 0, s1 = 0, s2 = 0;
-    for (int w = 0; w < WPB; ++w) { s0 += red[w][0]; s1 += red[w][1]; s2 = fmax(s2, red[w][2]); }
+    for (int p = 0; p < pls; ++p) { s0 += red[p][0]; s1 += red[p][1]; s2 = fmax(s2, red[p][2]); }
     partials[blockIdx.x * 4 + 0] = s0;
     partials[blockIdx.x * 4 + 1] = s1;
     partials[blockIdx.x * 4 + 2] = s2;
     __threadfence();
-    unsigned tk = atomicAdd(&ctl->ticket, 1u);
+    const unsigned tk = atomicAdd(&ctl->ticket, 1u);
     is_last = (tk == gridDim.x - 1);
   }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // deterministic reduction over blocks by the last CTA: thread-strided partial sums, then a fixed tree
-  double (*fin_red)[3] = reinterpret_cast<double (*)[3]>(smem_raw);  // warp regions are dead by now
+  double (*fin_red)[3] = reinterpret_cast<double (*)[3]>(smem_raw);  // staging area is dead by now
   {
     double s0 = 0, s1 = 0, s2 = 0;
     const volatile double* pv = partials;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += WPB * 32) {
+    for (int b = tid; b < (int)gridDim.x; b += nthr) {
       s0 += pv[b * 4 + 0];
       s1 += pv[b * 4 + 1];
       s2 = fmax(s2, pv[b * 4 + 2]);
     }
-    fin_red[threadIdx.x][0] = s0;
-    fin_red[threadIdx.x][1] = s1;
-    fin_red[threadIdx.x][2] = s2;
+    fin_red[tid][0] = s0;
+    fin_red[tid][1] = s1;
+    fin_red[tid][2] = s2;
   }
   __syncthreads();
-  for (int o = WPB * 16; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) {
-      fin_red[threadIdx.x][0] += fin_red[threadIdx.x + o][0];
-      fin_red[threadIdx.x][1] += fin_red[threadIdx.x + o][1];
-      fin_red[threadIdx.x][2] = fmax(fin_red[threadIdx.x][2], fin_red[threadIdx.x + o][2]);
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    const double R_entry = sqrt(fin_red[0][0]), R_exit = sqrt(fin_red[0][1]), rho_max_used = fin_red[0][2];
+  if (tid == 0) {
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int i = 0; i < nthr; ++i) { s0 += fin_red[i][0]; s1 += fin_red[i][1]; s2 = fmax(s2, fin_red[i][2]); }
+    const double R_entry = sqrt(s0), R_exit = sqrt(s1), rho_max_used = s2;
     const double res_old = (nk == 0) ? R_entry : ctl->res_old;
     // al_utils.py:560-564 — evaluated exactly as written there (NaN compares false -> no break)
     bool stop = (fabs(res_old - R_exit) / R_exit < 1e-3) || (R_exit < 1e-3);
@@ -977,43 +1200,98 @@ static int check_desc(const almpc_desc* d) {
 
 constexpr int kWPB = 4;
 
-static size_t ws_ctl_bytes() { return 256; }
 static int n_blocks(int B) { return (B + kWPB - 1) / kWPB; }
+
+// line-search launch geometry: `pls` problems per CTA, threads = one per (candidate, stage) item when it fits
+struct LsGeom { int pls, threads, blocks; };
+static LsGeom ls_geom(int B, int T) {
+  const int IT = NLS * (T - 1);
+  LsGeom g;
+  g.pls = 160 / IT;
+  if (g.pls < 1) g.pls = 1;
+  if (g.pls > 8) g.pls = 8;
+  int thr = g.pls * IT;
+  if (thr > 256) thr = 256;
+  g.threads = (thr + 31) & ~31;
+  g.blocks = (B + g.pls - 1) / g.pls;
+  return g;
+}
+
+// device workspace carved out of the caller's buffer
+struct WsPlan {
+  size_t ctl, partials, merit, rentry, status, c, d, G, total;
+};
+static WsPlan ws_plan(int B, int T, int nx, int nu, size_t es) {
+  const size_t nn = (size_t)nx + nu;
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  WsPlan w;
+  size_t o = 0;
+  w.ctl = o; o += 256;
+  w.partials = o; o = up(o + (size_t)ls_geom(B, T).blocks * 4 * sizeof(double));
+  w.merit = o; o = up(o + (size_t)B * es);
+  w.rentry = o; o = up(o + (size_t)B * sizeof(double));
+  w.status = o; o = up(o + (size_t)B * sizeof(int32_t));
+  w.c = o; o = up(o + (size_t)B * T * nx * es);
+  w.d = o; o = up(o + (size_t)B * T * nn * es);
+  w.G = o; o = up(o + (size_t)B * (T - 1) * nx * nn * es);
+  w.total = o;
+  return w;
+}
 
 template <class M, typename S>
 static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* q, S* xu, S* lam, S* rho, S* factor,
                         float* x_out, float* u_out, S* dyn_res_out, int32_t* status_out, int32_t* info_out,
                         S* debug_out, void* workspace, cudaStream_t st) {
-  constexpr int NX = M::NX, NU = M::NU;
+  constexpr int NX = M::NX, NU = M::NU, NN = NX + NU;
   if (d->B == 0) return 0;
   if (!x0 || !Qd || !q || !xu || !lam || !rho || !factor || !info_out || !workspace)
     return set_err(-10, "null buffer");
-  const Layout<NX, NU> L(d->T);
-  const size_t smem = (size_t)kWPB * L.total * sizeof(S);
-  if (smem + 1024 > 227 * 1024) return set_err(-11, "horizon too long for the shared-memory layout");
-  auto kern = k_newton_step<M, S, kWPB>;
+  const int T = d->T, B = d->B;
+  const Layout<NX, NU> L(T);
+  const LsLayout<NX, NU> LL(T);
+  const LsGeom lg = ls_geom(B, T);
+  const size_t smem_fac = (size_t)kWPB * L.total * sizeof(S);
+  size_t smem_ls = (size_t)lg.pls * LL.total * sizeof(S);
+  if (smem_ls < (size_t)lg.threads * 3 * sizeof(double)) smem_ls = (size_t)lg.threads * 3 * sizeof(double);
+  const size_t smem_fin = (size_t)kWPB * (L.N + L.neq) * sizeof(S);
+  if (smem_fac + 1024 > 227 * 1024 || smem_ls + 1024 > 227 * 1024)
+    return set_err(-11, "horizon too long for the shared-memory layout");
+  auto kjac = k_jacobian<M, S>;
+  auto kfac = k_factor_solve<NX, NU, S, kWPB>;
+  auto kls = k_line_search<M, S>;
   auto kfin = k_final_dual<M, S, kWPB>;
   cudaError_t e;
-  const size_t smem_fin = (size_t)kWPB * (L.N + L.neq) * sizeof(S);
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(newton_step)");
+  e = cudaFuncSetAttribute(kfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fac);
+  if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(factor_solve)");
+  e = cudaFuncSetAttribute(kls, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ls);
+  if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(line_search)");
   e = cudaFuncSetAttribute(kfin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fin);
   if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(final_dual)");
   const KParams<S> P = make_params<S>(d);
-  const int nb = n_blocks(d->B);
+  const WsPlan w = ws_plan(B, T, NX, NU, sizeof(S));
   unsigned char* ws = (unsigned char*)workspace;
-  Ctl* ctl = (Ctl*)ws;
-  double* partials = (double*)(ws + ws_ctl_bytes());
-  S* merit = (S*)(ws + ws_ctl_bytes() + (size_t)nb * 4 * sizeof(double));
-  int32_t* status = status_out ? status_out : (int32_t*)(merit + d->B);
-  e = cudaMemsetAsync(ctl, 0, ws_ctl_bytes(), st);
+  Ctl* ctl = (Ctl*)(ws + w.ctl);
+  double* partials = (double*)(ws + w.partials);
+  S* merit = (S*)(ws + w.merit);
+  double* rentry = (double*)(ws + w.rentry);
+  int32_t* status = status_out ? status_out : (int32_t*)(ws + w.status);
+  S* c_g = (S*)(ws + w.c);
+  S* d_g = (S*)(ws + w.d);
+  S* G_g = (S*)(ws + w.G);
+  e = cudaMemsetAsync(ctl, 0, 256, st);
   if (e != cudaSuccess) return cuda_err(e, "cudaMemsetAsync(ctl)");
   e = cudaMemsetAsync(info_out, 0, ALMPC_INFO_INTS * sizeof(int32_t), st);
   if (e != cudaSuccess) return cuda_err(e, "cudaMemsetAsync(info)");
+  const long jac_items = (long)B * (T - 1) * NN;
+  const unsigned jac_blocks = (unsigned)((jac_items + 127) / 128);
+  const int nb = n_blocks(B);
   const int launches = d->al_iter * d->max_newton;
   for (int i = 0; i < launches; ++i) {
-    kern<<<nb, kWPB * 32, smem, st>>>(P, x0, Qd, q, xu, lam, rho, factor, status, info_out, debug_out, ctl, partials,
-                                      merit);
+    kjac<<<jac_blocks, 128, 0, st>>>(P, x0, xu, G_g, c_g, ctl);
+    kfac<<<nb, kWPB * 32, smem_fac, st>>>(P, Qd, q, xu, lam, rho, factor, G_g, c_g, d_g, merit, rentry, status,
+                                          debug_out, ctl);
+    kls<<<lg.blocks, lg.threads, smem_ls, st>>>(P, lg.pls, x0, Qd, q, xu, lam, rho, d_g, merit, rentry, status,
+                                                info_out, debug_out, ctl, partials);
   }
   kfin<<<nb, kWPB * 32, smem_fin, st>>>(P, x0, xu, lam, rho, x_out, u_out, dyn_res_out, info_out, ctl);
   return cuda_err(cudaGetLastError(), "almpc_forward launch");
@@ -1126,9 +1404,9 @@ size_t almpc_factor_elems(const almpc_desc* d) {
 }
 
 size_t almpc_workspace_bytes(const almpc_desc* d) {
-  if (!d) return 0;
-  const size_t nb = (size_t)n_blocks(d->B);
-  return ws_ctl_bytes() + nb * 4 * sizeof(double) + (size_t)d->B * sizeof(double) + (size_t)d->B * sizeof(int32_t) + 64;
+  int32_t nx, nu;
+  if (!d || d->T < 2 || almpc_model_dims(d->dyn_id, &nx, &nu)) return 0;
+  return ws_plan(d->B, d->T, nx, nu, sizeof(double)).total;
 }
 
 size_t almpc_debug_elems(const almpc_desc* d) {
