@@ -109,6 +109,15 @@ __device__ __forceinline__ void warp_copy_async(S* dst, const S* src, int lane) 
     else cp_async4((char*)dst + o, (const char*)src + o);
   }
 }
+// dense global block [ROWS][NN] -> shared block with odd row stride LB (element-wise copies)
+template <int ROWS, int NN, int LB, typename S>
+__device__ __forceinline__ void warp_copy_block_async(S* dst, const S* src, int lane) {
+  for (int e = lane; e < ROWS * NN; e += 32) {
+    const int r = e / NN, c = e - r * NN;
+    if constexpr (sizeof(S) == 8) cp_async8(dst + r * LB + c, src + e);
+    else cp_async4(dst + r * LB + c, src + e);
+  }
+}
 template <int NX, int NU, typename S>
 struct CopyWidth {
   static constexpr int NN = NX + NU;
@@ -143,9 +152,9 @@ struct Layout {
     xu = take(N);
     dv = take(N);
     w = take(neq);
-    Gt = take(NX * NN);
-    Ep = take(NX * NN);
-    scr = take(64 + NN * ((NN % 2 == 0) ? NN + 2 : NN + 1));
+    Gt = take(NX * (NN | 1));
+    Ep = take(NX * (NN | 1));
+    scr = take(64 + NN * (NN | 1));
     total = o;
   }
 };
@@ -254,7 +263,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 template <int NN>
 struct ScrLd {
-  static constexpr int LD = (NN % 2 == 0) ? NN + 2 : NN + 1;  // even: rows start 16-byte aligned
+  static constexpr int LD = NN | 1;  // odd row stride: one row per lane is bank-conflict free
 };
 
 // D_t = diag(Qd_t) + rho (G_t^T G_t + I_x + active bounds) - E_{t-1} E_{t-1}^T   (lower tiles) -> scr
@@ -263,6 +272,7 @@ __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, 
                                             int lane, S rho, const S* __restrict__ Qd_t, const S* ulo, const S* uhi) {
   constexpr int NN = NX + NU;
   constexpr int LD = ScrLd<NN>::LD;
+  constexpr int LB = NN | 1;  // row stride of the staged G / E blocks
   if constexpr (sizeof(S) == 8) {
     constexpr int NT = (NN + 7) / 8, KG = (NX + 3) / 4, NTX = (NX + 7) / 8, KE = (NN + 3) / 4;
     const int g = lane >> 2, q4 = lane & 3;
@@ -278,7 +288,7 @@ __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, 
 #pragma unroll
         for (int ch = 0; ch < KG; ++ch) {
           const int col = tl * 8 + g, row = 4 * ch + q4;
-          f[tl][ch] = (col < NN && row < NX) ? (double)Gt[row * NN + col] : 0.0;
+          f[tl][ch] = (col < NN && row < NX) ? (double)Gt[row * LB + col] : 0.0;
         }
 #pragma unroll
       for (int rt = 0; rt < NT; ++rt)
@@ -299,7 +309,7 @@ __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, 
 #pragma unroll
         for (int ch = 0; ch < KE; ++ch) {
           const int row = tl * 8 + g, k = 4 * ch + q4;
-          f[tl][ch] = (row < NX && k < NN) ? (double)Ep[row * NN + k] : 0.0;
+          f[tl][ch] = (row < NX && k < NN) ? (double)Ep[row * LB + k] : 0.0;
         }
 #pragma unroll
       for (int rt = 0; rt < NTX; ++rt)
@@ -343,10 +353,10 @@ __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, 
       if (has_G) {
 #pragma unroll
         for (int i = 0; i + 1 < NX; i += 2) {
-          v0 += Gt[i * NN + r] * Gt[i * NN + c];
-          v1 += Gt[(i + 1) * NN + r] * Gt[(i + 1) * NN + c];
+          v0 += Gt[i * LB + r] * Gt[i * LB + c];
+          v1 += Gt[(i + 1) * LB + r] * Gt[(i + 1) * LB + c];
         }
-        if (NX & 1) v0 += Gt[(NX - 1) * NN + r] * Gt[(NX - 1) * NN + c];
+        if (NX & 1) v0 += Gt[(NX - 1) * LB + r] * Gt[(NX - 1) * LB + c];
       }
       S v = v0 + v1;
       if (r == c) {
@@ -363,10 +373,10 @@ __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, 
         S s0 = S(0), s1 = S(0);
 #pragma unroll
         for (int k = 0; k + 1 < NN; k += 2) {
-          s0 += Ep[r * NN + k] * Ep[c * NN + k];
-          s1 += Ep[r * NN + k + 1] * Ep[c * NN + k + 1];
+          s0 += Ep[r * LB + k] * Ep[c * LB + k];
+          s1 += Ep[r * LB + k + 1] * Ep[c * LB + k + 1];
         }
-        if (NN & 1) s0 += Ep[r * NN + NN - 1] * Ep[c * NN + NN - 1];
+        if (NN & 1) s0 += Ep[r * LB + NN - 1] * Ep[c * LB + NN - 1];
         v -= s0 + s1;
       }
       scr[r * LD + c] = v;
@@ -506,6 +516,7 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
   constexpr int LD = ScrLd<NN>::LD;
   constexpr int EX0 = 32 - NN - 1;  // sub-diagonal rows that fit next to the L rows and the rhs row
   constexpr int CW = CopyWidth<NX, NU, S>::W;
+  constexpr int LB = NN | 1;  // odd row stride of the staged G / E blocks (bank-conflict free rows)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int mode = ctl->mode;
   if (mode == MODE_DONE) return;
@@ -530,7 +541,7 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
   S* fac = fac_g + (size_t)prob * factor_elems<NX, NU>(T);
   S* dbg = debug_g ? debug_g + (size_t)prob * (2 * L.N + 24) : nullptr;
 
-  if (T > 1) warp_copy_async<NX * NN, CW>(Gt, Gp, lane);  // G_0, consumed after the residual statistics
+  if (T > 1) warp_copy_block_async<NX, NN, LB>(Gt, Gp, lane);  // G_0, consumed after the residual statistics
   cp_async_commit();
   for (int i = lane; i < L.N; i += 32) xu[i] = xu_g[pN + i];
   S rho = rho_g[prob];
@@ -567,8 +578,9 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
       sl += lam[L.neq + i] * ci;
     }
     for (int i = lane; i < L.N; i += 32) {
-      const S z = xu[i];
-      cost += S(0.5) * (z * Qd[i] * z) + qv[i] * z;
+      const S z = xu[i], Qi = Qd[i], qi = qv[i];
+      cost += S(0.5) * (z * Qi * z) + qi * z;
+      dv[i] = Qi * z + qi;  // cost gradient (al_utils.py:438-446), completed per stage below
     }
     s2 = warp_sum(s2);
     sl = warp_sum(sl);
@@ -595,15 +607,15 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
     // gradient of stage t (al_utils.py:113-117) minus the coupling E_{t-1} y_{t-1}
     if (lane < NN) {
       const int j = lane, idx = t * NN + j;
-      S g = Qd[idx] * xu[idx] + qv[idx];
+      S g = dv[idx];
       if (has_G) {
         S s0 = S(0), s1 = S(0);
 #pragma unroll
         for (int i = 0; i + 1 < NX; i += 2) {
-          s0 += X[i * NN + j] * wv[t * NX + i];
-          s1 += X[(i + 1) * NN + j] * wv[t * NX + i + 1];
+          s0 += X[i * LB + j] * wv[t * NX + i];
+          s1 += X[(i + 1) * LB + j] * wv[t * NX + i + 1];
         }
-        if (NX & 1) s0 += X[(NX - 1) * NN + j] * wv[t * NX + NX - 1];
+        if (NX & 1) s0 += X[(NX - 1) * LB + j] * wv[t * NX + NX - 1];
         g -= s0 + s1;
       }
       if (j < NX) {
@@ -620,10 +632,10 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
         S s0 = S(0), s1 = S(0);
 #pragma unroll
         for (int k = 0; k + 1 < NN; k += 2) {
-          s0 += Y[j * NN + k] * dv[(t - 1) * NN + k];
-          s1 += Y[j * NN + k + 1] * dv[(t - 1) * NN + k + 1];
+          s0 += Y[j * LB + k] * dv[(t - 1) * NN + k];
+          s1 += Y[j * LB + k + 1] * dv[(t - 1) * NN + k + 1];
         }
-        if (NN & 1) s0 += Y[j * NN + NN - 1] * dv[(t - 1) * NN + NN - 1];
+        if (NN & 1) s0 += Y[j * LB + NN - 1] * dv[(t - 1) * NN + NN - 1];
         g -= s0 + s1;
       }
       dv[idx] = g;
@@ -642,10 +654,10 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
       const int i = lane - NN - 1;
       const bool act = (i < NX) && has_G;
 #pragma unroll
-      for (int c = 0; c < NN; ++c) a[c] = act ? -rho * X[i * NN + c] : S(0);
+      for (int c = 0; c < NN; ++c) a[c] = act ? -rho * X[i * LB + c] : S(0);
     }
     __syncwarp();  // Y (E_{t-1}) has no reader left: prefetch G_{t+1} into it behind the pivot chain
-    if (t + 1 < T - 1) warp_copy_async<NX * NN, CW>(Y, Gp + (size_t)(t + 1) * NX * NN, lane);
+    if (t + 1 < T - 1) warp_copy_block_async<NX, NN, LB>(Y, Gp + (size_t)(t + 1) * NX * NN, lane);
     cp_async_commit();
     ok = eliminate<NN, true>(a, lane, scr) && ok;
     __syncwarp();
@@ -664,7 +676,7 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
       if (i < NX && has_G && NX <= EX0) {
 #pragma unroll
         for (int c = 0; c < NN; ++c) {
-          X[i * NN + c] = a[c];
+          X[i * LB + c] = a[c];
           Eg[i * NN + c] = a[c];
         }
       }
@@ -681,7 +693,7 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
         const bool act = (lane >= NN) && (i < NX);
         if (lane >= NN) {
 #pragma unroll
-          for (int c = 0; c < NN; ++c) a[c] = act ? -rho * X[i * NN + c] : S(0);
+          for (int c = 0; c < NN; ++c) a[c] = act ? -rho * X[i * LB + c] : S(0);
         }
         __syncwarp();
         eliminate<NN, false>(a, lane, scr + 64, LD);
@@ -689,7 +701,7 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
         if (act) {
 #pragma unroll
           for (int c = 0; c < NN; ++c) {
-            X[i * NN + c] = a[c];
+            X[i * LB + c] = a[c];
             Eg[i * NN + c] = a[c];
           }
         }
@@ -697,7 +709,7 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
       if (lane > NN && i0 < NX) {
 #pragma unroll
         for (int c = 0; c < NN; ++c) {
-          X[i0 * NN + c] = keep[c];
+          X[i0 * LB + c] = keep[c];
           Eg[i0 * NN + c] = keep[c];
         }
       }
@@ -728,16 +740,16 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
       S s0 = S(0), s1 = S(0);
 #pragma unroll
       for (int i = 0; i + 1 < NX; i += 2) {
-        s0 += Ecur[i * NN + lane] * dv[(t + 1) * NN + i];
-        s1 += Ecur[(i + 1) * NN + lane] * dv[(t + 1) * NN + i + 1];
+        s0 += Ecur[i * LB + lane] * dv[(t + 1) * NN + i];
+        s1 += Ecur[(i + 1) * LB + lane] * dv[(t + 1) * NN + i + 1];
       }
-      if (NX & 1) s0 += Ecur[(NX - 1) * NN + lane] * dv[(t + 1) * NN + NX - 1];
+      if (NX & 1) s0 += Ecur[(NX - 1) * LB + lane] * dv[(t + 1) * NN + NX - 1];
       b -= s0 + s1;
     }
     __syncwarp();
     if (t > 0) {
       warp_copy_async<NN * NN, CW>(Lsm, fac + (size_t)(t - 1) * NN * NN, lane);
-      warp_copy_async<NX * NN, CW>(Enext, fac + (size_t)T * NN * NN + (size_t)(t - 1) * NX * NN, lane);
+      warp_copy_block_async<NX, NN, LB>(Enext, fac + (size_t)T * NN * NN + (size_t)(t - 1) * NX * NN, lane);
     }
     cp_async_commit();
 #pragma unroll
