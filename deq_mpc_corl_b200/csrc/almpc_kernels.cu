@@ -778,10 +778,35 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
 // kernel 3/3: 20-point line search + iterate update + batch-global stop statistics / control block.
 // 1 thread = 1 (problem, candidate k, stage t); `pls` problems per CTA.
 // ------------------------------------------------------------------------------------------------
+// asynchronous staging of one problem's line-search inputs into shared memory (all threads of the CTA)
+template <int NX, int NU, typename S>
+__device__ __forceinline__ void ls_stage_async(S* sp, const LsLayout<NX, NU>& L, int prob, int tid, int nthr,
+                                               const S* x0_g, const S* Qd_g, const S* q_g, const S* xu_g,
+                                               const S* lam_g, const S* d_g) {
+  const size_t pN = (size_t)prob * L.N;
+  auto copy = [&](S* dst, const S* src, int count) {
+    if ((((size_t)count * sizeof(S)) & 15) == 0 && ((reinterpret_cast<size_t>(src) & 15) == 0)) {
+      const int bytes = count * (int)sizeof(S);
+      for (int o = tid * 16; o < bytes; o += nthr * 16) cp_async16((char*)dst + o, (const char*)src + o);
+    } else {
+      for (int e = tid; e < count; e += nthr) {
+        if constexpr (sizeof(S) == 8) cp_async8(dst + e, src + e);
+        else cp_async4(dst + e, src + e);
+      }
+    }
+  };
+  copy(sp + L.xu, xu_g + pN, L.N);
+  copy(sp + L.d, d_g + pN, L.N);
+  copy(sp + L.Qd, Qd_g + pN, L.N);
+  copy(sp + L.q, q_g + pN, L.N);
+  copy(sp + L.lam, lam_g + (size_t)prob * L.m, L.m);
+  copy(sp + L.x0, x0_g + (size_t)prob * NX, NX);
+}
+
 template <class M, typename S>
 __global__ void __launch_bounds__(256, 2)
 k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, const S* __restrict__ Qd_g,
-              const S* __restrict__ q_g, S* __restrict__ xu_g, const S* __restrict__ lam_g,
+              const S* __restrict__ q_g, S* xu_g, const S* __restrict__ lam_g,
               const S* __restrict__ rho_g, const S* __restrict__ d_g, S* __restrict__ merit_g,
               const double* __restrict__ rentry_g, int* __restrict__ status_g, int* __restrict__ info_g,
               S* __restrict__ debug_g, Ctl* ctl, double* __restrict__ partials) {
@@ -797,30 +822,40 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
   const int IT = NLS * (T - 1);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int prob0 = blockIdx.x * pls;
   S* smem = reinterpret_cast<S*>(smem_raw);
+  const int ngroups = (P.B + pls - 1) / pls;
+  const size_t buf_elems = (size_t)pls * L.total;
+  double blk0 = 0.0, blk1 = 0.0, blk2 = 0.0;  // thread 0: this CTA's running statistics
 
-  // cooperative, coalesced staging of the CTA's problems
-  for (int p = 0; p < pls; ++p) {
-    const int prob = prob0 + p;
-    if (prob >= P.B) break;
-    S* sp = smem + (size_t)p * L.total;
-    const size_t pN = (size_t)prob * L.N;
-    for (int i = tid; i < L.N; i += nthr) {
-      sp[L.xu + i] = xu_g[pN + i];
-      sp[L.d + i] = d_g[pN + i];
-      sp[L.Qd + i] = Qd_g[pN + i];
-      sp[L.q + i] = q_g[pN + i];
+  // persistent CTA: groups of `pls` problems, double-buffered; the next group's inputs stream in (cp.async)
+  // while the current group's 20 x (T-1) dynamics evaluations run
+  int cur = 0;
+  if ((int)blockIdx.x < ngroups) {
+    for (int p = 0; p < pls; ++p) {
+      const int prob = blockIdx.x * pls + p;
+      if (prob < P.B) ls_stage_async<NX, NU, S>(smem + (size_t)p * L.total, L, prob, tid, nthr, x0_g, Qd_g, q_g, xu_g, lam_g, d_g);
     }
-    for (int i = tid; i < L.m; i += nthr) sp[L.lam + i] = lam_g[(size_t)prob * L.m + i];
-    for (int i = tid; i < NX; i += nthr) sp[L.x0 + i] = x0_g[(size_t)prob * NX + i];
   }
-  __syncthreads();
+  cp_async_commit();
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int prob0 = grp * pls;
+    const int nxt = grp + gridDim.x;
+    if (nxt < ngroups) {
+      S* nb = smem + (size_t)(cur ^ 1) * buf_elems;
+      for (int p = 0; p < pls; ++p) {
+        const int prob = nxt * pls + p;
+        if (prob < P.B) ls_stage_async<NX, NU, S>(nb + (size_t)p * L.total, L, prob, tid, nthr, x0_g, Qd_g, q_g, xu_g, lam_g, d_g);
+      }
+    }
+    cp_async_commit();
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    S* base = smem + (size_t)cur * buf_elems;
 
   for (int wi = tid; wi < pls * IT; wi += nthr) {
     const int p = wi / IT, it = wi - p * IT;
     if (prob0 + p >= P.B) continue;
-    const S* sp = smem + (size_t)p * L.total;
+    const S* sp = base + (size_t)p * L.total;
     const S* xu = sp + L.xu;
     const S* dv = sp + L.d;
     const S* lam = sp + L.lam;
@@ -888,7 +923,7 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
     const int prob = prob0 + p;
     double r_entry = 0.0, r_exit = 0.0, rho_used = 0.0;
     if (prob < P.B) {
-      const S* sp = smem + (size_t)p * L.total;
+      const S* sp = base + (size_t)p * L.total;
       const S* xu = sp + L.xu;
       const S* dv = sp + L.d;
       const S* part = sp + L.part;
@@ -954,13 +989,19 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
     }
   }
   __syncthreads();
+    // fold this group's statistics into the CTA totals in a fixed order
+    if (tid == 0) {
+      for (int p = 0; p < pls; ++p) { blk0 += red[p][0]; blk1 += red[p][1]; blk2 = fmax(blk2, red[p][2]); }
+    }
+    __syncthreads();  // buffer `cur` may be overwritten by the prefetch of the iteration after next
+    cur ^= 1;
+  }
+  cp_async_wait_all();
   // ---- batch-global statistics: per-CTA partials, last CTA reduces in a fixed order and steers the solve
   if (tid == 0) {
-    double s0 = 0, s1 = 0, s2 = 0;
-    for (int p = 0; p < pls; ++p) { s0 += red[p][0]; s1 += red[p][1]; s2 = fmax(s2, red[p][2]); }
-    partials[blockIdx.x * 4 + 0] = s0;
-    partials[blockIdx.x * 4 + 1] = s1;
-    partials[blockIdx.x * 4 + 2] = s2;
+    partials[blockIdx.x * 4 + 0] = blk0;
+    partials[blockIdx.x * 4 + 1] = blk1;
+    partials[blockIdx.x * 4 + 2] = blk2;
     __threadfence();
     const unsigned tk = atomicAdd(&ctl->ticket, 1u);
     is_last = (tk == gridDim.x - 1);
@@ -1263,7 +1304,7 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   const LsLayout<NX, NU> LL(T);
   const LsGeom lg = ls_geom(B, T);
   const size_t smem_fac = (size_t)kWPB * L.total * sizeof(S);
-  size_t smem_ls = (size_t)lg.pls * LL.total * sizeof(S);
+  size_t smem_ls = 2 * (size_t)lg.pls * LL.total * sizeof(S);  // double-buffered staging
   if (smem_ls < (size_t)lg.threads * 3 * sizeof(double)) smem_ls = (size_t)lg.threads * 3 * sizeof(double);
   const size_t smem_fin = (size_t)kWPB * (L.N + L.neq) * sizeof(S);
   if (smem_fac + 1024 > 227 * 1024 || smem_ls + 1024 > 227 * 1024)
@@ -1279,6 +1320,16 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(line_search)");
   e = cudaFuncSetAttribute(kfin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fin);
   if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(final_dual)");
+  // persistent line-search grid: as many CTAs as fit on the device at once
+  int ls_per_sm = 0, n_sm = 0, dev = 0;
+  e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_err(e, "cudaGetDevice");
+  e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return cuda_err(e, "cudaDeviceGetAttribute");
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ls_per_sm, kls, lg.threads, smem_ls);
+  if (e != cudaSuccess) return cuda_err(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  int ls_grid = n_sm * (ls_per_sm > 0 ? ls_per_sm : 1);
+  if (ls_grid > lg.blocks) ls_grid = lg.blocks;
   const KParams<S> P = make_params<S>(d);
   const WsPlan w = ws_plan(B, T, NX, NU, sizeof(S));
   unsigned char* ws = (unsigned char*)workspace;
@@ -1302,7 +1353,7 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
     kjac<<<jac_blocks, 128, 0, st>>>(P, x0, xu, G_g, c_g, ctl);
     kfac<<<nb, kWPB * 32, smem_fac, st>>>(P, Qd, q, xu, lam, rho, factor, G_g, c_g, d_g, merit, rentry, status,
                                           debug_out, ctl);
-    kls<<<lg.blocks, lg.threads, smem_ls, st>>>(P, lg.pls, x0, Qd, q, xu, lam, rho, d_g, merit, rentry, status,
+    kls<<<ls_grid, lg.threads, smem_ls, st>>>(P, lg.pls, x0, Qd, q, xu, lam, rho, d_g, merit, rentry, status,
                                                 info_out, debug_out, ctl, partials);
   }
   kfin<<<nb, kWPB * 32, smem_fin, st>>>(P, x0, xu, lam, rho, x_out, u_out, dyn_res_out, info_out, ctl);
