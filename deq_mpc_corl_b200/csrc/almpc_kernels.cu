@@ -163,17 +163,18 @@ struct Layout {
 template <int NX, int NU>
 struct LsLayout {
   static constexpr int NN = NX + NU;
+  static constexpr int LS = NN | 1;  // odd stage stride: lanes working on different stages hit different banks
   int N, neq, nin, m;
   int xu, d, lam, Qd, q, x0, part, total;
   __host__ __device__ LsLayout(int T) {
     N = T * NN; neq = T * NX; nin = 2 * T * NU; m = neq + nin;
     int o = 0;
     auto take = [&](int cnt) { int at = o; o += (cnt + 3) & ~3; return at; };  // regions 16-byte aligned for float and double
-    xu = take(N);
-    d = take(N);
+    xu = take(T * LS);
+    d = take(T * LS);
     lam = take(m);
-    Qd = take(N);
-    q = take(N);
+    Qd = take(T * LS);
+    q = take(T * LS);
     x0 = take(NX);
     part = take(NLS * (T - 1) * 3);
     total = o;
@@ -795,10 +796,22 @@ __device__ __forceinline__ void ls_stage_async(S* sp, const LsLayout<NX, NU>& L,
       }
     }
   };
-  copy(sp + L.xu, xu_g + pN, L.N);
-  copy(sp + L.d, d_g + pN, L.N);
-  copy(sp + L.Qd, Qd_g + pN, L.N);
-  copy(sp + L.q, q_g + pN, L.N);
+  constexpr int NN = NX + NU, LS = NN | 1;
+  for (int e = tid; e < L.N; e += nthr) {
+    const int t = e / NN, c = e - t * NN;
+    const int o = t * LS + c;
+    if constexpr (sizeof(S) == 8) {
+      cp_async8(sp + L.xu + o, xu_g + pN + e);
+      cp_async8(sp + L.d + o, d_g + pN + e);
+      cp_async8(sp + L.Qd + o, Qd_g + pN + e);
+      cp_async8(sp + L.q + o, q_g + pN + e);
+    } else {
+      cp_async4(sp + L.xu + o, xu_g + pN + e);
+      cp_async4(sp + L.d + o, d_g + pN + e);
+      cp_async4(sp + L.Qd + o, Qd_g + pN + e);
+      cp_async4(sp + L.q + o, q_g + pN + e);
+    }
+  }
   copy(sp + L.lam, lam_g + (size_t)prob * L.m, L.m);
   copy(sp + L.x0, x0_g + (size_t)prob * NX, NX);
 }
@@ -810,7 +823,7 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
               const S* __restrict__ rho_g, const S* __restrict__ d_g, S* __restrict__ merit_g,
               const double* __restrict__ rentry_g, int* __restrict__ status_g, int* __restrict__ info_g,
               S* __restrict__ debug_g, Ctl* ctl, double* __restrict__ partials) {
-  constexpr int NX = M::NX, NU = M::NU, NN = NX + NU;
+  constexpr int NX = M::NX, NU = M::NU, NN = NX + NU, LS = NN | 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[8][3];
   __shared__ bool is_last;
@@ -869,15 +882,15 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
     S cost = S(0), s2 = S(0), sl = S(0);
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-      const S z = xu[t * NN + i] + alpha * dv[t * NN + i];
+      const S z = xu[t * LS + i] + alpha * dv[t * LS + i];
       xs[i] = z;
-      cost += S(0.5) * (z * Qd[t * NN + i] * z) + qv[t * NN + i] * z;
+      cost += S(0.5) * (z * Qd[t * LS + i] * z) + qv[t * LS + i] * z;
     }
 #pragma unroll
     for (int i = 0; i < NU; ++i) {
-      const S z = xu[t * NN + NX + i] + alpha * dv[t * NN + NX + i];
+      const S z = xu[t * LS + NX + i] + alpha * dv[t * LS + NX + i];
       us[i] = z;
-      cost += S(0.5) * (z * Qd[t * NN + NX + i] * z) + qv[t * NN + NX + i] * z;
+      cost += S(0.5) * (z * Qd[t * LS + NX + i] * z) + qv[t * LS + NX + i] * z;
       const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
       sl += lam[L.neq + t * 2 * NU + i] * cu + lam[L.neq + t * 2 * NU + NU + i] * cl;
       const S pu = fmax0(cu), pl = fmax0(cl);
@@ -894,16 +907,16 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
     rk4_step<M, S, S>(xs, us, xn, P.dyn);
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-      const S z1 = xu[(t + 1) * NN + i] + alpha * dv[(t + 1) * NN + i];
+      const S z1 = xu[(t + 1) * LS + i] + alpha * dv[(t + 1) * LS + i];
       const S ci = z1 - xn[i];
       s2 += ci * ci;
       sl += lam[t * NX + i] * ci;
-      if (t == T - 2) cost += S(0.5) * (z1 * Qd[(t + 1) * NN + i] * z1) + qv[(t + 1) * NN + i] * z1;
+      if (t == T - 2) cost += S(0.5) * (z1 * Qd[(t + 1) * LS + i] * z1) + qv[(t + 1) * LS + i] * z1;
     }
     if (t == T - 2) {
 #pragma unroll
       for (int i = 0; i < NU; ++i) {
-        const int e = (T - 1) * NN + NX + i;
+        const int e = (T - 1) * LS + NX + i;
         const S z = xu[e] + alpha * dv[e];
         cost += S(0.5) * (z * Qd[e] * z) + qv[e] * z;
         const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
@@ -963,8 +976,9 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
       bool fin = true;
       const size_t pN = (size_t)prob * L.N;
       for (int i = lane; i < L.N; i += 32) {
-        const S xo = xu[i];
-        const S xnew = xo + alpha * dv[i];
+        const int ts = i / NN, si = ts * LS + (i - ts * NN);
+        const S xo = xu[si];
+        const S xnew = xo + alpha * dv[si];
         // status*x_next + (1-status)*x_est (al_utils.py:640-641): a non-finite rejected candidate poisons the element
         const S xr = accept ? xnew : (finite_(xnew) ? xo : S(NAN));
         fin = fin && finite_(xr);
