@@ -11,7 +11,8 @@ per GPU, fp64 (BASELINE.json).  One *step* = one cold-start `MPC.forward` (al_it
 Prints ONE JSON line (contract in the task statement): value = device-timed whole-job solves/s with
 inputs resident in HBM; e2e = the same through the reference-facing `MPC` module with pinned HOST
 buffers and the H2D/D2H copies inside the timed region; roofline = FP64 (FP32) FMA-pipe fraction of
-the dominant kernel (k_newton_step) from algorithmic flops / CUDA-event time, against the FMA peak
+the dominant kernel of the Newton step (k_jacobian / k_factor_solve / k_line_search, timed per launch with
+CUDA events inside the library) from algorithmic flops and bytes, against the FMA peak
 measured in this run by almpc_fma_peak (MEASURED_PEAKS.json has no FP64 figure), plus the HBM view;
 cpu_baseline = the oracle port timed on this box's host cores on a bounded sample.
 """
@@ -49,6 +50,27 @@ def algorithmic_flops(model, T):
     f_dual = (T - 1) * f_dyn + 3 * m
     f_bwd = subst + T * n
     return dict(newton=f_newton, dual=f_dual, bwd=f_bwd)
+
+
+def kernel_work(model, T, esize):
+    """Algorithmic flops / HBM bytes per problem of the three kernels of one Newton step (same SURVEY §8d
+    terms as algorithmic_flops, split by kernel; G and c cross HBM between the kernels)."""
+    spec = MODEL_SPECS[model]
+    nx, nu = spec["nx"], spec["nu"]
+    n, N, m = nx + nu, T * (nx + nu), T * nx + 2 * T * nu
+    f_dyn = F_DYN[model]
+    G = (T - 1) * nx * n
+    factor = T * n * n + (T - 1) * nx * n
+    subst = 2 * (T * n * n + 2 * (T - 1) * nx * n)
+    return {
+        "k_jacobian": dict(flops=(T - 1) * 2 * n * f_dyn, bytes=(N + nx + G + T * nx) * esize),
+        "k_factor_solve": dict(
+            flops=(T - 1) * nx * n * (n + 1) + 4 * (T - 1) * nx * n + 4 * T * nu + T * n ** 3 / 3
+            + (T - 1) * (nx * n * n + nx * nx * n) + subst + 6 * N + 3 * m,
+            bytes=(G + T * nx + 3 * N + m + 1 + factor + N + 2) * esize),
+        "k_line_search": dict(flops=20 * ((T - 1) * f_dyn + 6 * T * n + 2 * m) + 2 * N,
+                              bytes=(5 * N + m + nx + 3 + N) * esize),
+    }
 
 
 def algorithmic_bytes(model, T, esize):
@@ -277,18 +299,23 @@ def main():
     newton = info[_lib.INFO_NEWTON0:_lib.INFO_NEWTON0 + info[_lib.INFO_AL_DONE]]
     n_newton = sum(newton)
 
-    # ---- kernel-level timing of the forward (dominant kernel = k_newton_step) for the roofline
-    fwd_ms = []
+    # ---- kernel-level timing for the roofline: CUDA events around every launch inside the library
+    # (almpc_set_profiling), on the stream the kernels are launched on; median of 3 forward solves
+    prof_runs = []
+    lib.almpc_set_profiling(1)
     for _ in range(3):
         xu.copy_(xu_init); lam.copy_(lam0); rho.copy_(rho0)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
         raw_forward(cfg, x0, Qd, q, xu, lam, rho)
-        e1.record()
         torch.cuda.synchronize()
-        fwd_ms.append(e0.elapsed_time(e1))
-    fwd_ms.sort()
-    newton_launch_ms = fwd_ms[len(fwd_ms) // 2] / max(n_newton, 1)
+        buf = (ctypes.c_double * 8)()
+        lib.almpc_get_profile(buf)
+        prof_runs.append(list(buf))
+    lib.almpc_set_profiling(0)
+    prof_runs.sort(key=lambda r: r[0] + r[1] + r[2])
+    pr = prof_runs[len(prof_runs) // 2]
+    kernel_ms = {"k_jacobian": pr[0] / max(pr[4], 1), "k_factor_solve": pr[1] / max(pr[5], 1),
+                 "k_line_search": pr[2] / max(pr[6], 1)}
+    newton_launch_ms = sum(kernel_ms.values())
 
     # ---- timed region: K steps, device resident
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -344,6 +371,7 @@ def main():
     if rank == 0:
         fl = algorithmic_flops(model, T)
         by = algorithmic_bytes(model, T, esize)
+        fma_name = "fp64_fma" if dtype == torch.float64 else "fp32_fma"
         ach_tflops = fl["newton"] * B / (newton_launch_ms * 1e-3) / 1e12
         peaks = {}
         try:
@@ -352,6 +380,16 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_ach = by["newton_launch"] * B / (newton_launch_ms * 1e-3) / 1e9
+        kw = kernel_work(model, T, esize)
+        kernels = {}
+        for kn, ms in kernel_ms.items():
+            tf = kw[kn]["flops"] * B / (ms * 1e-3) / 1e12
+            gb = kw[kn]["bytes"] * B / (ms * 1e-3) / 1e9
+            kernels[kn] = {"avg_launch_ms": ms, "flops_per_problem": kw[kn]["flops"], "bytes_per_problem": kw[kn]["bytes"],
+                           "fma_tflops": tf, "fma_frac": tf / peak_tflops, "hbm_gbs": gb, "hbm_frac": gb / hbm_peak}
+        dom = max(kernel_ms, key=kernel_ms.get)
+        dk = kernels[dom]
+        dom_fma = dk["fma_frac"] >= dk["hbm_frac"]
         value = args.steps * B * world / (el_ms * 1e-3)
         line = {
             "metric": "AL-MPC solves/sec (fwd+implicit bwd)", "value": value, "unit": "solves/s", "n_gpus": world,
@@ -365,13 +403,21 @@ def main():
                     "api": "deq_mpc_corl_b200.al_mpc.MPC.forward + autograd backward, pinned host buffers"},
             "gpu_launches": args.steps * (cfg.al_iter * cfg.max_newton * 3 + 2),
             "roofline": {
-                "bound": "fp64_fma" if dtype == torch.float64 else "fp32_fma", "kernel": "k_newton_step",
-                "achieved": ach_tflops, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach_tflops / peak_tflops,
-                "peak_source": "measured in this run by almpc_fma_peak (8 independent FMA chains/thread); MEASURED_PEAKS.json has no FP64/FP32 FMA figure",
-                "flops_per_problem_per_launch": fl["newton"], "avg_launch_ms": newton_launch_ms, "traffic": None,
-                "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                        "bytes_per_problem_per_launch": by["newton_launch"],
-                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
+                # dominant kernel by time, against whichever of its two rooflines it sits closer to
+                "kernel": dom, "bound": (fma_name if dom_fma else "hbm"),
+                "achieved": dk["fma_tflops"] if dom_fma else dk["hbm_gbs"],
+                "peak": peak_tflops if dom_fma else hbm_peak, "unit": "TFLOP/s" if dom_fma else "GB/s",
+                "frac": dk["fma_frac"] if dom_fma else dk["hbm_frac"], "avg_launch_ms": dk["avg_launch_ms"],
+                "traffic": None,
+                "peak_source": {"fma": "measured in this run by almpc_fma_peak (8 independent FMA chains/thread); MEASURED_PEAKS.json has no FP64/FP32 FMA figure",
+                                "hbm": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
+                "kernels": kernels,
+                # the whole Newton step (3 launches) against the FMA roofline that binds the path
+                "newton_step": {"bound": fma_name, "achieved": ach_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+                                "frac": ach_tflops / peak_tflops, "flops_per_problem": fl["newton"],
+                                "ms": newton_launch_ms,
+                                "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                                        "bytes_per_problem": by["newton_launch"]}},
             },
             "flops_per_solve": fl["newton"] * n_newton + 2 * fl["dual"] + fl["bwd"],
         }

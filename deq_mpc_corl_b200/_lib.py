@@ -83,6 +83,10 @@ def load():
         p = getattr(lib, "almpc_fma_peak_" + sfx)
         p.argtypes = [i32, i32, vp, ctypes.POINTER(dbl), vp]
         p.restype = ctypes.c_int
+    lib.almpc_set_profiling.argtypes = [i32]
+    lib.almpc_set_profiling.restype = None
+    lib.almpc_get_profile.argtypes = [ctypes.POINTER(dbl)]
+    lib.almpc_get_profile.restype = None
     _lib = lib
     return lib
 
@@ -91,7 +95,7 @@ EXPORTS = [
     "almpc_model_dims", "almpc_factor_elems", "almpc_workspace_bytes", "almpc_debug_elems",
     "almpc_forward_f64", "almpc_forward_f32", "almpc_backward_f64", "almpc_backward_f32",
     "almpc_dynamics_f64", "almpc_dynamics_f32", "almpc_fma_peak_f64", "almpc_fma_peak_f32",
-    "almpc_last_error", "almpc_version",
+    "almpc_set_profiling", "almpc_get_profile", "almpc_last_error", "almpc_version",
 ]
 
 

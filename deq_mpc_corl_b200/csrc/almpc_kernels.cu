@@ -1267,6 +1267,11 @@ static int check_desc(const almpc_desc* d) {
 
 constexpr int kWPB = 4;
 
+// optional per-kernel timing (bench.py): events around every launch of one forward call
+static int g_profile_on = 0;
+static double g_profile[8] = {0};  // ms: [0] jacobian [1] factor_solve [2] line_search [3] final_dual, [4..7] launch counts
+struct ProfEv { cudaEvent_t a, b; int kind; };
+
 static int n_blocks(int B) { return (B + kWPB - 1) / kWPB; }
 
 // line-search launch geometry: `pls` problems per CTA, threads = one per (candidate, stage) item when it fits
@@ -1363,14 +1368,51 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   const unsigned jac_blocks = (unsigned)((jac_items + 127) / 128);
   const int nb = n_blocks(B);
   const int launches = d->al_iter * d->max_newton;
+  ProfEv pe[3 * ALMPC_MAX_AL_ITER * 8 + 1];
+  int npe = 0;
+  const bool prof = g_profile_on && launches * 3 + 1 <= (int)(sizeof(pe) / sizeof(pe[0]));
+  auto tic = [&](int kind) {
+    if (!prof) return;
+    cudaEventCreate(&pe[npe].a);
+    cudaEventCreate(&pe[npe].b);
+    pe[npe].kind = kind;
+    cudaEventRecord(pe[npe].a, st);
+  };
+  auto toc = [&]() {
+    if (!prof) return;
+    cudaEventRecord(pe[npe].b, st);
+    ++npe;
+  };
   for (int i = 0; i < launches; ++i) {
+    tic(0);
     kjac<<<jac_blocks, 128, 0, st>>>(P, x0, xu, G_g, c_g, ctl);
+    toc();
+    tic(1);
     kfac<<<nb, kWPB * 32, smem_fac, st>>>(P, Qd, q, xu, lam, rho, factor, G_g, c_g, d_g, merit, rentry, status,
                                           debug_out, ctl);
+    toc();
+    tic(2);
     kls<<<ls_grid, lg.threads, smem_ls, st>>>(P, lg.pls, x0, Qd, q, xu, lam, rho, d_g, merit, rentry, status,
                                                 info_out, debug_out, ctl, partials);
+    toc();
   }
+  tic(3);
   kfin<<<nb, kWPB * 32, smem_fin, st>>>(P, x0, xu, lam, rho, x_out, u_out, dyn_res_out, info_out, ctl);
+  toc();
+  if (prof) {  // profiling mode synchronises (never used on the timed path)
+    cudaStreamSynchronize(st);
+    for (int k = 0; k < 8; ++k) g_profile[k] = 0;
+    for (int i = 0; i < npe; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, pe[i].a, pe[i].b);
+      if (ms > 0.02f || pe[i].kind == 3) {  // skip the no-op launches after the solve finished
+        g_profile[pe[i].kind] += ms;
+        g_profile[4 + pe[i].kind] += 1;
+      }
+      cudaEventDestroy(pe[i].a);
+      cudaEventDestroy(pe[i].b);
+    }
+  }
   return cuda_err(cudaGetLastError(), "almpc_forward launch");
 }
 
@@ -1525,6 +1567,10 @@ int almpc_fma_peak_f64(int32_t blocks, int32_t iters, double* sink, double* flop
 }
 int almpc_fma_peak_f32(int32_t blocks, int32_t iters, float* sink, double* flops, void* stream) {
   return fma_peak<float>(blocks, iters, sink, flops, stream);
+}
+void almpc_set_profiling(int32_t on) { g_profile_on = on; }
+void almpc_get_profile(double* out8) {
+  for (int k = 0; k < 8; ++k) out8[k] = g_profile[k];
 }
 const char* almpc_last_error(void) { return g_err; }
 const char* almpc_version(void) { return "almpc 0.1 (sm_100a)"; }

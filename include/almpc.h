@@ -125,6 +125,13 @@ int almpc_dynamics_f32(const almpc_desc* d, int64_t R, const float* x, const flo
 int almpc_fma_peak_f64(int32_t blocks, int32_t iters, double* sink, double* flops, void* stream);
 int almpc_fma_peak_f32(int32_t blocks, int32_t iters, float* sink, double* flops, void* stream);
 
+/* Optional per-kernel timing for benchmarks: when on, almpc_forward_* brackets every launch with CUDA
+ * events and SYNCHRONISES at the end (never enable it on a timed or graph-captured path).
+ * almpc_get_profile: out8[0..3] = total ms of k_jacobian, k_factor_solve, k_line_search, k_final_dual of the
+ * last profiled forward (no-op launches after the solve finished excluded), out8[4..7] = launches counted. */
+void almpc_set_profiling(int32_t on);
+void almpc_get_profile(double* out8);
+
 const char* almpc_last_error(void);
 const char* almpc_version(void);
 
