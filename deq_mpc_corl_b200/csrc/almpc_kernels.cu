@@ -194,21 +194,27 @@ struct LsLayout {
 template <int NN, bool FUSED, typename S>
 __device__ __forceinline__ bool eliminate(S (&a)[NN], int lane, S* colbuf, int LDL = 0) {
   bool ok = true;
+  if (FUSED) {
+    // software-pipelined pivots: as soon as column k+1 has its update, the next pivot is broadcast and its
+    // reciprocal square root (the longest dependent chain of the step) runs under the remaining updates
+    S d = __shfl_sync(FULL, a[0], 0);
+    ok = (d > S(0)) && (d < S(1e30));
+    S inv = rsqrt_(d);
 #pragma unroll
-  for (int k = 0; k < NN; ++k) {
-    if (FUSED) {
-      const S d = __shfl_sync(FULL, a[k], k);
-      ok = ok && (d > S(0)) && (d < S(1e30));
-      const S inv = rsqrt_(d);
+    for (int k = 0; k < NN; ++k) {
       const S lk = a[k] * inv;
       a[k] = (lane == k) ? inv : lk;
       if (k + 1 < NN) {
         S* col = colbuf + (k & 1) * 32;
         col[lane] = lk;
         __syncwarp();
-        // pivot column: one scalar head (odd start), 16-byte pairs, one scalar tail (odd NN)
+        a[k + 1] -= lk * col[k + 1];
+        d = __shfl_sync(FULL, a[k + 1], k + 1);
+        ok = ok && (d > S(0)) && (d < S(1e30));
+        inv = rsqrt_(d);
+        // rest of the pivot column: one scalar head (odd start), 16-byte pairs, one scalar tail (odd NN)
         constexpr bool kVec = !ALMPC_NO_VEC2;
-        const int j0 = k + 1;
+        const int j0 = k + 2;
         const int js = kVec ? ((j0 + 1) & ~1) : NN;  // first even index >= j0
         if (kVec && (j0 & 1) && j0 < NN) a[j0] -= lk * col[j0];
 #pragma unroll
@@ -226,7 +232,10 @@ __device__ __forceinline__ bool eliminate(S (&a)[NN], int lane, S* colbuf, int L
             if (j >= j0) a[j] -= lk * col[j];
         }
       }
-    } else {
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NN; ++k) {
       const S inv = colbuf[k * LDL + k];
       const S lk = a[k] * inv;
       if (lane >= NN) a[k] = lk;
@@ -544,49 +553,95 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
 
   if (T > 1) warp_copy_block_async<NX, NN, LB>(Gt, Gp, lane);  // G_0, consumed after the residual statistics
   cp_async_commit();
-  for (int i = lane; i < L.N; i += 32) xu[i] = xu_g[pN + i];
   S rho = rho_g[prob];
+  for (int base = 0; base < L.N; base += 128) {
+    S xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + lane + 32 * u;
+      xv[u] = (i < L.N) ? xu_g[pN + i] : S(0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + lane + 32 * u;
+      if (i < L.N) xu[i] = xv[u];
+    }
+  }
   __syncwarp();
 
-  // ---- dual / penalty update of the previous AL iteration (AL_mpc.py:316-317,325)
-  if (mode == MODE_DUAL_NEWTON) {
-    for (int i = lane; i < L.neq; i += 32) lam[i] += rho * cres[i];
-    for (int i = lane; i < L.nin; i += 32) {
-      const int t = i / (2 * NU), s = i - t * 2 * NU;
-      const S u = xu[t * NN + NX + (s < NU ? s : s - NU)];
-      const S ci = (s < NU) ? (u - P.uhi[s]) : (P.ulo[s - NU] - u);
-      lam[L.neq + i] = fmax0(lam[L.neq + i] + rho * ci);
-    }
-    rho = next_rho(rho, P.rho_mult, P.rho_f32);
-    if (lane == 0) rho_g[prob] = rho;
-    __syncwarp();
-  }
-  // ---- entry residual ||c+||^2, merit at the entry point, w = lam_eq + rho c
+  // ---- dual / penalty update of the previous AL iteration (AL_mpc.py:316-317,325), entry residual
+  // ||c+||^2, merit at the entry point, w = lam_eq + rho c, cost gradient.  Global loads are issued four
+  // at a time per lane so that their latencies overlap.
+  const bool dual = (mode == MODE_DUAL_NEWTON);
+  const S rho_old = rho;
+  if (dual) rho = next_rho(rho, P.rho_mult, P.rho_f32);
   {
     S s2 = S(0), sl = S(0), cost = S(0);
-    for (int i = lane; i < L.neq; i += 32) {
-      const S ci = cres[i], li = lam[i];
-      s2 += ci * ci;
-      sl += li * ci;
-      wv[i] = li + rho * ci;
+    for (int base = 0; base < L.neq; base += 128) {
+      S cv[4], lv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + lane + 32 * u;
+        cv[u] = (i < L.neq) ? cres[i] : S(0);
+        lv[u] = (i < L.neq) ? lam[i] : S(0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + lane + 32 * u;
+        if (i < L.neq) {
+          S li = lv[u];
+          if (dual) { li += rho_old * cv[u]; lam[i] = li; }
+          s2 += cv[u] * cv[u];
+          sl += li * cv[u];
+          wv[i] = li + rho * cv[u];
+        }
+      }
     }
-    for (int i = lane; i < L.nin; i += 32) {
-      const int t = i / (2 * NU), s = i - t * 2 * NU;
-      const S u = xu[t * NN + NX + (s < NU ? s : s - NU)];
-      const S ci = (s < NU) ? (u - P.uhi[s]) : (P.ulo[s - NU] - u);
-      const S cp = fmax0(ci);
-      s2 += cp * cp;
-      sl += lam[L.neq + i] * ci;
+    for (int base = 0; base < L.nin; base += 128) {
+      S lv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + lane + 32 * u;
+        lv[u] = (i < L.nin) ? lam[L.neq + i] : S(0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + lane + 32 * u;
+        if (i < L.nin) {
+          const int t = i / (2 * NU), sidx = i - t * 2 * NU;
+          const S uu = xu[t * NN + NX + (sidx < NU ? sidx : sidx - NU)];
+          const S ci = (sidx < NU) ? (uu - P.uhi[sidx]) : (P.ulo[sidx - NU] - uu);
+          S li = lv[u];
+          if (dual) { li = fmax0(li + rho_old * ci); lam[L.neq + i] = li; }
+          const S cp = fmax0(ci);
+          s2 += cp * cp;
+          sl += li * ci;
+        }
+      }
     }
-    for (int i = lane; i < L.N; i += 32) {
-      const S z = xu[i], Qi = Qd[i], qi = qv[i];
-      cost += S(0.5) * (z * Qi * z) + qi * z;
-      dv[i] = Qi * z + qi;  // cost gradient (al_utils.py:438-446), completed per stage below
+    for (int base = 0; base < L.N; base += 128) {
+      S Qv[4], qq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + lane + 32 * u;
+        Qv[u] = (i < L.N) ? Qd[i] : S(0);
+        qq[u] = (i < L.N) ? qv[i] : S(0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + lane + 32 * u;
+        if (i < L.N) {
+          const S z = xu[i];
+          cost += S(0.5) * (z * Qv[u] * z) + qq[u] * z;
+          dv[i] = Qv[u] * z + qq[u];  // cost gradient (al_utils.py:438-446), completed per stage below
+        }
+      }
     }
     s2 = warp_sum(s2);
     sl = warp_sum(sl);
     cost = warp_sum(cost);
     if (lane == 0) {
+      if (dual) rho_g[prob] = rho;
       rentry_g[prob] = (double)s2;
       if (mode != MODE_CONT) merit_g[prob] = cost + S(0.5) * rho * s2 + sl;
     }
