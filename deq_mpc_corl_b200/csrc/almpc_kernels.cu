@@ -28,6 +28,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "almpc.h"
@@ -61,6 +62,7 @@ struct KParams {
   S ulo[ALMPC_MAX_NU], uhi[ALMPC_MAX_NU];
   double rho_mult, rho_max;
   int B, T, al_iter, max_newton, stream_mode, rho_f32, flags;
+  int part_off, ticket_total;  // k_line_search: slot offset of this part's CTA partials / CTAs of all parts
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1068,12 +1070,13 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
   cp_async_wait_all();
   // ---- batch-global statistics: per-CTA partials, last CTA reduces in a fixed order and steers the solve
   if (tid == 0) {
-    partials[blockIdx.x * 4 + 0] = blk0;
-    partials[blockIdx.x * 4 + 1] = blk1;
-    partials[blockIdx.x * 4 + 2] = blk2;
+    const int slot = P.part_off + blockIdx.x;
+    partials[slot * 4 + 0] = blk0;
+    partials[slot * 4 + 1] = blk1;
+    partials[slot * 4 + 2] = blk2;
     __threadfence();
     const unsigned tk = atomicAdd(&ctl->ticket, 1u);
-    is_last = (tk == gridDim.x - 1);
+    is_last = (tk == (unsigned)P.ticket_total - 1);
   }
   __syncthreads();
   if (!is_last) return;
@@ -1082,7 +1085,7 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
   {
     double s0 = 0, s1 = 0, s2 = 0;
     const volatile double* pv = partials;
-    for (int b = tid; b < (int)gridDim.x; b += nthr) {
+    for (int b = tid; b < P.ticket_total; b += nthr) {
       s0 += pv[b * 4 + 0];
       s1 += pv[b * 4 + 1];
       s2 = fmax(s2, pv[b * 4 + 2]);
@@ -1307,6 +1310,7 @@ static KParams<S> make_params(const almpc_desc* d) {
   P.rho_max = d->rho_max;
   P.B = d->B; P.T = d->T; P.al_iter = d->al_iter; P.max_newton = d->max_newton;
   P.stream_mode = d->stream_mode; P.rho_f32 = d->rho_f32; P.flags = d->flags;
+  P.part_off = 0; P.ticket_total = 0;
   return P;
 }
 
@@ -1321,6 +1325,7 @@ static int check_desc(const almpc_desc* d) {
 }
 
 constexpr int kWPB = 4;
+constexpr int kMaxParts = 4;
 
 // optional per-kernel timing (bench.py): events around every launch of one forward call
 static int g_profile_on = 0;
@@ -1354,7 +1359,7 @@ static WsPlan ws_plan(int B, int T, int nx, int nu, size_t es) {
   WsPlan w;
   size_t o = 0;
   w.ctl = o; o += 256;
-  w.partials = o; o = up(o + (size_t)ls_geom(B, T).blocks * 4 * sizeof(double));
+  w.partials = o; o = up(o + ((size_t)ls_geom(B, T).blocks + kMaxParts) * 4 * sizeof(double));
   w.merit = o; o = up(o + (size_t)B * es);
   w.rentry = o; o = up(o + (size_t)B * sizeof(double));
   w.status = o; o = up(o + (size_t)B * sizeof(int32_t));
@@ -1377,7 +1382,8 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   const Layout<NX, NU> L(T);
   const LsLayout<NX, NU> LL(T);
   const LsGeom lg = ls_geom(B, T);
-  const size_t smem_fac = (size_t)kWPB * L.total * sizeof(S);
+  size_t smem_fac = (size_t)kWPB * L.total * sizeof(S);
+  if (const char* pad = getenv("ALMPC_FAC_SMEM_PAD")) smem_fac += (size_t)atoi(pad);  // occupancy experiments
   size_t smem_ls = 2 * (size_t)lg.pls * LL.total * sizeof(S);  // double-buffered staging
   if (smem_ls < (size_t)lg.threads * 3 * sizeof(double)) smem_ls = (size_t)lg.threads * 3 * sizeof(double);
   const size_t smem_fin = (size_t)kWPB * (L.N + L.neq) * sizeof(S);
@@ -1404,7 +1410,8 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   if (e != cudaSuccess) return cuda_err(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
   int ls_grid = n_sm * (ls_per_sm > 0 ? ls_per_sm : 1);
   if (ls_grid > lg.blocks) ls_grid = lg.blocks;
-  const KParams<S> P = make_params<S>(d);
+  KParams<S> P = make_params<S>(d);
+  const bool prof_requested = g_profile_on != 0;
   const WsPlan w = ws_plan(B, T, NX, NU, sizeof(S));
   unsigned char* ws = (unsigned char*)workspace;
   Ctl* ctl = (Ctl*)(ws + w.ctl);
@@ -1419,13 +1426,67 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   if (e != cudaSuccess) return cuda_err(e, "cudaMemsetAsync(ctl)");
   e = cudaMemsetAsync(info_out, 0, ALMPC_INFO_INTS * sizeof(int32_t), st);
   if (e != cudaSuccess) return cuda_err(e, "cudaMemsetAsync(info)");
-  const long jac_items = (long)B * (T - 1) * NN;
-  const unsigned jac_blocks = (unsigned)((jac_items + 127) / 128);
+  // Optional (ALMPC_PARTS=2..4, default 1): process the batch in contiguous parts on separate streams so that
+  // the LSU-bound factor kernel of one part could overlap the FMA-bound jacobian / line-search kernels of
+  // another.  All parts feed the same batch-global statistics (one ticket counter) and the streams join
+  // after every Newton step.  Measured on B200 (quadrotor, 64K): no gain — k_factor_solve fills the SM's
+  // registers and shared memory, so CTAs of other kernels do not co-reside; kept as an experiment knob.
+  int nparts = 1;
+  {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    const char* env = getenv("ALMPC_PARTS");
+    if (env) nparts = atoi(env);
+    if (nparts < 1) nparts = 1;
+    if (nparts > kMaxParts) nparts = kMaxParts;
+    if (cs != cudaStreamCaptureStatusNone || prof_requested) nparts = 1;
+  }
+  static thread_local cudaStream_t aux[kMaxParts] = {nullptr};
+  static thread_local cudaEvent_t ev_fork = nullptr, ev_part[kMaxParts] = {nullptr};
+  static thread_local int aux_dev = -1;
+  if (nparts > 1 && (aux_dev != dev || !ev_fork)) {
+    for (int p = 0; p < kMaxParts; ++p) {
+      if (p > 0) { e = cudaStreamCreateWithFlags(&aux[p], cudaStreamNonBlocking); if (e != cudaSuccess) return cuda_err(e, "cudaStreamCreate"); }
+      e = cudaEventCreateWithFlags(&ev_part[p], cudaEventDisableTiming);
+      if (e != cudaSuccess) return cuda_err(e, "cudaEventCreate");
+    }
+    e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    if (e != cudaSuccess) return cuda_err(e, "cudaEventCreate");
+    aux_dev = dev;
+  }
+  struct Part { int lo, n, ls_grid, nb; unsigned jac_blocks; cudaStream_t s; KParams<S> P; };
+  Part parts[kMaxParts];
+  const int chunk = ((B + nparts - 1) / nparts + 7) & ~7;
+  int ticket_total = 0, np = 0;
+  for (int p = 0; p < nparts; ++p) {
+    const int lo = p * chunk;
+    if (lo >= B) break;
+    Part& pt = parts[np];
+    pt.lo = lo;
+    pt.n = (lo + chunk <= B) ? chunk : B - lo;
+    const int groups = (pt.n + lg.pls - 1) / lg.pls;
+    pt.ls_grid = ls_grid < groups ? ls_grid : groups;
+    pt.nb = n_blocks(pt.n);
+    pt.jac_blocks = (unsigned)(((long)pt.n * (T - 1) * NN + 127) / 128);
+    pt.s = (np == 0) ? st : aux[np];
+    pt.P = P;
+    pt.P.B = pt.n;
+    pt.P.part_off = ticket_total;
+    ticket_total += pt.ls_grid;
+    ++np;
+  }
+  for (int p = 0; p < np; ++p) parts[p].P.ticket_total = ticket_total;
+  const size_t FE = factor_elems<NX, NU>(T), GE = (size_t)(T - 1) * NX * NN, DBG = 2 * (size_t)L.N + 24;
+  if (np > 1) {
+    e = cudaEventRecord(ev_fork, st);
+    if (e != cudaSuccess) return cuda_err(e, "cudaEventRecord");
+    for (int p = 1; p < np; ++p) cudaStreamWaitEvent(parts[p].s, ev_fork, 0);
+  }
   const int nb = n_blocks(B);
   const int launches = d->al_iter * d->max_newton;
   ProfEv pe[3 * ALMPC_MAX_AL_ITER * 8 + 1];
   int npe = 0;
-  const bool prof = g_profile_on && launches * 3 + 1 <= (int)(sizeof(pe) / sizeof(pe[0]));
+  const bool prof = prof_requested && launches * 3 + 1 <= (int)(sizeof(pe) / sizeof(pe[0]));
   auto tic = [&](int kind) {
     if (!prof) return;
     cudaEventCreate(&pe[npe].a);
@@ -1439,17 +1500,31 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
     ++npe;
   };
   for (int i = 0; i < launches; ++i) {
-    tic(0);
-    kjac<<<jac_blocks, 128, 0, st>>>(P, x0, xu, G_g, c_g, ctl);
-    toc();
-    tic(1);
-    kfac<<<nb, kWPB * 32, smem_fac, st>>>(P, Qd, q, xu, lam, rho, factor, G_g, c_g, d_g, merit, rentry, status,
-                                          debug_out, ctl);
-    toc();
-    tic(2);
-    kls<<<ls_grid, lg.threads, smem_ls, st>>>(P, lg.pls, x0, Qd, q, xu, lam, rho, d_g, merit, rentry, status,
-                                                info_out, debug_out, ctl, partials);
-    toc();
+    for (int p = 0; p < np; ++p) {
+      const Part& pt = parts[p];
+      const size_t lo = (size_t)pt.lo;
+      S* dbg = debug_out ? debug_out + lo * DBG : nullptr;
+      tic(0);
+      kjac<<<pt.jac_blocks, 128, 0, pt.s>>>(pt.P, x0 + lo * NX, xu + lo * L.N, G_g + lo * GE, c_g + lo * L.neq, ctl);
+      toc();
+      tic(1);
+      kfac<<<pt.nb, kWPB * 32, smem_fac, pt.s>>>(pt.P, Qd + lo * L.N, q + lo * L.N, xu + lo * L.N, lam + lo * L.m,
+                                                 rho + lo, factor + lo * FE, G_g + lo * GE, c_g + lo * L.neq,
+                                                 d_g + lo * L.N, merit + lo, rentry + lo, status + lo, dbg, ctl);
+      toc();
+      tic(2);
+      kls<<<pt.ls_grid, lg.threads, smem_ls, pt.s>>>(pt.P, lg.pls, x0 + lo * NX, Qd + lo * L.N, q + lo * L.N,
+                                                      xu + lo * L.N, lam + lo * L.m, rho + lo, d_g + lo * L.N,
+                                                      merit + lo, rentry + lo, status + lo, info_out, dbg, ctl,
+                                                      partials);
+      toc();
+    }
+    if (np > 1) {  // join: every part must see the control block written by the globally last CTA
+      for (int p = 0; p < np; ++p) cudaEventRecord(ev_part[p], parts[p].s);
+      for (int p = 0; p < np; ++p)
+        for (int o = 0; o < np; ++o)
+          if (o != p) cudaStreamWaitEvent(parts[p].s, ev_part[o], 0);
+    }
   }
   tic(3);
   kfin<<<nb, kWPB * 32, smem_fin, st>>>(P, x0, xu, lam, rho, x_out, u_out, dyn_res_out, info_out, ctl);
