@@ -484,14 +484,16 @@ __global__ void __launch_bounds__(128)
 k_jacobian(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__ xu_g, S* __restrict__ G_g,
            S* __restrict__ c_g, const Ctl* __restrict__ ctl) {
   constexpr int NX = M::NX, NU = M::NU, NN = NX + NU;
+  constexpr int NTRIV = M::NTRIV;    // leading state columns the ODE does not depend on: identity columns
+  constexpr int NC = NN - NTRIV;     // tangent columns actually propagated per stage
   if (ctl->mode == MODE_DONE) return;
   const int T = P.T;
-  const int IT = (T - 1) * NN;
+  const int IT = (T - 1) * NC;
   const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long)P.B * IT) return;
   const int prob = (int)(gid / IT);
   const int it = (int)(gid - (long)prob * IT);
-  const int t = it / NN, j = it - t * NN;
+  const int t = it / NC, jj = it - t * NC, j = jj + NTRIV;
   const S* xz = xu_g + (size_t)prob * T * NN + (size_t)t * NN;
   Dual<S> xd[NX], ud[NU], xn[NX];
 #pragma unroll
@@ -503,9 +505,13 @@ k_jacobian(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__
 #pragma unroll
   for (int i = 0; i < NX; ++i) Gp[i * NN + j] = xn[i].d;
   S* cp = c_g + (size_t)prob * T * NX;
-  if (j == 0) {
+  if (jj == 0) {
 #pragma unroll
     for (int i = 0; i < NX; ++i) cp[t * NX + i] = xz[NN + i] - xn[i].v;
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int c = 0; c < NTRIV; ++c) Gp[i * NN + c] = (i == c) ? S(1) : S(0);
   }
   if (it == IT - 1) {  // the x_0 - x0 block (al_utils.py:219)
     const S* z0 = xu_g + (size_t)prob * T * NN;
@@ -1467,7 +1473,7 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
     const int groups = (pt.n + lg.pls - 1) / lg.pls;
     pt.ls_grid = ls_grid < groups ? ls_grid : groups;
     pt.nb = n_blocks(pt.n);
-    pt.jac_blocks = (unsigned)(((long)pt.n * (T - 1) * NN + 127) / 128);
+    pt.jac_blocks = (unsigned)(((long)pt.n * (T - 1) * (NN - M::NTRIV) + 127) / 128);
     pt.s = (np == 0) ? st : aux[np];
     pt.P = P;
     pt.P.B = pt.n;

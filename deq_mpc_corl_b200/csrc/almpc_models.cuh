@@ -152,6 +152,8 @@ __device__ __forceinline__ void quad_body(const V* m, const V* v, const V* w, co
 
 struct RexQuad {
   static constexpr int NX = 12, NU = 4;
+  // the ODE does not depend on the position r = x[0..2]: d x+ / d r = [I; 0], no tangent pass needed
+  static constexpr int NTRIV = 3;
   template <typename S, typename V>
   __device__ __forceinline__ static void f(const V* x, const V* u, V* xd, const S* p) {
     V q0, qv[3];
@@ -161,6 +163,7 @@ struct RexQuad {
 
 struct FlyingCartpole {
   static constexpr int NX = 14, NU = 4;
+  static constexpr int NTRIV = 3;  // position columns are identity (as for RexQuad)
   // state [r(3), m(3), theta, v(3), w(3), theta_dot]
   template <typename S, typename V>
   __device__ __forceinline__ static void f(const V* x, const V* u, V* xd, const S* p) {
@@ -177,6 +180,7 @@ struct FlyingCartpole {
 
 struct Pendulum {
   static constexpr int NX = 2, NU = 1;
+  static constexpr int NTRIV = 0;
   // qdd = 4 u - 2 * (9.81 sin q)
   template <typename S, typename V>
   __device__ __forceinline__ static void f(const V* x, const V* u, V* xd, const S* p) {
@@ -189,6 +193,7 @@ struct Pendulum {
 
 struct Cartpole1L {
   static constexpr int NX = 4, NU = 1;
+  static constexpr int NTRIV = 1;  // cart position does not enter the ODE
   // M = [[11,-c],[-c,2]], b = [s thd^2, -9.81 s], M qdd + b = [u, 0]
   template <typename S, typename V>
   __device__ __forceinline__ static void f(const V* x, const V* u, V* xd, const S* p) {
@@ -206,6 +211,7 @@ struct Cartpole1L {
 
 struct Cartpole2L {
   static constexpr int NX = 6, NU = 1;
+  static constexpr int NTRIV = 1;  // cart position does not enter the ODE
   // cart (10 kg) + two unit links, relative angles; M(q) qdd = tau - b(q,qd), solved by LDL^T of the 3x3
   template <typename S, typename V>
   __device__ __forceinline__ static void f(const V* x, const V* u, V* xd, const S* p) {
