@@ -208,7 +208,7 @@ __device__ __forceinline__ bool eliminate(S (&a)[NN], int lane, S* colbuf, int L
       a[k] = (lane == k) ? inv : lk;
       if (k + 1 < NN) {
         S* col = colbuf + (k & 1) * 32;
-        col[lane] = lk;
+        if (lane < NN) col[lane] = lk;  // only rows k+1..NN-1 of the pivot column are read
         __syncwarp();
         a[k + 1] -= lk * col[k + 1];
         d = __shfl_sync(FULL, a[k + 1], k + 1);
@@ -726,8 +726,18 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
     ok = eliminate<NN, true>(a, lane, scr) && ok;
     __syncwarp();
     if (lane < NN) {
+      if constexpr (NN % 2 == 0) {  // rows are 16-byte aligned: 128-bit stores
 #pragma unroll
-      for (int c = 0; c < NN; ++c) Lg[lane * NN + c] = (c <= lane) ? a[c] : S(0);
+        for (int c = 0; c < NN; c += 2) {
+          Vec2<S> v;
+          v.x = (c <= lane) ? a[c] : S(0);
+          v.y = (c + 1 <= lane) ? a[c + 1] : S(0);
+          *reinterpret_cast<Vec2<S>*>(Lg + lane * NN + c) = v;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NN; ++c) Lg[lane * NN + c] = (c <= lane) ? a[c] : S(0);
+      }
       if (NX > EX0 && has_G) {  // publish L for the second elimination pass
 #pragma unroll
         for (int c = 0; c < NN; ++c) scr[64 + lane * LD + c] = a[c];
@@ -739,9 +749,18 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
       const int i = lane - NN - 1;
       if (i < NX && has_G && NX <= EX0) {
 #pragma unroll
-        for (int c = 0; c < NN; ++c) {
-          X[i * LB + c] = a[c];
-          Eg[i * NN + c] = a[c];
+        for (int c = 0; c < NN; ++c) X[i * LB + c] = a[c];
+        if constexpr (NN % 2 == 0) {
+#pragma unroll
+          for (int c = 0; c < NN; c += 2) {
+            Vec2<S> v;
+            v.x = a[c];
+            v.y = a[c + 1];
+            *reinterpret_cast<Vec2<S>*>(Eg + i * NN + c) = v;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < NN; ++c) Eg[i * NN + c] = a[c];
         }
       }
     }
