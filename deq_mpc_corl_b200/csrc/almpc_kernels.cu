@@ -40,6 +40,9 @@
 #ifndef ALMPC_NO_CP16
 #define ALMPC_NO_CP16 0
 #endif
+#ifndef ALMPC_FAC_MINB
+#define ALMPC_FAC_MINB 6  // CTAs/SM the factor kernel is compiled for (register cap 80; 5..7 measured within 2%)
+#endif
 
 namespace almpc {
 
@@ -200,7 +203,7 @@ __device__ __forceinline__ bool eliminate(S (&a)[NN], int lane, S* colbuf, int L
     // software-pipelined pivots: as soon as column k+1 has its update, the next pivot is broadcast and its
     // reciprocal square root (the longest dependent chain of the step) runs under the remaining updates
     S d = __shfl_sync(FULL, a[0], 0);
-    ok = (d > S(0)) && (d < S(1e30));
+    ok = (d > S(0));
     S inv = rsqrt_(d);
 #pragma unroll
     for (int k = 0; k < NN; ++k) {
@@ -212,7 +215,7 @@ __device__ __forceinline__ bool eliminate(S (&a)[NN], int lane, S* colbuf, int L
         __syncwarp();
         a[k + 1] -= lk * col[k + 1];
         d = __shfl_sync(FULL, a[k + 1], k + 1);
-        ok = ok && (d > S(0)) && (d < S(1e30));
+        ok = ok && (d > S(0));
         inv = rsqrt_(d);
         // rest of the pivot column: one scalar head (odd start), 16-byte pairs, one scalar tail (odd NN)
         constexpr bool kVec = !ALMPC_NO_VEC2;
@@ -525,7 +528,7 @@ k_jacobian(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__
 // 1 warp = 1 problem.
 // ------------------------------------------------------------------------------------------------
 template <int NX, int NU, typename S, int WPB>
-__global__ void __launch_bounds__(WPB * 32, 7)
+__global__ void __launch_bounds__(WPB * 32, ALMPC_FAC_MINB)
 k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restrict__ q_g, const S* __restrict__ xu_g,
                S* __restrict__ lam_g, S* __restrict__ rho_g, S* fac_g, const S* __restrict__ G_g,
                const S* __restrict__ c_g, S* __restrict__ d_g, S* __restrict__ merit_g, double* __restrict__ rentry_g,
@@ -838,8 +841,7 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
 #pragma unroll
     for (int r = NN - 1; r >= 0; --r) {
       const S dr = __shfl_sync(FULL, b * l[r], r);  // lane r: l[r] = 1/L_rr
-      if (lane == r) b = dr;
-      else if (lane < r) b -= l[r] * dr;
+      b = (lane == r) ? dr : (b - l[r] * dr);       // l[r] = 0 on lanes > r
     }
     if (lane < NN) dv[t * NN + lane] = b;
     S* tmp = Ecur; Ecur = Enext; Enext = tmp;
