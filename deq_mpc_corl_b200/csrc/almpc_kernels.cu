@@ -863,6 +863,121 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
 // kernel 3/3: 20-point line search + iterate update + batch-global stop statistics / control block.
 // 1 thread = 1 (problem, candidate k, stage t); `pls` problems per CTA.
 // ------------------------------------------------------------------------------------------------
+// Executed by the LAST CTA of the line-search launch: deterministic reduction of the per-CTA statistics and the
+// batch-global decisions of the reference (stop rule al_utils.py:560-564, rho_max exit AL_mpc.py:412).
+template <typename S>
+__device__ __forceinline__ void steer_solve(const KParams<S>& P, Ctl* ctl, int* info_g, const double* partials,
+                                            double (*fin_red)[3], int tid, int nthr, int al_a, int nk) {
+  {
+    double s0 = 0, s1 = 0, s2 = 0;
+    const volatile double* pv = partials;
+    for (int b = tid; b < P.ticket_total; b += nthr) {
+      s0 += pv[b * 4 + 0];
+      s1 += pv[b * 4 + 1];
+      s2 = fmax(s2, pv[b * 4 + 2]);
+    }
+    fin_red[tid][0] = s0;
+    fin_red[tid][1] = s1;
+    fin_red[tid][2] = s2;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int i = 0; i < nthr; ++i) { s0 += fin_red[i][0]; s1 += fin_red[i][1]; s2 = fmax(s2, fin_red[i][2]); }
+    const double R_entry = sqrt(s0), R_exit = sqrt(s1), rho_max_used = s2;
+    const double res_old = (nk == 0) ? R_entry : ctl->res_old;
+    // al_utils.py:560-564 — evaluated exactly as written there (NaN compares false -> no break)
+    bool stop = (fabs(res_old - R_exit) / R_exit < 1e-3) || (R_exit < 1e-3);
+    const int steps_done = nk + 1;
+    if (steps_done >= P.max_newton) stop = true;
+    ctl->ticket = 0;
+    ctl->total_newton += 1;
+    info_g[ALMPC_INFO_TOTAL_NEWTON] = ctl->total_newton;
+    if (!stop) {
+      ctl->k = steps_done;
+      ctl->mode = MODE_CONT;
+      ctl->res_old = R_exit;
+    } else {
+      info_g[ALMPC_INFO_NEWTON0 + al_a] = steps_done;
+      info_g[ALMPC_INFO_AL_DONE] = al_a + 1;
+      double rho_next = rho_max_used * P.rho_mult;
+      if (P.rho_f32) rho_next = (double)(float)rho_next;
+      ctl->rho_final_max = rho_next;
+      const bool exceed = P.stream_mode && (rho_next > P.rho_max);
+      if (al_a + 1 >= P.al_iter || exceed) {
+        ctl->mode = MODE_DONE;
+      } else {
+        ctl->a = al_a + 1;
+        ctl->k = 0;
+        ctl->mode = MODE_DUAL_NEWTON;
+      }
+    }
+  }
+}
+
+// One line-search item: candidate alpha = 2^-kk, stage t.  Evaluates the stage's share of the merit
+// (al_utils.py:52-77): cost, sum c+^2 and lam.c of the dynamics residual x_{t+1} - f(x_t,u_t), the control
+// bounds of stage t (and of the last stage for t = T-2) and the initial-state residual (t = 0).
+template <class M, typename S>
+__device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU>& L, const KParams<S>& P, int T,
+                                        int kk, int t, S& cost, S& s2, S& sl) {
+  constexpr int NX = M::NX, NU = M::NU, NN = NX + NU, LS = NN | 1;
+  const S* xu = sp + L.xu;
+  const S* dv = sp + L.d;
+  const S* lam = sp + L.lam;
+  const S* Qd = sp + L.Qd;
+  const S* qv = sp + L.q;
+  const S* x0 = sp + L.x0;
+    const S alpha = (S)ldexpf(1.0f, -kk);
+    S xs[NX], us[NU], xn[NX];
+    cost = S(0); s2 = S(0); sl = S(0);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      const S z = xu[t * LS + i] + alpha * dv[t * LS + i];
+      xs[i] = z;
+      cost += S(0.5) * (z * Qd[t * LS + i] * z) + qv[t * LS + i] * z;
+    }
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      const S z = xu[t * LS + NX + i] + alpha * dv[t * LS + NX + i];
+      us[i] = z;
+      cost += S(0.5) * (z * Qd[t * LS + NX + i] * z) + qv[t * LS + NX + i] * z;
+      const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
+      sl += lam[L.neq + t * 2 * NU + i] * cu + lam[L.neq + t * 2 * NU + NU + i] * cl;
+      const S pu = fmax0(cu), pl = fmax0(cl);
+      s2 += pu * pu + pl * pl;
+    }
+    if (t == 0) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        const S ci = xs[i] - x0[i];
+        s2 += ci * ci;
+        sl += lam[(T - 1) * NX + i] * ci;
+      }
+    }
+    rk4_step<M, S, S>(xs, us, xn, P.dyn);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      const S z1 = xu[(t + 1) * LS + i] + alpha * dv[(t + 1) * LS + i];
+      const S ci = z1 - xn[i];
+      s2 += ci * ci;
+      sl += lam[t * NX + i] * ci;
+      if (t == T - 2) cost += S(0.5) * (z1 * Qd[(t + 1) * LS + i] * z1) + qv[(t + 1) * LS + i] * z1;
+    }
+    if (t == T - 2) {
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        const int e = (T - 1) * LS + NX + i;
+        const S z = xu[e] + alpha * dv[e];
+        cost += S(0.5) * (z * Qd[e] * z) + qv[e] * z;
+        const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
+        sl += lam[L.neq + (T - 1) * 2 * NU + i] * cu + lam[L.neq + (T - 1) * 2 * NU + NU + i] * cl;
+        const S pu = fmax0(cu), pl = fmax0(cl);
+        s2 += pu * pu + pl * pl;
+      }
+    }
+}
+
 // asynchronous staging of one problem's line-search inputs into shared memory (all threads of the CTA)
 template <int NX, int NU, typename S>
 __device__ __forceinline__ void ls_stage_async(S* sp, const LsLayout<NX, NU>& L, int prob, int tid, int nthr,
@@ -953,62 +1068,10 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
     const int p = wi / IT, it = wi - p * IT;
     if (prob0 + p >= P.B) continue;
     const S* sp = base + (size_t)p * L.total;
-    const S* xu = sp + L.xu;
-    const S* dv = sp + L.d;
-    const S* lam = sp + L.lam;
-    const S* Qd = sp + L.Qd;
-    const S* qv = sp + L.q;
-    const S* x0 = sp + L.x0;
     S* part = const_cast<S*>(sp) + L.part;
     const int kk = it / (T - 1), t = it - kk * (T - 1);
-    const S alpha = (S)ldexpf(1.0f, -kk);
-    S xs[NX], us[NU], xn[NX];
-    S cost = S(0), s2 = S(0), sl = S(0);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-      const S z = xu[t * LS + i] + alpha * dv[t * LS + i];
-      xs[i] = z;
-      cost += S(0.5) * (z * Qd[t * LS + i] * z) + qv[t * LS + i] * z;
-    }
-#pragma unroll
-    for (int i = 0; i < NU; ++i) {
-      const S z = xu[t * LS + NX + i] + alpha * dv[t * LS + NX + i];
-      us[i] = z;
-      cost += S(0.5) * (z * Qd[t * LS + NX + i] * z) + qv[t * LS + NX + i] * z;
-      const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
-      sl += lam[L.neq + t * 2 * NU + i] * cu + lam[L.neq + t * 2 * NU + NU + i] * cl;
-      const S pu = fmax0(cu), pl = fmax0(cl);
-      s2 += pu * pu + pl * pl;
-    }
-    if (t == 0) {
-#pragma unroll
-      for (int i = 0; i < NX; ++i) {
-        const S ci = xs[i] - x0[i];
-        s2 += ci * ci;
-        sl += lam[(T - 1) * NX + i] * ci;
-      }
-    }
-    rk4_step<M, S, S>(xs, us, xn, P.dyn);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-      const S z1 = xu[(t + 1) * LS + i] + alpha * dv[(t + 1) * LS + i];
-      const S ci = z1 - xn[i];
-      s2 += ci * ci;
-      sl += lam[t * NX + i] * ci;
-      if (t == T - 2) cost += S(0.5) * (z1 * Qd[(t + 1) * LS + i] * z1) + qv[(t + 1) * LS + i] * z1;
-    }
-    if (t == T - 2) {
-#pragma unroll
-      for (int i = 0; i < NU; ++i) {
-        const int e = (T - 1) * LS + NX + i;
-        const S z = xu[e] + alpha * dv[e];
-        cost += S(0.5) * (z * Qd[e] * z) + qv[e] * z;
-        const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
-        sl += lam[L.neq + (T - 1) * 2 * NU + i] * cu + lam[L.neq + (T - 1) * 2 * NU + NU + i] * cl;
-        const S pu = fmax0(cu), pl = fmax0(cl);
-        s2 += pu * pu + pl * pl;
-      }
-    }
+    S cost, s2, sl;
+    ls_item<M, S>(sp, L, P, T, kk, t, cost, s2, sl);
     part[it * 3 + 0] = cost;
     part[it * 3 + 1] = s2;
     part[it * 3 + 2] = sl;
@@ -1108,52 +1171,162 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  double (*fin_red)[3] = reinterpret_cast<double (*)[3]>(smem_raw);  // staging area is dead by now
-  {
-    double s0 = 0, s1 = 0, s2 = 0;
-    const volatile double* pv = partials;
-    for (int b = tid; b < P.ticket_total; b += nthr) {
-      s0 += pv[b * 4 + 0];
-      s1 += pv[b * 4 + 1];
-      s2 = fmax(s2, pv[b * 4 + 2]);
+  steer_solve<S>(P, ctl, info_g, partials, reinterpret_cast<double (*)[3]>(smem_raw), tid, nthr, al_a, nk);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 3/3, warp-synchronous variant for horizons with (T-1) | 32  (T = 2, 3, 5, 9, 17, 33).
+// One warp owns PW = max(1, 8/(T-1)) problems at a time (PW * 20 * (T-1) items = a whole number of 32-lane
+// rounds, no idle lanes); the T-1 stage items of a candidate sit in adjacent lanes, so candidate totals are
+// segmented shuffle reductions and there is no CTA barrier and no partial-sum traffic in the loop.
+// ------------------------------------------------------------------------------------------------
+template <class M, typename S, int TM1, int WPB>
+__global__ void __launch_bounds__(WPB * 32, 4)
+k_line_search_warp(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__ Qd_g,
+                   const S* __restrict__ q_g, S* xu_g, const S* __restrict__ lam_g, const S* __restrict__ rho_g,
+                   const S* __restrict__ d_g, S* __restrict__ merit_g, const double* __restrict__ rentry_g,
+                   int* __restrict__ status_g, int* __restrict__ info_g, S* __restrict__ debug_g, Ctl* ctl,
+                   double* __restrict__ partials) {
+  constexpr int NX = M::NX, NU = M::NU, NN = NX + NU, LS = NN | 1;
+  constexpr int PW = (8 / TM1) > 0 ? (8 / TM1) : 1;
+  constexpr int IT = NLS * TM1;          // items per problem
+  constexpr int ROUNDS = PW * IT / 32;
+  static_assert((PW * IT) % 32 == 0 && 32 % TM1 == 0, "warp variant needs (T-1) | 32");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double wred[WPB][3];
+  __shared__ bool is_last;
+  const int mode = ctl->mode;
+  if (mode == MODE_DONE) return;
+  const int al_a = ctl->a, nk = ctl->k;
+  constexpr int T = TM1 + 1;
+  const LsLayout<NX, NU> L(T);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int stride = L.part;  // staged scalars per problem (the partial-sum area of the CTA variant is unused)
+  S* wsm = reinterpret_cast<S*>(smem_raw) + (size_t)warp * PW * stride;
+  const int ngroups = (P.B + PW - 1) / PW;
+  const int gwarp = blockIdx.x * WPB + warp, nwarps = gridDim.x * WPB;
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;  // this warp's running statistics (identical on all lanes)
+
+  for (int grp = gwarp; grp < ngroups; grp += nwarps) {
+    const int prob0 = grp * PW;
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < PW; ++p) {
+      if (prob0 + p < P.B)
+        ls_stage_async<NX, NU, S>(wsm + (size_t)p * stride, L, prob0 + p, lane, 32, x0_g, Qd_g, q_g, xu_g, lam_g, d_g);
     }
-    fin_red[tid][0] = s0;
-    fin_red[tid][1] = s1;
-    fin_red[tid][2] = s2;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    double s0 = 0, s1 = 0, s2 = 0;
-    for (int i = 0; i < nthr; ++i) { s0 += fin_red[i][0]; s1 += fin_red[i][1]; s2 = fmax(s2, fin_red[i][2]); }
-    const double R_entry = sqrt(s0), R_exit = sqrt(s1), rho_max_used = s2;
-    const double res_old = (nk == 0) ? R_entry : ctl->res_old;
-    // al_utils.py:560-564 — evaluated exactly as written there (NaN compares false -> no break)
-    bool stop = (fabs(res_old - R_exit) / R_exit < 1e-3) || (R_exit < 1e-3);
-    const int steps_done = nk + 1;
-    if (steps_done >= P.max_newton) stop = true;
-    ctl->ticket = 0;
-    ctl->total_newton += 1;
-    info_g[ALMPC_INFO_TOTAL_NEWTON] = ctl->total_newton;
-    if (!stop) {
-      ctl->k = steps_done;
-      ctl->mode = MODE_CONT;
-      ctl->res_old = R_exit;
-    } else {
-      info_g[ALMPC_INFO_NEWTON0 + al_a] = steps_done;
-      info_g[ALMPC_INFO_AL_DONE] = al_a + 1;
-      double rho_next = rho_max_used * P.rho_mult;
-      if (P.rho_f32) rho_next = (double)(float)rho_next;
-      ctl->rho_final_max = rho_next;
-      const bool exceed = P.stream_mode && (rho_next > P.rho_max);
-      if (al_a + 1 >= P.al_iter || exceed) {
-        ctl->mode = MODE_DONE;
-      } else {
-        ctl->a = al_a + 1;
-        ctl->k = 0;
-        ctl->mode = MODE_DUAL_NEWTON;
+    cp_async_commit();
+    // per-problem scalars travel in registers while the copies are in flight
+    S rho_p[PW], mcur_p[PW];
+    double rent_p[PW];
+#pragma unroll
+    for (int p = 0; p < PW; ++p) {
+      const bool v = prob0 + p < P.B;
+      rho_p[p] = v ? rho_g[prob0 + p] : S(0);
+      mcur_p[p] = v ? merit_g[prob0 + p] : S(0);
+      rent_p[p] = v ? rentry_g[prob0 + p] : 0.0;
+    }
+    cp_async_wait_all();
+    __syncwarp();
+
+    S best_v[PW], best_r2[PW];
+    int best_i[PW];
+    bool nan_p[PW];
+#pragma unroll
+    for (int p = 0; p < PW; ++p) { best_v[p] = S(INFINITY); best_r2[p] = S(0); best_i[p] = NLS; nan_p[p] = false; }
+#pragma unroll 1
+    for (int r = 0; r < ROUNDS; ++r) {
+      const int w = r * 32 + lane;
+      const int p = w / IT, it = w - p * IT;
+      const int kk = it / TM1, t = it - kk * TM1;
+      const bool valid = prob0 + p < P.B;
+      S cost = S(0), s2 = S(0), sl = S(0);
+      if (valid) ls_item<M, S>(wsm + (size_t)p * stride, L, P, T, kk, t, cost, s2, sl);
+      // candidate totals: the TM1 stage items of a candidate are adjacent lanes; fixed summation order t=0..TM1-1
+      S c_tot = S(0), s_tot = S(0), l_tot = S(0);
+#pragma unroll
+      for (int tt = 0; tt < TM1; ++tt) {
+        const int src = (lane & ~(TM1 - 1)) + tt;
+        c_tot += __shfl_sync(FULL, cost, src);
+        s_tot += __shfl_sync(FULL, s2, src);
+        l_tot += __shfl_sync(FULL, sl, src);
+      }
+#pragma unroll
+      for (int q = 0; q < PW; ++q) {
+        if (valid && p == q && t == 0) {
+          const S mk = c_tot + S(0.5) * rho_p[q] * s_tot + l_tot;
+          if (debug_g) debug_g[(size_t)(prob0 + q) * (2 * L.N + 24) + 2 * L.N + kk] = mk;
+          if (mk != mk) nan_p[q] = true;
+          if (mk < best_v[q] || (mk == best_v[q] && kk < best_i[q])) { best_v[q] = mk; best_i[q] = kk; best_r2[q] = s_tot; }
+        }
+      }
+    }
+    // per problem: first-argmin over the lanes (torch.min NaN semantics), accept, iterate update
+#pragma unroll
+    for (int q = 0; q < PW; ++q) {
+      const int prob = prob0 + q;
+      if (prob >= P.B) continue;  // uniform across the warp
+      S bv = best_v[q], br2 = best_r2[q];
+      int bi = best_i[q];
+      const bool any_nan = __any_sync(FULL, nan_p[q]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const S ov = __shfl_xor_sync(FULL, bv, o);
+        const S or2 = __shfl_xor_sync(FULL, br2, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; br2 = or2; }
+      }
+      if (bi >= NLS) { bi = 0; br2 = S(0); }  // all +inf
+      if (any_nan) bv = S(NAN);
+      const bool accept = bv < mcur_p[q];
+      const S alpha = (S)ldexpf(1.0f, -bi);
+      const S* xu = wsm + (size_t)q * stride + L.xu;
+      const S* dv = wsm + (size_t)q * stride + L.d;
+      bool fin = true;
+      const size_t pN = (size_t)prob * L.N;
+      for (int i = lane; i < L.N; i += 32) {
+        const int ts = i / NN, si = ts * LS + (i - ts * NN);
+        const S xo = xu[si];
+        const S xnew = xo + alpha * dv[si];
+        const S xr = accept ? xnew : (finite_(xnew) ? xo : S(NAN));  // al_utils.py:640-641
+        fin = fin && finite_(xr);
+        if (accept || !finite_(xnew)) xu_g[pN + i] = xr;
+      }
+      fin = __all_sync(FULL, fin);
+      const double r_exit = accept ? (double)br2 : (fin ? rent_p[q] : (double)NAN);
+      acc0 += rent_p[q];
+      acc1 += r_exit;
+      acc2 = fmax(acc2, (double)rho_p[q]);
+      if (lane == 0) {
+        merit_g[prob] = bv;  // merit <- new_merit even when the step was rejected (al_utils.py:569)
+        if (!fin) status_g[prob] &= ~ALMPC_STATUS_FINITE;
+        if (debug_g) {
+          S* dbg = debug_g + (size_t)prob * (2 * L.N + 24) + 2 * L.N + NLS;
+          dbg[0] = (S)bi;
+          dbg[1] = accept ? S(1) : S(0);
+          dbg[2] = mcur_p[q];
+        }
       }
     }
   }
+  if (lane == 0) { wred[warp][0] = acc0; wred[warp][1] = acc1; wred[warp][2] = acc2; }
+  __syncthreads();
+  if (tid == 0) {
+    double b0 = 0, b1 = 0, b2 = 0;
+    for (int w = 0; w < WPB; ++w) { b0 += wred[w][0]; b1 += wred[w][1]; b2 = fmax(b2, wred[w][2]); }
+    const int slot = P.part_off + blockIdx.x;
+    partials[slot * 4 + 0] = b0;
+    partials[slot * 4 + 1] = b1;
+    partials[slot * 4 + 2] = b2;
+    __threadfence();
+    const unsigned tk = atomicAdd(&ctl->ticket, 1u);
+    is_last = (tk == (unsigned)P.ticket_total - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  steer_solve<S>(P, ctl, info_g, partials, reinterpret_cast<double (*)[3]>(smem_raw), tid, nthr, al_a, nk);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1397,6 +1570,29 @@ static WsPlan ws_plan(int B, int T, int nx, int nu, size_t es) {
   return w;
 }
 
+constexpr int kWLS = 4;  // warps per CTA of the warp-synchronous line search
+
+struct LsWarpCfg { const void* fn; int grid_cap; size_t smem; int pw; };
+
+template <class M, typename S, int TM1>
+static cudaError_t ls_warp_cfg(LsWarpCfg& c, int n_sm) {
+  constexpr int PW = (8 / TM1) > 0 ? (8 / TM1) : 1;
+  const LsLayout<M::NX, M::NU> LL(TM1 + 1);
+  auto k = k_line_search_warp<M, S, TM1, kWLS>;
+  size_t smem = (size_t)kWLS * PW * LL.part * sizeof(S);
+  if (smem < (size_t)kWLS * 32 * 3 * sizeof(double)) smem = (size_t)kWLS * 32 * 3 * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kWLS * 32, smem);
+  if (e != cudaSuccess) return e;
+  c.fn = (const void*)k;
+  c.grid_cap = n_sm * (per_sm > 0 ? per_sm : 1);
+  c.smem = smem;
+  c.pw = PW;
+  return cudaSuccess;
+}
+
 template <class M, typename S>
 static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* q, S* xu, S* lam, S* rho, S* factor,
                         float* x_out, float* u_out, S* dyn_res_out, int32_t* status_out, int32_t* info_out,
@@ -1437,6 +1633,20 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   if (e != cudaSuccess) return cuda_err(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
   int ls_grid = n_sm * (ls_per_sm > 0 ? ls_per_sm : 1);
   if (ls_grid > lg.blocks) ls_grid = lg.blocks;
+  // warp-synchronous line search when the stage items of a candidate fit a power-of-two lane group
+  LsWarpCfg lw{nullptr, 0, 0, 1};
+  if (!getenv("ALMPC_LS_CTA")) {
+    switch (T - 1) {
+      case 1: e = ls_warp_cfg<M, S, 1>(lw, n_sm); break;
+      case 2: e = ls_warp_cfg<M, S, 2>(lw, n_sm); break;
+      case 4: e = ls_warp_cfg<M, S, 4>(lw, n_sm); break;
+      case 8: e = ls_warp_cfg<M, S, 8>(lw, n_sm); break;
+      case 16: e = ls_warp_cfg<M, S, 16>(lw, n_sm); break;
+      case 32: e = ls_warp_cfg<M, S, 32>(lw, n_sm); break;
+      default: break;
+    }
+    if (e != cudaSuccess) return cuda_err(e, "line-search (warp) configuration");
+  }
   KParams<S> P = make_params<S>(d);
   const bool prof_requested = g_profile_on != 0;
   const WsPlan w = ws_plan(B, T, NX, NU, sizeof(S));
@@ -1491,8 +1701,14 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
     Part& pt = parts[np];
     pt.lo = lo;
     pt.n = (lo + chunk <= B) ? chunk : B - lo;
-    const int groups = (pt.n + lg.pls - 1) / lg.pls;
-    pt.ls_grid = ls_grid < groups ? ls_grid : groups;
+    if (lw.fn) {
+      const int groups = (pt.n + lw.pw - 1) / lw.pw;
+      const int ctas = (groups + kWLS - 1) / kWLS;
+      pt.ls_grid = lw.grid_cap < ctas ? lw.grid_cap : ctas;
+    } else {
+      const int groups = (pt.n + lg.pls - 1) / lg.pls;
+      pt.ls_grid = ls_grid < groups ? ls_grid : groups;
+    }
     pt.nb = n_blocks(pt.n);
     pt.jac_blocks = (unsigned)(((long)pt.n * (T - 1) * (NN - M::NTRIV) + 127) / 128);
     pt.s = (np == 0) ? st : aux[np];
@@ -1540,10 +1756,22 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
                                                  d_g + lo * L.N, merit + lo, rentry + lo, status + lo, dbg, ctl);
       toc();
       tic(2);
-      kls<<<pt.ls_grid, lg.threads, smem_ls, pt.s>>>(pt.P, lg.pls, x0 + lo * NX, Qd + lo * L.N, q + lo * L.N,
-                                                      xu + lo * L.N, lam + lo * L.m, rho + lo, d_g + lo * L.N,
-                                                      merit + lo, rentry + lo, status + lo, info_out, dbg, ctl,
-                                                      partials);
+      if (lw.fn) {
+        const S *a_x0 = x0 + lo * NX, *a_Qd = Qd + lo * L.N, *a_q = q + lo * L.N, *a_lam = lam + lo * L.m;
+        const S *a_rho = rho + lo, *a_d = d_g + lo * L.N;
+        S *a_xu = xu + lo * L.N, *a_merit = merit + lo;
+        const double* a_re = rentry + lo;
+        int* a_st = status + lo;
+        void* args[] = {(void*)&pt.P, &a_x0, &a_Qd, &a_q, &a_xu, &a_lam, &a_rho, &a_d, &a_merit, &a_re, &a_st,
+                        &info_out, &dbg, &ctl, &partials};
+        e = cudaLaunchKernel(lw.fn, dim3(pt.ls_grid), dim3(kWLS * 32), args, lw.smem, pt.s);
+        if (e != cudaSuccess) return cuda_err(e, "k_line_search_warp launch");
+      } else {
+        kls<<<pt.ls_grid, lg.threads, smem_ls, pt.s>>>(pt.P, lg.pls, x0 + lo * NX, Qd + lo * L.N, q + lo * L.N,
+                                                        xu + lo * L.N, lam + lo * L.m, rho + lo, d_g + lo * L.N,
+                                                        merit + lo, rentry + lo, status + lo, info_out, dbg, ctl,
+                                                        partials);
+      }
       toc();
     }
     if (np > 1) {  // join: every part must see the control block written by the globally last CTA
