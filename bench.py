@@ -421,7 +421,7 @@ def main():
             },
             "flops_per_solve": fl["newton"] * n_newton + 2 * fl["dual"] + fl["bwd"],
         }
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:
             v, steps, secs = cpu_oracle_run(model, T, args.cpu_sample, dtype, 1003)
             line["cpu_baseline"] = {
                 "value": v, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
