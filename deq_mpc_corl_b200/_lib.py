@@ -83,6 +83,13 @@ def load():
         p = getattr(lib, "almpc_fma_peak_" + sfx)
         p.argtypes = [i32, i32, vp, ctypes.POINTER(dbl), vp]
         p.restype = ctypes.c_int
+    for sfx in ("f64", "f32"):
+        f = getattr(lib, "almpc_tracking_cost_" + sfx)
+        f.argtypes = [i32] * 4 + [vp] * 7
+        f.restype = ctypes.c_int
+        f = getattr(lib, "almpc_tracking_cost_bwd_" + sfx)
+        f.argtypes = [i32] * 4 + [vp] * 10
+        f.restype = ctypes.c_int
     lib.almpc_set_profiling.argtypes = [i32]
     lib.almpc_set_profiling.restype = None
     lib.almpc_get_profile.argtypes = [ctypes.POINTER(dbl)]
@@ -95,6 +102,7 @@ EXPORTS = [
     "almpc_model_dims", "almpc_factor_elems", "almpc_workspace_bytes", "almpc_debug_elems",
     "almpc_forward_f64", "almpc_forward_f32", "almpc_backward_f64", "almpc_backward_f32",
     "almpc_dynamics_f64", "almpc_dynamics_f32", "almpc_fma_peak_f64", "almpc_fma_peak_f32",
+    "almpc_tracking_cost_f64", "almpc_tracking_cost_f32", "almpc_tracking_cost_bwd_f64", "almpc_tracking_cost_bwd_f32",
     "almpc_set_profiling", "almpc_get_profile", "almpc_last_error", "almpc_version",
 ]
 

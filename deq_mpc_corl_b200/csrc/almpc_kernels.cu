@@ -84,6 +84,10 @@ __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
 template <typename S> __device__ __forceinline__ S fmax0(S x) { return x > S(0) ? x : S(0); }
 template <typename S> __device__ __forceinline__ bool finite_(S x) { return (x - x) == S(0); }
 
+// Programmatic dependent launch: the step kernels are launched with stream serialization relaxed, so a kernel's
+// CTAs are scheduled while the previous kernel drains; nothing of the predecessor may be read before this wait.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <typename S> struct alignas(2 * sizeof(S)) Vec2 { S x, y; };
 
 // Ampere-style asynchronous global->shared copies (LDGSTS): the factor kernel prefetches the next stage's
@@ -489,6 +493,7 @@ k_jacobian(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__
   constexpr int NX = M::NX, NU = M::NU, NN = NX + NU;
   constexpr int NTRIV = M::NTRIV;    // leading state columns the ODE does not depend on: identity columns
   constexpr int NC = NN - NTRIV;     // tangent columns actually propagated per stage
+  grid_dep_wait();
   if (ctl->mode == MODE_DONE) return;
   const int T = P.T;
   const int IT = (T - 1) * NC;
@@ -539,6 +544,7 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
   constexpr int CW = CopyWidth<NX, NU, S>::W;
   constexpr int LB = NN | 1;  // odd row stride of the staged G / E blocks (bank-conflict free rows)
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  grid_dep_wait();
   const int mode = ctl->mode;
   if (mode == MODE_DONE) return;
   const int T = P.T;
@@ -1026,6 +1032,7 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[8][3];
   __shared__ bool is_last;
+  grid_dep_wait();
   const int mode = ctl->mode;
   if (mode == MODE_DONE) return;
   const int al_a = ctl->a, nk = ctl->k;
@@ -1195,6 +1202,7 @@ k_line_search_warp(const KParams<S> P, const S* __restrict__ x0_g, const S* __re
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double wred[WPB][3];
   __shared__ bool is_last;
+  grid_dep_wait();
   const int mode = ctl->mode;
   if (mode == MODE_DONE) return;
   const int al_a = ctl->a, nk = ctl->k;
@@ -1344,6 +1352,7 @@ k_final_dual(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict
   const Layout<NX, NU> L(T);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int prob = blockIdx.x * WPB + warp;
+  grid_dep_wait();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     info_g[ALMPC_INFO_RHO_EXCEEDED] = (ctl->rho_final_max > P.rho_max) ? 1 : 0;
   }
@@ -1472,6 +1481,50 @@ __global__ void k_dynamics(const KParams<S> P, int64_t R, const S* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tracking cost build / its backward (deqmpc/policies.py:1285-1297 compute_pf, :1245-1248 q_scaling):
+//   Qd[b,t,j] = Q0[j] (1 + s[b,t]) ;  q[b,t,j] = -Qd[b,t,j] ref[b,t,j] ,  ref = [x_ref | u_ref] (fp32 network output)
+// fuses the cat / cast / diag-embed / multiply chain of the caller into one pass over the batch.
+// ------------------------------------------------------------------------------------------------
+template <typename S>
+__global__ void k_tracking_cost(int B, int T, int nx, int nu, const S* __restrict__ Q0, const float* __restrict__ x_ref,
+                                const float* __restrict__ u_ref, const float* __restrict__ scale,
+                                S* __restrict__ Qd, S* __restrict__ q) {
+  const int n = nx + nu;
+  const long total = (long)B * T * n;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long bt = i / n;
+    const int j = (int)(i - bt * n);
+    const S r = (S)(j < nx ? x_ref[bt * nx + j] : u_ref[bt * nu + (j - nx)]);
+    const S Qv = scale ? Q0[j] * (S(1) + (S)scale[bt]) : Q0[j];
+    Qd[i] = Qv;
+    q[i] = -(Qv * r);
+  }
+}
+
+// grad_xref / grad_uref = -Qd * grad_q ; grad_scale[b,t] = sum_j Q0[j] (grad_Q - grad_q * ref)   (one thread per (b,t))
+template <typename S>
+__global__ void k_tracking_cost_bwd(int B, int T, int nx, int nu, const S* __restrict__ Q0,
+                                    const float* __restrict__ x_ref, const float* __restrict__ u_ref,
+                                    const float* __restrict__ scale, const S* __restrict__ gQ,
+                                    const S* __restrict__ gq, float* __restrict__ gx, float* __restrict__ gu,
+                                    float* __restrict__ gs) {
+  const int n = nx + nu;
+  const long bt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (bt >= (long)B * T) return;
+  const S sc = scale ? (S(1) + (S)scale[bt]) : S(1);
+  S acc = S(0);
+  for (int j = 0; j < n; ++j) {
+    const S r = (S)(j < nx ? x_ref[bt * nx + j] : u_ref[bt * nu + (j - nx)]);
+    const S g = gq[bt * n + j];
+    const S v = -(Q0[j] * sc) * g;
+    if (j < nx) { if (gx) gx[bt * nx + j] = (float)v; }
+    else if (gu) gu[bt * nu + (j - nx)] = (float)v;
+    acc += Q0[j] * ((gQ ? gQ[bt * n + j] : S(0)) - g * r);
+  }
+  if (gs) gs[bt] = (float)acc;
+}
+
+// ------------------------------------------------------------------------------------------------
 // FMA-pipe peak micro-benchmark (roofline denominator for bench.py)
 // ------------------------------------------------------------------------------------------------
 template <typename S>
@@ -1568,6 +1621,23 @@ static WsPlan ws_plan(int B, int T, int nx, int nu, size_t es) {
   w.G = o; o = up(o + (size_t)B * (T - 1) * nx * nn * es);
   w.total = o;
   return w;
+}
+
+// launch with (optional) programmatic stream serialization
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*k)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool pdl,
+                            Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k, KArgs(args)...);
 }
 
 constexpr int kWLS = 4;  // warps per CTA of the warp-synchronous line search
@@ -1727,6 +1797,7 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   }
   const int nb = n_blocks(B);
   const int launches = d->al_iter * d->max_newton;
+  const bool pdl = !prof_requested && np == 1 && getenv("ALMPC_PDL");  // measured: no gain on B200, off by default
   ProfEv pe[3 * ALMPC_MAX_AL_ITER * 8 + 1];
   int npe = 0;
   const bool prof = prof_requested && launches * 3 + 1 <= (int)(sizeof(pe) / sizeof(pe[0]));
@@ -1748,12 +1819,13 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
       const size_t lo = (size_t)pt.lo;
       S* dbg = debug_out ? debug_out + lo * DBG : nullptr;
       tic(0);
-      kjac<<<pt.jac_blocks, 128, 0, pt.s>>>(pt.P, x0 + lo * NX, xu + lo * L.N, G_g + lo * GE, c_g + lo * L.neq, ctl);
+      launch_k(kjac, pt.jac_blocks, 128, 0, pt.s, pdl, pt.P, x0 + lo * NX, xu + lo * L.N, G_g + lo * GE,
+               c_g + lo * L.neq, ctl);
       toc();
       tic(1);
-      kfac<<<pt.nb, kWPB * 32, smem_fac, pt.s>>>(pt.P, Qd + lo * L.N, q + lo * L.N, xu + lo * L.N, lam + lo * L.m,
-                                                 rho + lo, factor + lo * FE, G_g + lo * GE, c_g + lo * L.neq,
-                                                 d_g + lo * L.N, merit + lo, rentry + lo, status + lo, dbg, ctl);
+      launch_k(kfac, pt.nb, kWPB * 32, smem_fac, pt.s, pdl, pt.P, Qd + lo * L.N, q + lo * L.N, xu + lo * L.N,
+               lam + lo * L.m, rho + lo, factor + lo * FE, G_g + lo * GE, c_g + lo * L.neq, d_g + lo * L.N,
+               merit + lo, rentry + lo, status + lo, dbg, ctl);
       toc();
       tic(2);
       if (lw.fn) {
@@ -1764,13 +1836,22 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
         int* a_st = status + lo;
         void* args[] = {(void*)&pt.P, &a_x0, &a_Qd, &a_q, &a_xu, &a_lam, &a_rho, &a_d, &a_merit, &a_re, &a_st,
                         &info_out, &dbg, &ctl, &partials};
-        e = cudaLaunchKernel(lw.fn, dim3(pt.ls_grid), dim3(kWLS * 32), args, lw.smem, pt.s);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(pt.ls_grid);
+        cfg.blockDim = dim3(kWLS * 32);
+        cfg.dynamicSmemBytes = lw.smem;
+        cfg.stream = pt.s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = pdl ? 1 : 0;
+        e = cudaLaunchKernelExC(&cfg, lw.fn, args);
         if (e != cudaSuccess) return cuda_err(e, "k_line_search_warp launch");
       } else {
-        kls<<<pt.ls_grid, lg.threads, smem_ls, pt.s>>>(pt.P, lg.pls, x0 + lo * NX, Qd + lo * L.N, q + lo * L.N,
-                                                        xu + lo * L.N, lam + lo * L.m, rho + lo, d_g + lo * L.N,
-                                                        merit + lo, rentry + lo, status + lo, info_out, dbg, ctl,
-                                                        partials);
+        launch_k(kls, pt.ls_grid, lg.threads, smem_ls, pt.s, pdl, pt.P, lg.pls, x0 + lo * NX, Qd + lo * L.N,
+                 q + lo * L.N, xu + lo * L.N, lam + lo * L.m, rho + lo, d_g + lo * L.N, merit + lo, rentry + lo,
+                 status + lo, info_out, dbg, ctl, partials);
       }
       toc();
     }
@@ -1782,7 +1863,7 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
     }
   }
   tic(3);
-  kfin<<<nb, kWPB * 32, smem_fin, st>>>(P, x0, xu, lam, rho, x_out, u_out, dyn_res_out, info_out, ctl);
+  launch_k(kfin, nb, kWPB * 32, smem_fin, st, pdl, P, x0, xu, lam, rho, x_out, u_out, dyn_res_out, info_out, ctl);
   toc();
   if (prof) {  // profiling mode synchronises (never used on the timed path)
     cudaStreamSynchronize(st);
@@ -1876,6 +1957,32 @@ static int fma_peak(int blocks, int iters, S* sink, double* flops, void* stream)
   return cuda_err(cudaGetLastError(), "almpc_fma_peak launch");
 }
 
+template <typename S>
+static int tracking_cost(int B, int T, int nx, int nu, const S* Q0, const float* x_ref, const float* u_ref,
+                         const float* scale, S* Qd, S* q, void* stream) {
+  if (B < 0 || T < 1 || nx < 1 || nu < 0) return set_err(-3, "bad tracking_cost dimensions");
+  if (B == 0) return 0;
+  if (!Q0 || !x_ref || (nu > 0 && !u_ref) || !Qd || !q) return set_err(-10, "null buffer");
+  const long total = (long)B * T * (nx + nu);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_tracking_cost<S><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(B, T, nx, nu, Q0, x_ref, u_ref, scale, Qd, q);
+  return cuda_err(cudaGetLastError(), "almpc_tracking_cost launch");
+}
+
+template <typename S>
+static int tracking_cost_bwd(int B, int T, int nx, int nu, const S* Q0, const float* x_ref, const float* u_ref,
+                             const float* scale, const S* gQ, const S* gq, float* gx, float* gu, float* gs,
+                             void* stream) {
+  if (B < 0 || T < 1 || nx < 1 || nu < 0) return set_err(-3, "bad tracking_cost dimensions");
+  if (B == 0) return 0;
+  if (!Q0 || !x_ref || (nu > 0 && !u_ref) || !gq) return set_err(-10, "null buffer");
+  const long bt = (long)B * T;
+  k_tracking_cost_bwd<S><<<(unsigned)((bt + 127) / 128), 128, 0, (cudaStream_t)stream>>>(B, T, nx, nu, Q0, x_ref, u_ref,
+                                                                                     scale, gQ, gq, gx, gu, gs);
+  return cuda_err(cudaGetLastError(), "almpc_tracking_cost_bwd launch");
+}
+
 }  // namespace almpc
 
 // ------------------------------------------------------------------------------------------------
@@ -1952,6 +2059,26 @@ int almpc_fma_peak_f64(int32_t blocks, int32_t iters, double* sink, double* flop
 }
 int almpc_fma_peak_f32(int32_t blocks, int32_t iters, float* sink, double* flops, void* stream) {
   return fma_peak<float>(blocks, iters, sink, flops, stream);
+}
+int almpc_tracking_cost_f64(int32_t B, int32_t T, int32_t nx, int32_t nu, const double* Q0, const float* x_ref,
+                            const float* u_ref, const float* scale, double* Qd, double* q, void* stream) {
+  return tracking_cost<double>(B, T, nx, nu, Q0, x_ref, u_ref, scale, Qd, q, stream);
+}
+int almpc_tracking_cost_f32(int32_t B, int32_t T, int32_t nx, int32_t nu, const float* Q0, const float* x_ref,
+                            const float* u_ref, const float* scale, float* Qd, float* q, void* stream) {
+  return tracking_cost<float>(B, T, nx, nu, Q0, x_ref, u_ref, scale, Qd, q, stream);
+}
+int almpc_tracking_cost_bwd_f64(int32_t B, int32_t T, int32_t nx, int32_t nu, const double* Q0, const float* x_ref,
+                                const float* u_ref, const float* scale, const double* grad_Q, const double* grad_q,
+                                float* grad_x_ref, float* grad_u_ref, float* grad_scale, void* stream) {
+  return tracking_cost_bwd<double>(B, T, nx, nu, Q0, x_ref, u_ref, scale, grad_Q, grad_q, grad_x_ref, grad_u_ref,
+                                   grad_scale, stream);
+}
+int almpc_tracking_cost_bwd_f32(int32_t B, int32_t T, int32_t nx, int32_t nu, const float* Q0, const float* x_ref,
+                                const float* u_ref, const float* scale, const float* grad_Q, const float* grad_q,
+                                float* grad_x_ref, float* grad_u_ref, float* grad_scale, void* stream) {
+  return tracking_cost_bwd<float>(B, T, nx, nu, Q0, x_ref, u_ref, scale, grad_Q, grad_q, grad_x_ref, grad_u_ref,
+                                  grad_scale, stream);
 }
 void almpc_set_profiling(int32_t on) { g_profile_on = on; }
 void almpc_get_profile(double* out8) {

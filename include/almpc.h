@@ -119,6 +119,21 @@ int almpc_dynamics_f64(const almpc_desc* d, int64_t R, const double* x, const do
 int almpc_dynamics_f32(const almpc_desc* d, int64_t R, const float* x, const float* u, float* xn,
                        float* Jx, float* Ju, void* stream);
 
+/* Tracking-cost build of the caller (deqmpc/policies.py:1285-1297 compute_pf, with the optional per-stage
+ * q_scaling of :1245-1248), fused: Qd[b,t,j] = Q0[j] (1 + scale[b,t]), q = -Qd * [x_ref | u_ref].  x_ref / u_ref /
+ * scale are the fp32 network outputs (scale may be NULL).  The backward maps the solver's grad_Q / grad_q to
+ * grad_x_ref, grad_u_ref, grad_scale (any of the three outputs, and grad_Q, may be NULL). */
+int almpc_tracking_cost_f64(int32_t B, int32_t T, int32_t nx, int32_t nu, const double* Q0, const float* x_ref,
+                            const float* u_ref, const float* scale, double* Qd, double* q, void* stream);
+int almpc_tracking_cost_f32(int32_t B, int32_t T, int32_t nx, int32_t nu, const float* Q0, const float* x_ref,
+                            const float* u_ref, const float* scale, float* Qd, float* q, void* stream);
+int almpc_tracking_cost_bwd_f64(int32_t B, int32_t T, int32_t nx, int32_t nu, const double* Q0, const float* x_ref,
+                                const float* u_ref, const float* scale, const double* grad_Q, const double* grad_q,
+                                float* grad_x_ref, float* grad_u_ref, float* grad_scale, void* stream);
+int almpc_tracking_cost_bwd_f32(int32_t B, int32_t T, int32_t nx, int32_t nu, const float* Q0, const float* x_ref,
+                                const float* u_ref, const float* scale, const float* grad_Q, const float* grad_q,
+                                float* grad_x_ref, float* grad_u_ref, float* grad_scale, void* stream);
+
 /* FMA-pipe micro-benchmark used by bench.py to measure the FP64 / FP32 roofline denominators:
  * launches `blocks` x 256 threads, each doing `iters` x 8 independent FMAs; returns via *flops the
  * number of floating-point operations performed (2 per FMA). */
