@@ -1495,7 +1495,8 @@ __global__ void k_tracking_cost(int B, int T, int nx, int nu, const S* __restric
     const long bt = i / n;
     const int j = (int)(i - bt * n);
     const S r = (S)(j < nx ? x_ref[bt * nx + j] : u_ref[bt * nu + (j - nx)]);
-    const S Qv = scale ? Q0[j] * (S(1) + (S)scale[bt]) : Q0[j];
+    // (1 + s) is an fp32 sum in the reference (policies.py:1247: q_scaling + ones_like(q_scaling))
+    const S Qv = scale ? Q0[j] * (S)(1.0f + scale[bt]) : Q0[j];
     Qd[i] = Qv;
     q[i] = -(Qv * r);
   }
@@ -1511,7 +1512,7 @@ __global__ void k_tracking_cost_bwd(int B, int T, int nx, int nu, const S* __res
   const int n = nx + nu;
   const long bt = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (bt >= (long)B * T) return;
-  const S sc = scale ? (S(1) + (S)scale[bt]) : S(1);
+  const S sc = scale ? (S)(1.0f + scale[bt]) : S(1);
   S acc = S(0);
   for (int j = 0; j < n; ++j) {
     const S r = (S)(j < nx ? x_ref[bt * nx + j] : u_ref[bt * nu + (j - nx)]);

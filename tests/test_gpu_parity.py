@@ -324,3 +324,53 @@ def test_newton_al_function_signature():
     Qg_o, qg_o = orc.newton_backward(saved, xo, torch.ones_like(xo))
     assert status.all() and rel_err(x_est.detach().cpu(), xo) < 1e-6
     assert rel_err(gq.cpu(), qg_o) < 1e-6 and rel_err(gQ.cpu(), Qg_o) < 1e-6
+
+
+def test_tracking_mpc_fused_cost_and_chain_rule():
+    """Tracking_MPC (policies.py:1117-1315) with the fused cost build: same solve and same gradients w.r.t.
+    x_ref, u_ref and q_scaling as the reference's torch-op route (diag-embedded Q, p = -(Q xu_ref))."""
+    from deq_mpc_corl_b200.tracking import Tracking_MPC
+
+    model, T, B = "rex_quadrotor", 5, 96
+    spec = MODEL_SPECS[model]
+    nx, nu = spec["nx"], spec["nu"]
+    inp = make_inputs(model, T, B, 77)
+    dyn = make_dyn(model)
+    args = types.SimpleNamespace(T=T, bsz=B, Q=torch.tensor(spec["Q"]), R=torch.tensor(spec["R"]), dtype="double",
+                                 device=DEV, solver_type="al", env="rexquadrotor", rho_init_max=1e4)
+    env = types.SimpleNamespace(nx=nx, nu=nu, nq=7, dt=spec["dt"], dynamics=dyn, dynamics_derivatives=dyn,
+                                action_space=types.SimpleNamespace(low=inp["u_lower"].numpy(), high=inp["u_upper"].numpy()))
+    g = torch.Generator().manual_seed(5)
+    gx, gu = torch.randn(B, T, nx, generator=g).to(DEV), torch.randn(B, T, nu, generator=g).to(DEV)
+    s0 = (0.3 * torch.rand(B, T, generator=g)).to(DEV)
+    x0 = inp["x0"].to(DEV)
+
+    def leaves():
+        return (inp["x_ref"].to(DEV).requires_grad_(True), inp["u_ref"].to(DEV).requires_grad_(True),
+                s0.clone().requires_grad_(True))
+
+    # fused route
+    tm = Tracking_MPC(args, env)
+    xr, ur, sc = leaves()
+    tm.reinitialize(xr, None)
+    x, u, st = tm(x0, None, xr, ur, q_scaling=sc, al_iters=2)
+    gr = torch.autograd.grad((x, u), (xr, ur, sc), (gx, gu))
+    # reference-shaped route through the same solver: diag-embedded Q and torch ops (policies.py:1245-1297)
+    ctrl = MPC(nx, nu, T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B)
+    xr2, ur2, sc2 = leaves()
+    ctrl.reinitialize(xr2, None)
+    ctrl.x_init, ctrl.u_init = xr2.detach().clone(), ur2.detach().clone()
+    Qfull = torch.diag(torch.tensor(spec["Q"] + spec["R"], dtype=torch.float64)).repeat(B, T, 1, 1).to(DEV)
+    qs = sc2 + torch.ones_like(sc2)
+    Q = Qfull * qs[:, :, None, None]
+    xu_ref = torch.cat([xr2, ur2], -1)
+    p = -(Q * xu_ref.unsqueeze(-2)).sum(-1)
+    x2, u2, _ = ctrl(x0, QuadCost(Q, p, None), dyn, dyn)
+    gr2 = torch.autograd.grad((x2, u2), (xr2, ur2, sc2), (gx, gu))
+    assert st is False and torch.equal(x, x2) and torch.equal(u, u2)
+    for a, b, nm in zip(gr, gr2, ("x_ref", "u_ref", "q_scaling")):
+        assert a.dtype == b.dtype and rel_err(a, b) < 1e-5, (nm, rel_err(a, b))
+    # streaming glue keeps working on top (warm start: lam <- 0, rho <- min(rho, rho_init_max))
+    tm.warm_start_initialize(xr.detach(), ur.detach())
+    x3, u3, st3 = tm(x0, None, xr.detach(), ur.detach(), al_iters=2)
+    assert tm.ctrl.warm_starting and isinstance(st3, bool) and torch.isfinite(x3).all()

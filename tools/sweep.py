@@ -50,5 +50,5 @@ if __name__ == "__main__":
                         ms, steps, ok = run(model, T, B, dtype)
                         print(f"| {model} | {nx} | {T} | {'f64' if dtype == torch.float64 else 'f32'} | {B} | {ms:.3f} | {steps} | {B / ms * 1e3:.3e} | {ok}/{B} |", flush=True)
                     except Exception as ex:
-                        print(f"| {model} | {nx} | {T} | {dtype} | {B} | ERROR {str(ex)[:60]} | | | |", flush=True)
+                        print(f"| {model} | {nx} | {T} | {dtype} | {B} | ERROR {str(ex)[-150:]} | | | |", flush=True)
                     torch.cuda.empty_cache()
