@@ -40,6 +40,9 @@
 #ifndef ALMPC_NO_CP16
 #define ALMPC_NO_CP16 0
 #endif
+#ifndef ALMPC_LS_MINB
+#define ALMPC_LS_MINB 4  // CTAs/SM the warp line search is compiled for
+#endif
 #ifndef ALMPC_FAC_MINB
 #define ALMPC_FAC_MINB 6  // CTAs/SM the factor kernel is compiled for (register cap 80; 5..7 measured within 2%)
 #endif
@@ -1188,7 +1191,7 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
 // segmented shuffle reductions and there is no CTA barrier and no partial-sum traffic in the loop.
 // ------------------------------------------------------------------------------------------------
 template <class M, typename S, int TM1, int WPB>
-__global__ void __launch_bounds__(WPB * 32, 4)
+__global__ void __launch_bounds__(WPB * 32, ALMPC_LS_MINB)
 k_line_search_warp(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__ Qd_g,
                    const S* __restrict__ q_g, S* xu_g, const S* __restrict__ lam_g, const S* __restrict__ rho_g,
                    const S* __restrict__ d_g, S* __restrict__ merit_g, const double* __restrict__ rentry_g,

@@ -130,3 +130,52 @@ def test_problem_generator_is_deterministic_and_shaped():
     assert a["x0"].dtype == torch.float32 and torch.equal(a["x_ref"][:, 0], a["x0"])
     Qd, q, f = tracking_cost(a["Qd"], a["x_ref"], a["u_ref"])
     assert Qd.shape == (7, 5, 16) and q.dtype == torch.float64 and f.shape == (7, 5)
+
+
+def test_newton_al_context_from_reference_style_closures():
+    """NewtonAL learns the dynamics functor and the control bounds from the closure of the reference's own
+    lambdas (AL_mpc.py:300-303 close over `self` and `dx_`) or from an explicit almpc_context."""
+    from deq_mpc_corl_b200.al_utils import NewtonContext, _context_from
+
+    dyn = make_dyn("cartpole1l")
+
+    class FakeMPC:  # what `self` looks like inside MPC.al_solve
+        n_ctrl = 1
+        u_lower = torch.tensor([-100.0])
+        u_upper = torch.tensor([100.0])
+
+    def al_solve_like(self, dx_):
+        x0 = rho = None
+        merit_fn = lambda xi, Qi, qi, yi, x0i=x0, rhoi=rho, grad=False: (self, dx_)  # noqa: E731
+        dyn_fn = lambda xi: (self, dx_, x0)  # noqa: E731
+        return merit_fn, dyn_fn
+
+    merit_fn, dyn_fn = al_solve_like(FakeMPC(), dyn)
+    ctx = _context_from(merit_fn, dyn_fn, None)
+    assert resolve(ctx.dynamics).dyn_id == dyn.dyn_id
+    assert float(torch.as_tensor(ctx.u_upper)[0]) == 100.0 and float(torch.as_tensor(ctx.u_lower)[0]) == -100.0
+
+    def explicit(*a):
+        return None
+
+    explicit.almpc_context = NewtonContext(dyn, [-1.0], [1.0])
+    assert _context_from(explicit).u_upper == [1.0]
+    with pytest.raises(_lib.AlmpcError, match="cannot tell"):
+        _context_from(lambda x: x)
+
+
+def test_tracking_mpc_refuses_non_al_paths():
+    from deq_mpc_corl_b200.tracking import Tracking_MPC
+
+    env = types.SimpleNamespace(nx=2, nu=1, nq=1, dt=0.05, dynamics=make_dyn("pendulum"),
+                                action_space=types.SimpleNamespace(low=[-2.0], high=[2.0]))
+    base = dict(T=5, bsz=4, Q=torch.ones(2), R=torch.ones(1) * 1e-3, dtype="double", device="cpu")
+    with pytest.raises(_lib.AlmpcError):
+        Tracking_MPC(types.SimpleNamespace(solver_type="ip", env="pendulum", **base), env)
+    with pytest.raises(_lib.AlmpcError):
+        Tracking_MPC(types.SimpleNamespace(solver_type="al", env="FlyingCartpole_obstacles", **base), env)
+    tm = Tracking_MPC(types.SimpleNamespace(solver_type="al", env="pendulum", **base), env)
+    # fp32 R rounded like the reference does (policies.py:1148: cat of fp32 tensors, then .to(dtype))
+    assert tm.Q.tolist() == [1.0, 1.0, float(torch.tensor(1e-3))] and tm.ctrl.neq == 10 and tm.ctrl.nineq == 10
+    with pytest.raises(_lib.AlmpcError, match="CUDA only"):
+        tm(torch.zeros(4, 2), None, torch.zeros(4, 5, 2), torch.zeros(4, 5, 1))
