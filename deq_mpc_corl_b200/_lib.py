@@ -39,6 +39,10 @@ class Desc(ctypes.Structure):
         ("dyn_params", ctypes.c_double * MAX_PARAMS),
         ("u_lower", ctypes.c_double * MAX_NU),
         ("u_upper", ctypes.c_double * MAX_NU),
+        ("n_obs", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("obs_radius", ctypes.c_double),
+        ("obstacles", ctypes.c_void_p),
     ]
 
 

@@ -121,7 +121,8 @@ class MPC(Module):
         cfg = SolveConfig(
             dyn=dyn, T=self.T, u_lower=self._bounds_host[0], u_upper=self._bounds_host[1], al_iter=int(self.al_iter),
             max_newton=self.max_newton_steps, stream_mode=bool(self.warm_starting),
-            rho_f32=(rho_dtype == torch.float32 and self.dtype == torch.float64), rho_max=self.rho_max)
+            rho_f32=(rho_dtype == torch.float32 and self.dtype == torch.float64), rho_max=self.rho_max,
+            **self._extra_constraints(dev))
         xu0 = torch.cat([x.to(self.dtype), u.to(self.dtype)], dim=2)
         xo, uo, xu, lam_new, rho_new, dyn_res, status, info, _ = ALSolve.apply(
             Qd, q, x0.to(self.dtype), xu0, lam.to(dev).to(self.dtype), rho.to(dev).to(self.dtype).reshape(-1), cfg)
@@ -138,6 +139,10 @@ class MPC(Module):
         if self.warm_starting:
             flag = bool(info[_lib.INFO_RHO_EXCEEDED].item())  # the reference syncs here too (AL_mpc.py:412,420)
         return xo, uo, flag
+
+    def _extra_constraints(self, dev):
+        """Hook for subclasses (Obstacle_MPC): extra SolveConfig fields."""
+        return {}
 
     # ------------------------------------------------------------------------------------------
     def rollout(self, x, actions, dynamics):
@@ -180,3 +185,46 @@ class MPC(Module):
         """Host copy of the realised Newton-step counts of the latest solve (synchronises)."""
         info = self.last_info.cpu().tolist()
         return info[_lib.INFO_NEWTON0:_lib.INFO_NEWTON0 + info[_lib.INFO_AL_DONE]]
+
+
+class Obstacle_MPC(MPC):
+    """Drop-in for ``qpth.AL_mpc_custom.Obstacle_MPC`` (qpth/AL_mpc_custom.py:22-135): the AL-MPC solve with
+    ``n_obstacle_constraints = 4`` sphere-avoidance rows per stage, ``r^2 - |p_t - c_k|^2 <= 0`` on the position
+    ``x[0:3]``, against the 4 obstacles nearest to the reference trajectory (chosen in ``reinitialize`` and
+    shifted in ``warm_start_initialize`` exactly like the reference).  ``env`` supplies ``obstacle_positions``
+    ``[n_obstacles,3]`` and ``obstacle_radius``."""
+
+    def __init__(self, n_state, n_ctrl, T, *args, env=None, **kwargs):
+        super().__init__(n_state, n_ctrl, T, *args, **kwargs)
+        self.n_obstacle_constraints = 4
+        self.nineq += self.n_obstacle_constraints * T
+        # the reference turns the radius into a default-dtype (fp32) tensor first (AL_mpc_custom.py:60)
+        self.obstacle_radius = float(torch.tensor(0.2 if env is None else float(env.obstacle_radius)))
+        self.obstacle_positions = None if env is None else torch.as_tensor(env.obstacle_positions)
+        self.n_obstacles = 0 if self.obstacle_positions is None else self.obstacle_positions.shape[0]
+        self.obstacles = None
+        if self.n_batch is not None:
+            self.lamda_prev = torch.zeros(self.n_batch, self.neq + self.nineq, dtype=self.dtype)
+
+    def _nearest(self, xyz):
+        """xyz [B,t,3] -> positions of the n_obstacle_constraints nearest obstacles [B,t,4,3]
+        (AL_mpc_custom.py:110-112: argsort of the distance to every obstacle)."""
+        obs = self.obstacle_positions.to(xyz.device)
+        d = (obs[None, None] - xyz[:, :, None, :]).norm(dim=-1)
+        ids = torch.argsort(d, dim=-1)[..., : self.n_obstacle_constraints]
+        return obs[ids]
+
+    def reinitialize(self, x, mask=None):
+        super().reinitialize(x, mask)
+        self.obstacles = (self._nearest(x[:, :, :3]), self.obstacle_radius)
+
+    def warm_start_initialize(self, x, u, args):
+        super().warm_start_initialize(x, u, args)
+        shifted = self.obstacles[0][:, 1:]
+        last = self._nearest(x[:, -1:, :3])
+        self.obstacles = (torch.cat([shifted, last], dim=1), self.obstacle_radius)
+
+    def _extra_constraints(self, dev):
+        if self.obstacles is None:
+            raise _lib.AlmpcError("Obstacle_MPC.forward before reinitialize(): no obstacles selected")
+        return dict(obstacles=self.obstacles[0].to(dev).to(self.dtype).contiguous(), obs_radius=self.obstacle_radius)

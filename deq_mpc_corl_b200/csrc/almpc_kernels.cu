@@ -69,6 +69,9 @@ struct KParams {
   double rho_mult, rho_max;
   int B, T, al_iter, max_newton, stream_mode, rho_f32, flags;
   int part_off, ticket_total;  // k_line_search: slot offset of this part's CTA partials / CTAs of all parts
+  int n_obs;                   // obstacle rows per stage (Obstacle_MPC), 0 = none
+  S obs_r2;                    // obstacle radius squared
+  const S* obs;                // [B][T][n_obs][3] obstacle centres (device)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -151,14 +154,37 @@ __device__ __forceinline__ S next_rho(S rho, double mult, int f32) {
   return (S)r;
 }
 
+// obstacle constraint k of stage t: c = r^2 - |p - c_k|^2 and its Jacobian row J = -2 (p - c_k)^T on the position.
+// The reference builds J in an fp32 buffer (al_utils.py:378-379: torch.zeros without dtype), so the entries
+// are rounded to fp32 before use.
+template <typename S>
+__device__ __forceinline__ S obstacle_res(const S* p, const S* ck, S r2, S* J) {
+  const S d0 = p[0] - ck[0], d1 = p[1] - ck[1], d2 = p[2] - ck[2];
+  if (J) {
+    J[0] = (S)(float)(S(-2) * d0);
+    J[1] = (S)(float)(S(-2) * d1);
+    J[2] = (S)(float)(S(-2) * d2);
+  }
+  return r2 - ((d0 * d0 + d1 * d1) + d2 * d2);
+}
+
+// residual of inequality row `sidx` (0..SI-1) of a stage: nu upper bounds, nu lower bounds, obstacle rows
+template <int NX, int NU, typename S>
+__device__ __forceinline__ S ineq_res(const S* z_t, int sidx, const S* ulo, const S* uhi, const S* obs_t, S r2) {
+  if (sidx < NU) return z_t[NX + sidx] - uhi[sidx];
+  if (sidx < 2 * NU) return ulo[sidx - NU] - z_t[NX + sidx - NU];
+  return obstacle_res<S>(z_t, obs_t + (sidx - 2 * NU) * 3, r2, nullptr);
+}
+
 // per-warp shared-memory layout of k_factor_solve, in units of S (every region 16-byte aligned)
 template <int NX, int NU>
 struct Layout {
   static constexpr int NN = NX + NU;
-  int N, neq, nin, m;
+  int N, neq, nin, m, SI;
   int xu, dv, w, Gt, Ep, scr, total;
-  __host__ __device__ Layout(int T) {
-    N = T * NN; neq = T * NX; nin = 2 * T * NU; m = neq + nin;
+  __host__ __device__ Layout(int T, int nobs = 0) {
+    SI = 2 * NU + nobs;  // inequality rows per stage: control bounds, then obstacle rows
+    N = T * NN; neq = T * NX; nin = T * SI; m = neq + nin;
     int o = 0;
     auto take = [&](int cnt) { int at = o; o += (cnt + 3) & ~3; return at; };  // regions 16-byte aligned for float and double
     xu = take(N);
@@ -176,10 +202,11 @@ template <int NX, int NU>
 struct LsLayout {
   static constexpr int NN = NX + NU;
   static constexpr int LS = NN | 1;  // odd stage stride: lanes working on different stages hit different banks
-  int N, neq, nin, m;
-  int xu, d, lam, Qd, q, x0, part, total;
-  __host__ __device__ LsLayout(int T) {
-    N = T * NN; neq = T * NX; nin = 2 * T * NU; m = neq + nin;
+  int N, neq, nin, m, SI;
+  int xu, d, lam, Qd, q, x0, obs, part, total;
+  __host__ __device__ LsLayout(int T, int nobs = 0) {
+    SI = 2 * NU + nobs;
+    N = T * NN; neq = T * NX; nin = T * SI; m = neq + nin;
     int o = 0;
     auto take = [&](int cnt) { int at = o; o += (cnt + 3) & ~3; return at; };  // regions 16-byte aligned for float and double
     xu = take(T * LS);
@@ -188,6 +215,7 @@ struct LsLayout {
     Qd = take(T * LS);
     q = take(T * LS);
     x0 = take(NX);
+    obs = take(T * nobs * 3);
     part = take(NLS * (T - 1) * 3);
     total = o;
   }
@@ -551,7 +579,7 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
   const int mode = ctl->mode;
   if (mode == MODE_DONE) return;
   const int T = P.T;
-  const Layout<NX, NU> L(T);
+  const Layout<NX, NU> L(T, P.n_obs);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int prob = blockIdx.x * WPB + warp;
   if (prob >= P.B) return;
@@ -570,6 +598,7 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
   const S* Gp = G_g + (size_t)prob * (T - 1) * NX * NN;
   S* fac = fac_g + (size_t)prob * factor_elems<NX, NU>(T);
   S* dbg = debug_g ? debug_g + (size_t)prob * (2 * L.N + 24) : nullptr;
+  const S* obs = P.n_obs ? P.obs + (size_t)prob * T * P.n_obs * 3 : nullptr;
 
   if (T > 1) warp_copy_block_async<NX, NN, LB>(Gt, Gp, lane);  // G_0, consumed after the residual statistics
   cp_async_commit();
@@ -628,9 +657,8 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
       for (int u = 0; u < 4; ++u) {
         const int i = base + lane + 32 * u;
         if (i < L.nin) {
-          const int t = i / (2 * NU), sidx = i - t * 2 * NU;
-          const S uu = xu[t * NN + NX + (sidx < NU ? sidx : sidx - NU)];
-          const S ci = (sidx < NU) ? (uu - P.uhi[sidx]) : (P.ulo[sidx - NU] - uu);
+          const int t = i / L.SI, sidx = i - t * L.SI;
+          const S ci = ineq_res<NX, NU, S>(xu + t * NN, sidx, P.ulo, P.uhi, obs + (size_t)t * P.n_obs * 3, P.obs_r2);
           S li = lv[u];
           if (dual) { li = fmax0(li + rho_old * ci); lam[L.neq + i] = li; }
           const S cp = fmax0(ci);
@@ -680,6 +708,20 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
     const bool has_G = t < T - 1, has_E = t > 0;
     cp_async_wait_all();  // G_t (issued one stage ago / in the prologue)
     __syncwarp();
+    // obstacle rows of stage t: (lam_k + rho c_k+) and the active-masked Jacobian rows, staged in scr[0..]
+    if (P.n_obs) {
+      if (lane < P.n_obs) {
+        S J[3];
+        const S ck = obstacle_res<S>(xu + t * NN, obs + ((size_t)t * P.n_obs + lane) * 3, P.obs_r2, J);
+        const S lk = lam[L.neq + t * L.SI + 2 * NU + lane];
+        scr[lane * 8 + 0] = J[0];
+        scr[lane * 8 + 1] = J[1];
+        scr[lane * 8 + 2] = J[2];
+        scr[lane * 8 + 3] = lk + rho * fmax0(ck);        // multiplies J in the gradient (al_utils.py:113-117)
+        scr[lane * 8 + 4] = (ck >= S(0)) ? rho : S(0);   // multiplies J^T J in the Hessian (active rows only)
+      }
+      __syncwarp();
+    }
     // gradient of stage t (al_utils.py:113-117) minus the coupling E_{t-1} y_{t-1}
     if (lane < NN) {
       const int j = lane, idx = t * NN + j;
@@ -700,8 +742,11 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
         const int sidx = j - NX;
         const S u = xu[idx];
         const S cu = u - P.uhi[sidx], cl = P.ulo[sidx] - u;
-        const S lu = lam[L.neq + t * 2 * NU + sidx], ll = lam[L.neq + t * 2 * NU + NU + sidx];
+        const S lu = lam[L.neq + t * L.SI + sidx], ll = lam[L.neq + t * L.SI + NU + sidx];
         g += (lu - ll) + rho * (fmax0(cu) - fmax0(cl));
+      }
+      if (P.n_obs && j < 3) {
+        for (int k = 0; k < P.n_obs; ++k) g += scr[k * 8 + 3] * scr[k * 8 + j];
       }
       if (dbg) dbg[idx] = g;
       if (has_E && j < NX) {
@@ -718,6 +763,15 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
     }
     build_block<NX, NU, S>(scr + 64, xu + t * NN, X, Y, has_G, has_E, lane, rho, Qd + t * NN, P.ulo, P.uhi);
     __syncwarp();
+    if (P.n_obs) {  // + rho sum_k active J_k^T J_k on the position block (lower part)
+      if (lane < 6) {
+        const int r = (lane < 1) ? 0 : (lane < 3 ? 1 : 2), c = lane - (r * (r + 1)) / 2;
+        S acc = S(0);
+        for (int k = 0; k < P.n_obs; ++k) acc += scr[k * 8 + 4] * scr[k * 8 + r] * scr[k * 8 + c];
+        scr[64 + r * LD + c] += acc;
+      }
+      __syncwarp();
+    }
     // rows into registers: L rows | rhs | -rho G_t rows
     S a[NN];
     if (lane < NN) {
@@ -952,7 +1006,7 @@ __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU
       us[i] = z;
       cost += S(0.5) * (z * Qd[t * LS + NX + i] * z) + qv[t * LS + NX + i] * z;
       const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
-      sl += lam[L.neq + t * 2 * NU + i] * cu + lam[L.neq + t * 2 * NU + NU + i] * cl;
+      sl += lam[L.neq + t * L.SI + i] * cu + lam[L.neq + t * L.SI + NU + i] * cl;
       const S pu = fmax0(cu), pl = fmax0(cl);
       s2 += pu * pu + pl * pl;
     }
@@ -964,6 +1018,16 @@ __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU
         sl += lam[(T - 1) * NX + i] * ci;
       }
     }
+    if (P.n_obs) {  // obstacle rows of stage t at the candidate position
+      const S* ob = sp + L.obs + t * P.n_obs * 3;
+      for (int k = 0; k < P.n_obs; ++k) {
+        const S ck = obstacle_res<S>(xs, ob + k * 3, P.obs_r2, nullptr);
+        sl += lam[L.neq + t * L.SI + 2 * NU + k] * ck;
+        const S cp = fmax0(ck);
+        s2 += cp * cp;
+      }
+    }
+    S zlast[3];
     rk4_step<M, S, S>(xs, us, xn, P.dyn);
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
@@ -971,6 +1035,7 @@ __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU
       const S ci = z1 - xn[i];
       s2 += ci * ci;
       sl += lam[t * NX + i] * ci;
+      if (i < 3) zlast[i] = z1;
       if (t == T - 2) cost += S(0.5) * (z1 * Qd[(t + 1) * LS + i] * z1) + qv[(t + 1) * LS + i] * z1;
     }
     if (t == T - 2) {
@@ -980,9 +1045,18 @@ __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU
         const S z = xu[e] + alpha * dv[e];
         cost += S(0.5) * (z * Qd[e] * z) + qv[e] * z;
         const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
-        sl += lam[L.neq + (T - 1) * 2 * NU + i] * cu + lam[L.neq + (T - 1) * 2 * NU + NU + i] * cl;
+        sl += lam[L.neq + (T - 1) * L.SI + i] * cu + lam[L.neq + (T - 1) * L.SI + NU + i] * cl;
         const S pu = fmax0(cu), pl = fmax0(cl);
         s2 += pu * pu + pl * pl;
+      }
+      if (P.n_obs) {  // obstacle rows of the last stage
+        const S* ob = sp + L.obs + (T - 1) * P.n_obs * 3;
+        for (int k = 0; k < P.n_obs; ++k) {
+          const S ck = obstacle_res<S>(zlast, ob + k * 3, P.obs_r2, nullptr);
+          sl += lam[L.neq + (T - 1) * L.SI + 2 * NU + k] * ck;
+          const S cp = fmax0(ck);
+          s2 += cp * cp;
+        }
       }
     }
 }
@@ -991,7 +1065,7 @@ __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU
 template <int NX, int NU, typename S>
 __device__ __forceinline__ void ls_stage_async(S* sp, const LsLayout<NX, NU>& L, int prob, int tid, int nthr,
                                                const S* x0_g, const S* Qd_g, const S* q_g, const S* xu_g,
-                                               const S* lam_g, const S* d_g) {
+                                               const S* lam_g, const S* d_g, const S* obs_g = nullptr) {
   const size_t pN = (size_t)prob * L.N;
   auto copy = [&](S* dst, const S* src, int count) {
     if ((((size_t)count * sizeof(S)) & 15) == 0 && ((reinterpret_cast<size_t>(src) & 15) == 0)) {
@@ -1022,6 +1096,7 @@ __device__ __forceinline__ void ls_stage_async(S* sp, const LsLayout<NX, NU>& L,
   }
   copy(sp + L.lam, lam_g + (size_t)prob * L.m, L.m);
   copy(sp + L.x0, x0_g + (size_t)prob * NX, NX);
+  if (obs_g) copy(sp + L.obs, obs_g + (size_t)prob * (L.nin / L.SI) * (L.SI - 2 * NU) * 3, (L.nin / L.SI) * (L.SI - 2 * NU) * 3);
 }
 
 template <class M, typename S>
@@ -1040,7 +1115,7 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
   if (mode == MODE_DONE) return;
   const int al_a = ctl->a, nk = ctl->k;
   const int T = P.T;
-  const LsLayout<NX, NU> L(T);
+  const LsLayout<NX, NU> L(T, P.n_obs);
   const int IT = NLS * (T - 1);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -1055,7 +1130,7 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
   if ((int)blockIdx.x < ngroups) {
     for (int p = 0; p < pls; ++p) {
       const int prob = blockIdx.x * pls + p;
-      if (prob < P.B) ls_stage_async<NX, NU, S>(smem + (size_t)p * L.total, L, prob, tid, nthr, x0_g, Qd_g, q_g, xu_g, lam_g, d_g);
+      if (prob < P.B) ls_stage_async<NX, NU, S>(smem + (size_t)p * L.total, L, prob, tid, nthr, x0_g, Qd_g, q_g, xu_g, lam_g, d_g, P.obs);
     }
   }
   cp_async_commit();
@@ -1066,7 +1141,7 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
       S* nb = smem + (size_t)(cur ^ 1) * buf_elems;
       for (int p = 0; p < pls; ++p) {
         const int prob = nxt * pls + p;
-        if (prob < P.B) ls_stage_async<NX, NU, S>(nb + (size_t)p * L.total, L, prob, tid, nthr, x0_g, Qd_g, q_g, xu_g, lam_g, d_g);
+        if (prob < P.B) ls_stage_async<NX, NU, S>(nb + (size_t)p * L.total, L, prob, tid, nthr, x0_g, Qd_g, q_g, xu_g, lam_g, d_g, P.obs);
       }
     }
     cp_async_commit();
@@ -1210,7 +1285,7 @@ k_line_search_warp(const KParams<S> P, const S* __restrict__ x0_g, const S* __re
   if (mode == MODE_DONE) return;
   const int al_a = ctl->a, nk = ctl->k;
   constexpr int T = TM1 + 1;
-  const LsLayout<NX, NU> L(T);
+  const LsLayout<NX, NU> L(T, P.n_obs);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int stride = L.part;  // staged scalars per problem (the partial-sum area of the CTA variant is unused)
@@ -1225,7 +1300,7 @@ k_line_search_warp(const KParams<S> P, const S* __restrict__ x0_g, const S* __re
 #pragma unroll
     for (int p = 0; p < PW; ++p) {
       if (prob0 + p < P.B)
-        ls_stage_async<NX, NU, S>(wsm + (size_t)p * stride, L, prob0 + p, lane, 32, x0_g, Qd_g, q_g, xu_g, lam_g, d_g);
+        ls_stage_async<NX, NU, S>(wsm + (size_t)p * stride, L, prob0 + p, lane, 32, x0_g, Qd_g, q_g, xu_g, lam_g, d_g, P.obs);
     }
     cp_async_commit();
     // per-problem scalars travel in registers while the copies are in flight
@@ -1352,7 +1427,7 @@ k_final_dual(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict
   constexpr int NX = M::NX, NU = M::NU, NN = NX + NU;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = P.T;
-  const Layout<NX, NU> L(T);
+  const Layout<NX, NU> L(T, P.n_obs);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int prob = blockIdx.x * WPB + warp;
   grid_dep_wait();
@@ -1387,10 +1462,10 @@ k_final_dual(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict
     if (upd) lamp[i] += rho * ci;
     s2 += ci * ci;
   }
+  const S* obs = P.n_obs ? P.obs + (size_t)prob * T * P.n_obs * 3 : nullptr;
   for (int i = lane; i < L.nin; i += 32) {
-    int t = i / (2 * NU), s = i - t * 2 * NU;
-    S u = xu[t * NN + NX + (s < NU ? s : s - NU)];
-    S ci = (s < NU) ? (u - P.uhi[s]) : (P.ulo[s - NU] - u);
+    const int t = i / L.SI, s = i - t * L.SI;
+    const S ci = ineq_res<NX, NU, S>(xu + t * NN, s, P.ulo, P.uhi, obs + (size_t)t * P.n_obs * 3, P.obs_r2);
     if (upd) lamp[L.neq + i] = fmax0(lamp[L.neq + i] + rho * ci);
     S cp = fmax0(ci);
     s2 += cp * cp;
@@ -1568,6 +1643,9 @@ static KParams<S> make_params(const almpc_desc* d) {
   P.B = d->B; P.T = d->T; P.al_iter = d->al_iter; P.max_newton = d->max_newton;
   P.stream_mode = d->stream_mode; P.rho_f32 = d->rho_f32; P.flags = d->flags;
   P.part_off = 0; P.ticket_total = 0;
+  P.n_obs = d->obstacles ? d->n_obs : 0;
+  P.obs_r2 = (S)(d->obs_radius * d->obs_radius);
+  P.obs = (const S*)d->obstacles;
   return P;
 }
 
@@ -1578,6 +1656,7 @@ static int check_desc(const almpc_desc* d) {
   if (d->T < 2 || d->T > 64) return set_err(-4, "horizon T must be in [2,64]");
   if (d->al_iter < 1 || d->al_iter > ALMPC_MAX_AL_ITER) return set_err(-5, "al_iter out of range");
   if (d->max_newton < 1) return set_err(-6, "max_newton must be >= 1");
+  if (d->n_obs < 0 || d->n_obs > 8) return set_err(-7, "n_obs must be in [0,8]");
   return 0;
 }
 
@@ -1649,9 +1728,9 @@ constexpr int kWLS = 4;  // warps per CTA of the warp-synchronous line search
 struct LsWarpCfg { const void* fn; int grid_cap; size_t smem; int pw; };
 
 template <class M, typename S, int TM1>
-static cudaError_t ls_warp_cfg(LsWarpCfg& c, int n_sm) {
+static cudaError_t ls_warp_cfg(LsWarpCfg& c, int n_sm, int n_obs) {
   constexpr int PW = (8 / TM1) > 0 ? (8 / TM1) : 1;
-  const LsLayout<M::NX, M::NU> LL(TM1 + 1);
+  const LsLayout<M::NX, M::NU> LL(TM1 + 1, n_obs);
   auto k = k_line_search_warp<M, S, TM1, kWLS>;
   size_t smem = (size_t)kWLS * PW * LL.part * sizeof(S);
   if (smem < (size_t)kWLS * 32 * 3 * sizeof(double)) smem = (size_t)kWLS * 32 * 3 * sizeof(double);
@@ -1676,8 +1755,9 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   if (!x0 || !Qd || !q || !xu || !lam || !rho || !factor || !info_out || !workspace)
     return set_err(-10, "null buffer");
   const int T = d->T, B = d->B;
-  const Layout<NX, NU> L(T);
-  const LsLayout<NX, NU> LL(T);
+  const int n_obs = d->obstacles ? d->n_obs : 0;
+  const Layout<NX, NU> L(T, n_obs);
+  const LsLayout<NX, NU> LL(T, n_obs);
   const LsGeom lg = ls_geom(B, T);
   size_t smem_fac = (size_t)kWPB * L.total * sizeof(S);
   if (const char* pad = getenv("ALMPC_FAC_SMEM_PAD")) smem_fac += (size_t)atoi(pad);  // occupancy experiments
@@ -1711,12 +1791,12 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   LsWarpCfg lw{nullptr, 0, 0, 1};
   if (!getenv("ALMPC_LS_CTA")) {
     switch (T - 1) {
-      case 1: e = ls_warp_cfg<M, S, 1>(lw, n_sm); break;
-      case 2: e = ls_warp_cfg<M, S, 2>(lw, n_sm); break;
-      case 4: e = ls_warp_cfg<M, S, 4>(lw, n_sm); break;
-      case 8: e = ls_warp_cfg<M, S, 8>(lw, n_sm); break;
-      case 16: e = ls_warp_cfg<M, S, 16>(lw, n_sm); break;
-      case 32: e = ls_warp_cfg<M, S, 32>(lw, n_sm); break;
+      case 1: e = ls_warp_cfg<M, S, 1>(lw, n_sm, n_obs); break;
+      case 2: e = ls_warp_cfg<M, S, 2>(lw, n_sm, n_obs); break;
+      case 4: e = ls_warp_cfg<M, S, 4>(lw, n_sm, n_obs); break;
+      case 8: e = ls_warp_cfg<M, S, 8>(lw, n_sm, n_obs); break;
+      case 16: e = ls_warp_cfg<M, S, 16>(lw, n_sm, n_obs); break;
+      case 32: e = ls_warp_cfg<M, S, 32>(lw, n_sm, n_obs); break;
       default: break;
     }
     if (e != cudaSuccess) return cuda_err(e, "line-search (warp) configuration");
@@ -1789,6 +1869,7 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
     pt.P = P;
     pt.P.B = pt.n;
     pt.P.part_off = ticket_total;
+    if (pt.P.obs) pt.P.obs = P.obs + (size_t)lo * T * P.n_obs * 3;
     ticket_total += pt.ls_grid;
     ++np;
   }

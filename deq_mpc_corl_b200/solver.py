@@ -29,6 +29,8 @@ class SolveConfig:
     rho_max: float = 1e8
     skip_final_dual: bool = False
     debug: bool = False
+    obstacles: object = None      # device tensor [B,T,n_obs,3] in the solver dtype (Obstacle_MPC)
+    obs_radius: float = 0.0
 
     def desc(self, B):
         d = _lib.Desc()
@@ -44,6 +46,10 @@ class SolveConfig:
         for i in range(self.dyn.nu):
             d.u_lower[i] = float(self.u_lower[i])
             d.u_upper[i] = float(self.u_upper[i])
+        if self.obstacles is not None:
+            d.n_obs = int(self.obstacles.shape[2])
+            d.obs_radius = float(self.obs_radius)
+            d.obstacles = self.obstacles.data_ptr()
         return d
 
 
@@ -61,7 +67,14 @@ def raw_forward(cfg: SolveConfig, x0, Qd, q, xu, lam, rho):
     nx, nu = cfg.dyn.nx, cfg.dyn.nu
     if T != cfg.T or n != nx + nu:
         raise _lib.AlmpcError(f"xu has shape {tuple(xu.shape)}, expected [B,{cfg.T},{nx + nu}]")
-    m = T * nx + 2 * T * nu
+    n_obs = 0
+    if cfg.obstacles is not None:
+        ob = cfg.obstacles
+        _lib.require_cuda(ob, "obstacles")
+        if ob.dtype != xu.dtype or not ob.is_contiguous() or ob.dim() != 4 or ob.shape[0] != B or ob.shape[1] != T or ob.shape[3] != 3:
+            raise _lib.AlmpcError("obstacles must be a contiguous [B,T,n_obs,3] tensor of the solver dtype")
+        n_obs = ob.shape[2]
+    m = T * nx + T * (2 * nu + n_obs)
     if x0.shape != (B, nx) or Qd.shape != (B, T, n) or q.shape != (B, T, n) or lam.shape != (B, m) or rho.numel() != B:
         raise _lib.AlmpcError("inconsistent AL-MPC buffer shapes")
     dev, dt = xu.device, xu.dtype

@@ -22,10 +22,10 @@
  *                             (deqmpc/my_envs/<pkg>/src/dynamics.cpp:13-54).
  *
  * Layouts (all contiguous, row-major, S = double or float):
- *   n = nx+nu, N = T*n, neq = T*nx, nineq = 2*T*nu, m = neq+nineq
+ *   n = nx+nu, N = T*n, neq = T*nx, nineq = T*(2*nu + n_obs), m = neq+nineq
  *   x0[B][nx]   Qd[B][T][n]   q[B][T][n]   xu[B][T][n] (x_t then u_t per stage)
  *   lam[B][m]   eq rows first: (T-1) dynamics blocks of nx, then the x_0 - x0 block (al_utils.py:224);
- *               then per stage t: nu upper-bound rows, nu lower-bound rows (al_utils.py:293)
+ *               then per stage t: nu upper-bound rows, nu lower-bound rows (al_utils.py:293), n_obs obstacle rows
  *   rho[B]      penalty per problem, stored in S
  *   factor[B][almpc_factor_elems]  block-tridiagonal Cholesky factor of the last Newton Hessian:
  *               T lower-triangular blocks L_tt[n][n] (diagonal holds 1/L_ii) followed by
@@ -73,6 +73,13 @@ typedef struct almpc_desc {
   double dyn_params[ALMPC_MAX_PARAMS]; /* model parameters, layout in DESIGN.md / dynamics.py */
   double u_lower[ALMPC_MAX_NU];
   double u_upper[ALMPC_MAX_NU];
+  /* Obstacle_MPC (qpth/AL_mpc_custom.py:22-135): n_obs sphere constraints r^2 - |p_t - c_k|^2 <= 0 per stage on
+   * the position x[0..2]; rows follow the 2*nu control rows of each stage (al_utils.py:313-323).  obstacles is a
+   * DEVICE pointer to [B][T][n_obs][3] scalars of the solver dtype (NULL / n_obs = 0: plain MPC). */
+  int32_t n_obs;
+  int32_t reserved;
+  double obs_radius;
+  const void* obstacles;
 } almpc_desc;
 
 /* info_out layout (int32, device memory, ALMPC_INFO_INTS entries) */

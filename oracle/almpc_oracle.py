@@ -52,14 +52,17 @@ class SolveTrace:
 class Problem:
     """Static description of one batched problem family (dims, dynamics, bounds)."""
 
-    def __init__(self, model, T, u_lower, u_upper, dtype=torch.float64):
+    def __init__(self, model, T, u_lower, u_upper, dtype=torch.float64, obstacles=None):
+        """obstacles = (positions [B,T,K,3], radius tensor) for Obstacle_MPC (qpth/AL_mpc_custom.py), else None."""
         self.model = model
         self.T = T
         self.nx, self.nu = model.nx, model.nu
         self.n = self.nx + self.nu
         self.N = T * self.n
         self.neq = T * self.nx
-        self.nineq = 2 * T * self.nu
+        self.obstacles = obstacles
+        self.n_obs = 0 if obstacles is None else obstacles[0].shape[2]
+        self.nineq = T * (2 * self.nu + self.n_obs)
         self.m = self.neq + self.nineq
         self.dtype = dtype
         self.u_lower = torch.as_tensor(u_lower).to(dtype)
@@ -77,10 +80,23 @@ def residuals(pb: Problem, xu, x0):
     xn = pb.model.step(x[:, :-1].reshape(-1, nx), u[:, :-1].reshape(-1, pb.nu)).view(B, pb.T - 1, nx)
     c_dyn = (x[:, 1:] - xn).reshape(B, -1)
     c_init = x[:, 0] - x0
-    c_in = torch.cat([u - pb.u_upper, -u + pb.u_lower], dim=2).reshape(B, -1)
+    c_in = _ineq_rows(pb, x, u).reshape(B, -1)
     c = torch.cat([c_dyn, c_init, c_in], dim=1)
     c_plus = torch.cat([c_dyn, c_init, c_in.clamp(min=0)], dim=1)
     return c, c_plus
+
+
+def _ineq_rows(pb, x, u):
+    """[B,T,2nu(+K)]: control bounds (al_utils.py:293) and obstacle rows r^2 - |p - c_k|^2 (al_utils.py:313-323)."""
+    rows = torch.cat([u - pb.u_upper, -u + pb.u_lower], dim=2)
+    if pb.obstacles is not None:
+        pos, radius = pb.obstacles
+        B = x.shape[0]
+        if pos.shape[0] != B:  # candidate-stacked batch of the line search
+            pos = pos.repeat(B // pos.shape[0], 1, 1, 1)
+        d2 = ((x[:, :, None, :3] - pos) ** 2).sum(-1)
+        rows = torch.cat([rows, radius ** 2 - d2], dim=2)
+    return rows
 
 
 def cost_value(xu, Qd, q):
@@ -113,12 +129,17 @@ def constraint_jacobian(pb: Problem, xu, x0):
         J[:, t * nx : (t + 1) * nx, t * n : (t + 1) * n] = -G[:, t]
         J[:, t * nx : (t + 1) * nx, (t + 1) * n : (t + 1) * n + nx] = eye
     J[:, (T - 1) * nx : T * nx, :nx] = eye
-    c_in = torch.cat([u - pb.u_upper, -u + pb.u_lower], dim=2).reshape(B, -1)
+    c_in = _ineq_rows(pb, x, u).reshape(B, -1)
+    SI = 2 * nu + pb.n_obs
     for t in range(T):
-        r0 = pb.neq + t * 2 * nu
+        r0 = pb.neq + t * SI
         for j in range(nu):
             J[:, r0 + j, t * n + nx + j] = 1.0
             J[:, r0 + nu + j, t * n + nx + j] = -1.0
+        if pb.n_obs:
+            # the reference builds these rows in a default-dtype (fp32) buffer: al_utils.py:376-379
+            jac = (-2 * (x[:, t, None, :3] - pb.obstacles[0][:, t])).float().to(xu.dtype)
+            J[:, r0 + 2 * nu : r0 + SI, t * n : t * n + 3] = jac
     active = (c_in >= 0).to(xu.dtype)
     Jc = J.clone()
     Jc[:, pb.neq :] = Jc[:, pb.neq :] * active[..., None]
@@ -233,8 +254,15 @@ class OracleMPC:
 
     rho_max = 1e8
 
-    def __init__(self, model, T, u_lower, u_upper, n_batch, dtype=torch.float64, al_iter=2):
+    def __init__(self, model, T, u_lower, u_upper, n_batch, dtype=torch.float64, al_iter=2, obstacle_positions=None,
+                 obstacle_radius=None):
         self.pb = Problem(model, T, u_lower, u_upper, dtype)
+        self.obstacle_positions = obstacle_positions  # [n_obstacles,3]: Obstacle_MPC (AL_mpc_custom.py:22-135)
+        self.obstacle_radius = None if obstacle_radius is None else torch.tensor(obstacle_radius).to(dtype)
+        if obstacle_positions is not None:
+            self.pb.n_obs = 4
+            self.pb.nineq = T * (2 * self.pb.nu + 4)
+            self.pb.m = self.pb.neq + self.pb.nineq
         self.dtype = dtype
         self.n_batch = n_batch
         self.al_iter = al_iter
@@ -253,12 +281,21 @@ class OracleMPC:
         self.rho_prev = torch.ones((self.n_batch, 1), dtype=x.dtype)
         self.lamda_prev = torch.zeros(self.n_batch, self.pb.m, dtype=x.dtype)
         self.warm_starting = False
+        if self.obstacle_positions is not None:  # AL_mpc_custom.py:110-113
+            self.pb.obstacles = (self._nearest(x[:, :, :3]), self.obstacle_radius)
+
+    def _nearest(self, xyz):
+        d = (self.obstacle_positions[None, None] - xyz[:, :, None, :]).norm(dim=-1)
+        return self.obstacle_positions[torch.argsort(d, dim=-1)[..., :4]]
 
     def warm_start_initialize(self, x, u, rho_init_max):  # AL_mpc.py:581-592
         self.x_init, self.u_init = x, u
         self.lamda_prev = self.lamda_prev * 0
         self.rho_prev = torch.clamp(self.rho_prev, max=rho_init_max)
         self.warm_starting = True
+        if self.obstacle_positions is not None:  # AL_mpc_custom.py:129-135
+            pos = torch.cat([self.pb.obstacles[0][:, 1:], self._nearest(x[:, -1:, :3])], dim=1)
+            self.pb.obstacles = (pos, self.obstacle_radius)
 
     def solve(self, x0, Qd, q, trace: Optional[SolveTrace] = None, keep_H=False):
         """MPC.forward + al_solve / al_solve_stream (AL_mpc.py:207-423).  Qd, q are [B,T,n].

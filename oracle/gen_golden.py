@@ -74,7 +74,8 @@ class CasadiDx:
 # --------------------------------------------------------------------------------------------------
 # synthetic inputs — shared with tests/ and bench.py through oracle/problem_gen.py
 # --------------------------------------------------------------------------------------------------
-def run_scenario(name, model_name, T, B, dtype_name, calls, seed, stream_after=None, rho_init_max=1e4):
+def run_scenario(name, model_name, T, B, dtype_name, calls, seed, stream_after=None, rho_init_max=1e4,
+                 obstacle_radius=None):
     """calls = list of al_iter per MPC.forward call; state (lam, rho, warm start) carries across calls
     exactly as in the DEQ loop (policies.py:147-171).  stream_after = index of the call before which
     warm_start_initialize is invoked (policies.py:1305-1310)."""
@@ -89,7 +90,10 @@ def run_scenario(name, model_name, T, B, dtype_name, calls, seed, stream_after=N
         env = rex_quadrotor.RexQuadrotor(bsz=B)
         dx, dx_jac = env.dynamics, env.dynamics_derivatives
     elif model_name == "flying_cartpole":
-        env = flying_cartpole2d.FlyingCartpole(bsz=B)
+        if obstacle_radius is None:
+            env = flying_cartpole2d.FlyingCartpole(bsz=B)
+        else:
+            env = flying_cartpole2d.FlyingCartpole(bsz=B, obstacles=True, obstacle_radius=obstacle_radius)
         dx, dx_jac = env.dynamics, env.dynamics_derivatives
     else:
         pkg, nq = {"pendulum": ("pendulum1l", 1), "cartpole1l": ("cartpole1l", 2), "cartpole2l": ("cartpole2l", 3)}[model_name]
@@ -102,8 +106,22 @@ def run_scenario(name, model_name, T, B, dtype_name, calls, seed, stream_after=N
     Qd1 = inp["Qd"].to(dtype)  # [n]
     Qfull = torch.diag(Qd1).repeat(B, T, 1, 1)
 
-    ctrl = AL_mpc.MPC(nx, nu, T, u_lower=torch.tensor(om.u_lower), u_upper=torch.tensor(om.u_upper),
-                      n_batch=B, dtype=dtype)
+    if obstacle_radius is None:
+        ctrl = AL_mpc.MPC(nx, nu, T, u_lower=torch.tensor(om.u_lower), u_upper=torch.tensor(om.u_upper),
+                          n_batch=B, dtype=dtype)
+    else:
+        from qpth import AL_mpc_custom
+
+        # start next to obstacles so that some sphere constraints are active
+        g0 = torch.Generator().manual_seed(seed + 11)
+        pick = torch.randint(0, env.obstacle_positions.shape[0], (B,), generator=g0)
+        x0 = x0.clone()
+        x0[:, :3] = env.obstacle_positions[pick] + 0.6 * obstacle_radius * torch.randn(B, 3, generator=g0)
+        x_ref = x_ref.clone()
+        x_ref[:, :, :3] = x0[:, None, :3] + 0.05 * torch.randn(B, T, 3, generator=g0)
+        x_ref[:, 0] = x0
+        ctrl = AL_mpc_custom.Obstacle_MPC(nx, nu, T, u_lower=torch.tensor(om.u_lower), u_upper=torch.tensor(om.u_upper),
+                                          n_batch=B, dtype=dtype, env=env)
     ctrl.reinitialize(x_ref, None)
 
     # ---- hooks
@@ -167,6 +185,8 @@ def run_scenario(name, model_name, T, B, dtype_name, calls, seed, stream_after=N
             gu = torch.randn(u.shape, generator=g)
             Qg, qg = torch.autograd.grad((x, u), (Qleaf, p), (gx, gu))
             pfx = f"c{ci}_"
+            if obstacle_radius is not None:
+                out[pfx + "obs_pos"] = ctrl.obstacles[0].clone()
             out.update({
                 pfx + "x_ref": x_ref, pfx + "u_ref": u_ref, pfx + "q": p.detach(), pfx + "xu_init": pre["xu_init"],
                 pfx + "lam_in": pre["lam"], pfx + "rho_in": pre["rho"], pfx + "al_iter": np.int64(al_iter),
@@ -186,6 +206,9 @@ def run_scenario(name, model_name, T, B, dtype_name, calls, seed, stream_after=N
     finally:
         al_utils.merit_grad_hessian, al_utils.line_search_newton, al_utils.NewtonAL = orig_mgh, orig_ls, orig_newton
 
+    if obstacle_radius is not None:
+        out["obstacle_positions"] = env.obstacle_positions
+        out["obstacle_radius"] = np.float64(obstacle_radius)
     out.update({"x0": x0, "Qd": Qd1, "u_lower": torch.tensor(om.u_lower), "u_upper": torch.tensor(om.u_upper),
                 "n_calls": np.int64(len(calls)), "T": np.int64(T), "B": np.int64(B), "seed": np.int64(seed),
                 "stream_after": np.int64(-1 if stream_after is None else stream_after),
@@ -210,6 +233,8 @@ SCENARIOS = {
     "cartpole1l_T5_f64_stream": ("cartpole1l", 5, 12, "f64", [2, 2, 2, 2, 2, 2, 2, 2, 2], 1001, 6),
     "flying_T10_f64_cold": ("flying_cartpole", 10, 4, "f64", [2, 2], 1002, None),
     "quad_T5_f64_lastqp": ("rex_quadrotor", 5, 4, "f64", [10], 1033, None),
+    # Obstacle_MPC (qpth/AL_mpc_custom.py): flying cartpole, 4 nearest-sphere rows per stage, 3 cold calls + 1 streaming
+    "flying_obs_T5_f64": ("flying_cartpole", 5, 6, "f64", [2, 2, 2, 2], 1043, 3, 1e4, 0.5),
 }
 
 if __name__ == "__main__":

@@ -80,8 +80,16 @@ def test_cartpole2l_known_answer_traj():
 def make_ctrl(gold):
     spec = MODEL_SPECS[gold.model]
     dyn = make_dyn(gold.model, dt=spec["dt"])
-    ctrl = MPC(spec["nx"], spec["nu"], gold.T, u_lower=gold.t("u_lower"), u_upper=gold.t("u_upper"),
-               n_batch=gold.B, dtype=gold.dtype)
+    if "obstacle_positions" in gold.z.files:  # Obstacle_MPC scenario (qpth/AL_mpc_custom.py)
+        from deq_mpc_corl_b200.al_mpc import Obstacle_MPC
+
+        env = types.SimpleNamespace(obstacle_positions=gold.t("obstacle_positions"),
+                                    obstacle_radius=float(gold.z["obstacle_radius"]))
+        ctrl = Obstacle_MPC(spec["nx"], spec["nu"], gold.T, u_lower=gold.t("u_lower"), u_upper=gold.t("u_upper"),
+                            n_batch=gold.B, dtype=gold.dtype, env=env)
+    else:
+        ctrl = MPC(spec["nx"], spec["nu"], gold.T, u_lower=gold.t("u_lower"), u_upper=gold.t("u_upper"),
+                   n_batch=gold.B, dtype=gold.dtype)
     return ctrl, dyn, spec
 
 
@@ -99,6 +107,8 @@ def test_solve_matches_reference_golden(name):
             ctrl.reinitialize(c["x_ref"].to(DEV))
         if gold.stream_after == ci:
             ctrl.warm_start_initialize(ctrl.x_init, ctrl.u_init, types.SimpleNamespace(rho_init_max=gold.rho_init_max))
+        if "obs_pos" in c:  # the nearest-obstacle selection must match the reference's
+            assert torch.equal(ctrl.obstacles[0].cpu(), c["obs_pos"]), f"{name} call {ci}: obstacle selection"
         # call-level parity: start from the reference's own state
         assert bool(c["warm"]) == ctrl.warm_starting
         ctrl.x_init = c["xu_init"][..., :nx].to(DEV)

@@ -12,7 +12,10 @@ def replay(gold, resync=True):
     """Run the oracle through the same call chain as the golden scenario, re-synchronising nothing:
     the oracle carries its own (lam, rho, warm start) state exactly like the reference's MPC does."""
     model = make_oracle_model(gold.model)
-    mpc = orc.OracleMPC(model, gold.T, gold.t("u_lower"), gold.t("u_upper"), gold.B, dtype=gold.dtype)
+    obs_kw = {}
+    if "obstacle_positions" in gold.z.files:  # Obstacle_MPC scenario
+        obs_kw = dict(obstacle_positions=gold.t("obstacle_positions"), obstacle_radius=float(gold.z["obstacle_radius"]))
+    mpc = orc.OracleMPC(model, gold.T, gold.t("u_lower"), gold.t("u_upper"), gold.B, dtype=gold.dtype, **obs_kw)
     x0 = gold.t("x0")
     Qd1 = gold.t("Qd").to(gold.dtype)
     out = []
@@ -27,6 +30,9 @@ def replay(gold, resync=True):
             mpc.warm_start_initialize(xi, ui, gold.rho_init_max)
         if mpc.x_init is None:
             mpc.x_init, mpc.u_init = c["x_ref"].clone(), c["u_ref"].clone()
+        if obs_kw:
+            # nearest-obstacle selection (AL_mpc_custom.py:110-113,129-135) must pick the reference's obstacles
+            assert torch.equal(mpc.pb.obstacles[0], c["obs_pos"]), f"call {ci}: obstacle selection"
         if resync:
             # call-level parity: start every call from the reference's own (warm start, lam, rho)
             nx = model.nx
@@ -49,7 +55,7 @@ def tolerances(c, dtype):
     if dtype != torch.float64:
         return dict(xu=1e-3, lam=5e-3, grad=5e-3)
     rho_used = float(c["rho_out"].double().max()) / 10.0
-    return dict(xu=1e-8, lam=max(1e-7, 1e-13 * rho_used), grad=max(1e-7, 3e-13 * rho_used))
+    return dict(xu=1e-8, lam=max(1e-7, 1e-11 * rho_used), grad=max(1e-7, 3e-13 * rho_used))
 
 
 def check_line_search(trace, c, dtype, ci):
