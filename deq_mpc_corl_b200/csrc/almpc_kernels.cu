@@ -563,7 +563,7 @@ k_jacobian(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__
 // kernel 2/3: residual statistics, dual update, merit, gradient, block-tridiagonal factor + solve.
 // 1 warp = 1 problem.
 // ------------------------------------------------------------------------------------------------
-template <int NX, int NU, typename S, int WPB>
+template <int NX, int NU, typename S, int WPB, bool OBS>
 __global__ void __launch_bounds__(WPB * 32, ALMPC_FAC_MINB)
 k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restrict__ q_g, const S* __restrict__ xu_g,
                S* __restrict__ lam_g, S* __restrict__ rho_g, S* fac_g, const S* __restrict__ G_g,
@@ -579,7 +579,9 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
   const int mode = ctl->mode;
   if (mode == MODE_DONE) return;
   const int T = P.T;
-  const Layout<NX, NU> L(T, P.n_obs);
+  const int n_obs = OBS ? P.n_obs : 0;
+  const Layout<NX, NU> L(T, n_obs);
+  const int SI = OBS ? L.SI : 2 * NU;  // compile-time constant without obstacle rows
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int prob = blockIdx.x * WPB + warp;
   if (prob >= P.B) return;
@@ -598,7 +600,7 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
   const S* Gp = G_g + (size_t)prob * (T - 1) * NX * NN;
   S* fac = fac_g + (size_t)prob * factor_elems<NX, NU>(T);
   S* dbg = debug_g ? debug_g + (size_t)prob * (2 * L.N + 24) : nullptr;
-  const S* obs = P.n_obs ? P.obs + (size_t)prob * T * P.n_obs * 3 : nullptr;
+  const S* obs = OBS ? P.obs + (size_t)prob * T * n_obs * 3 : nullptr;
 
   if (T > 1) warp_copy_block_async<NX, NN, LB>(Gt, Gp, lane);  // G_0, consumed after the residual statistics
   cp_async_commit();
@@ -657,8 +659,8 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
       for (int u = 0; u < 4; ++u) {
         const int i = base + lane + 32 * u;
         if (i < L.nin) {
-          const int t = i / L.SI, sidx = i - t * L.SI;
-          const S ci = ineq_res<NX, NU, S>(xu + t * NN, sidx, P.ulo, P.uhi, obs + (size_t)t * P.n_obs * 3, P.obs_r2);
+          const int t = i / SI, sidx = i - t * SI;
+          const S ci = ineq_res<NX, NU, S>(xu + t * NN, sidx, P.ulo, P.uhi, OBS ? obs + (size_t)t * n_obs * 3 : nullptr, P.obs_r2);
           S li = lv[u];
           if (dual) { li = fmax0(li + rho_old * ci); lam[L.neq + i] = li; }
           const S cp = fmax0(ci);
@@ -709,11 +711,11 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
     cp_async_wait_all();  // G_t (issued one stage ago / in the prologue)
     __syncwarp();
     // obstacle rows of stage t: (lam_k + rho c_k+) and the active-masked Jacobian rows, staged in scr[0..]
-    if (P.n_obs) {
-      if (lane < P.n_obs) {
+    if constexpr (OBS) {
+      if (lane < n_obs) {
         S J[3];
-        const S ck = obstacle_res<S>(xu + t * NN, obs + ((size_t)t * P.n_obs + lane) * 3, P.obs_r2, J);
-        const S lk = lam[L.neq + t * L.SI + 2 * NU + lane];
+        const S ck = obstacle_res<S>(xu + t * NN, obs + ((size_t)t * n_obs + lane) * 3, P.obs_r2, J);
+        const S lk = lam[L.neq + t * SI + 2 * NU + lane];
         scr[lane * 8 + 0] = J[0];
         scr[lane * 8 + 1] = J[1];
         scr[lane * 8 + 2] = J[2];
@@ -742,11 +744,12 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
         const int sidx = j - NX;
         const S u = xu[idx];
         const S cu = u - P.uhi[sidx], cl = P.ulo[sidx] - u;
-        const S lu = lam[L.neq + t * L.SI + sidx], ll = lam[L.neq + t * L.SI + NU + sidx];
+        const S lu = lam[L.neq + t * SI + sidx], ll = lam[L.neq + t * SI + NU + sidx];
         g += (lu - ll) + rho * (fmax0(cu) - fmax0(cl));
       }
-      if (P.n_obs && j < 3) {
-        for (int k = 0; k < P.n_obs; ++k) g += scr[k * 8 + 3] * scr[k * 8 + j];
+      if constexpr (OBS) {
+        if (j < 3)
+          for (int k = 0; k < n_obs; ++k) g += scr[k * 8 + 3] * scr[k * 8 + j];
       }
       if (dbg) dbg[idx] = g;
       if (has_E && j < NX) {
@@ -763,11 +766,11 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
     }
     build_block<NX, NU, S>(scr + 64, xu + t * NN, X, Y, has_G, has_E, lane, rho, Qd + t * NN, P.ulo, P.uhi);
     __syncwarp();
-    if (P.n_obs) {  // + rho sum_k active J_k^T J_k on the position block (lower part)
+    if constexpr (OBS) {  // + rho sum_k active J_k^T J_k on the position block (lower part)
       if (lane < 6) {
         const int r = (lane < 1) ? 0 : (lane < 3 ? 1 : 2), c = lane - (r * (r + 1)) / 2;
         S acc = S(0);
-        for (int k = 0; k < P.n_obs; ++k) acc += scr[k * 8 + 4] * scr[k * 8 + r] * scr[k * 8 + c];
+        for (int k = 0; k < n_obs; ++k) acc += scr[k * 8 + 4] * scr[k * 8 + r] * scr[k * 8 + c];
         scr[64 + r * LD + c] += acc;
       }
       __syncwarp();
@@ -981,7 +984,7 @@ __device__ __forceinline__ void steer_solve(const KParams<S>& P, Ctl* ctl, int* 
 // One line-search item: candidate alpha = 2^-kk, stage t.  Evaluates the stage's share of the merit
 // (al_utils.py:52-77): cost, sum c+^2 and lam.c of the dynamics residual x_{t+1} - f(x_t,u_t), the control
 // bounds of stage t (and of the last stage for t = T-2) and the initial-state residual (t = 0).
-template <class M, typename S>
+template <class M, typename S, bool OBS>
 __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU>& L, const KParams<S>& P, int T,
                                         int kk, int t, S& cost, S& s2, S& sl) {
   constexpr int NX = M::NX, NU = M::NU, NN = NX + NU, LS = NN | 1;
@@ -991,6 +994,8 @@ __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU
   const S* Qd = sp + L.Qd;
   const S* qv = sp + L.q;
   const S* x0 = sp + L.x0;
+  const int n_obs = OBS ? P.n_obs : 0;
+  const int SI = OBS ? L.SI : 2 * NU;
     const S alpha = (S)ldexpf(1.0f, -kk);
     S xs[NX], us[NU], xn[NX];
     cost = S(0); s2 = S(0); sl = S(0);
@@ -1006,7 +1011,7 @@ __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU
       us[i] = z;
       cost += S(0.5) * (z * Qd[t * LS + NX + i] * z) + qv[t * LS + NX + i] * z;
       const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
-      sl += lam[L.neq + t * L.SI + i] * cu + lam[L.neq + t * L.SI + NU + i] * cl;
+      sl += lam[L.neq + t * SI + i] * cu + lam[L.neq + t * SI + NU + i] * cl;
       const S pu = fmax0(cu), pl = fmax0(cl);
       s2 += pu * pu + pl * pl;
     }
@@ -1018,11 +1023,11 @@ __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU
         sl += lam[(T - 1) * NX + i] * ci;
       }
     }
-    if (P.n_obs) {  // obstacle rows of stage t at the candidate position
-      const S* ob = sp + L.obs + t * P.n_obs * 3;
-      for (int k = 0; k < P.n_obs; ++k) {
+    if constexpr (OBS) {  // obstacle rows of stage t at the candidate position
+      const S* ob = sp + L.obs + t * n_obs * 3;
+      for (int k = 0; k < n_obs; ++k) {
         const S ck = obstacle_res<S>(xs, ob + k * 3, P.obs_r2, nullptr);
-        sl += lam[L.neq + t * L.SI + 2 * NU + k] * ck;
+        sl += lam[L.neq + t * SI + 2 * NU + k] * ck;
         const S cp = fmax0(ck);
         s2 += cp * cp;
       }
@@ -1035,7 +1040,7 @@ __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU
       const S ci = z1 - xn[i];
       s2 += ci * ci;
       sl += lam[t * NX + i] * ci;
-      if (i < 3) zlast[i] = z1;
+      if (OBS && i < 3) zlast[i] = z1;
       if (t == T - 2) cost += S(0.5) * (z1 * Qd[(t + 1) * LS + i] * z1) + qv[(t + 1) * LS + i] * z1;
     }
     if (t == T - 2) {
@@ -1045,15 +1050,15 @@ __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU
         const S z = xu[e] + alpha * dv[e];
         cost += S(0.5) * (z * Qd[e] * z) + qv[e] * z;
         const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
-        sl += lam[L.neq + (T - 1) * L.SI + i] * cu + lam[L.neq + (T - 1) * L.SI + NU + i] * cl;
+        sl += lam[L.neq + (T - 1) * SI + i] * cu + lam[L.neq + (T - 1) * SI + NU + i] * cl;
         const S pu = fmax0(cu), pl = fmax0(cl);
         s2 += pu * pu + pl * pl;
       }
-      if (P.n_obs) {  // obstacle rows of the last stage
-        const S* ob = sp + L.obs + (T - 1) * P.n_obs * 3;
-        for (int k = 0; k < P.n_obs; ++k) {
+      if constexpr (OBS) {  // obstacle rows of the last stage
+        const S* ob = sp + L.obs + (T - 1) * n_obs * 3;
+        for (int k = 0; k < n_obs; ++k) {
           const S ck = obstacle_res<S>(zlast, ob + k * 3, P.obs_r2, nullptr);
-          sl += lam[L.neq + (T - 1) * L.SI + 2 * NU + k] * ck;
+          sl += lam[L.neq + (T - 1) * SI + 2 * NU + k] * ck;
           const S cp = fmax0(ck);
           s2 += cp * cp;
         }
@@ -1099,7 +1104,7 @@ __device__ __forceinline__ void ls_stage_async(S* sp, const LsLayout<NX, NU>& L,
   if (obs_g) copy(sp + L.obs, obs_g + (size_t)prob * (L.nin / L.SI) * (L.SI - 2 * NU) * 3, (L.nin / L.SI) * (L.SI - 2 * NU) * 3);
 }
 
-template <class M, typename S>
+template <class M, typename S, bool OBS>
 __global__ void __launch_bounds__(256, 2)
 k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, const S* __restrict__ Qd_g,
               const S* __restrict__ q_g, S* xu_g, const S* __restrict__ lam_g,
@@ -1115,7 +1120,7 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
   if (mode == MODE_DONE) return;
   const int al_a = ctl->a, nk = ctl->k;
   const int T = P.T;
-  const LsLayout<NX, NU> L(T, P.n_obs);
+  const LsLayout<NX, NU> L(T, OBS ? P.n_obs : 0);
   const int IT = NLS * (T - 1);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -1130,7 +1135,7 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
   if ((int)blockIdx.x < ngroups) {
     for (int p = 0; p < pls; ++p) {
       const int prob = blockIdx.x * pls + p;
-      if (prob < P.B) ls_stage_async<NX, NU, S>(smem + (size_t)p * L.total, L, prob, tid, nthr, x0_g, Qd_g, q_g, xu_g, lam_g, d_g, P.obs);
+      if (prob < P.B) ls_stage_async<NX, NU, S>(smem + (size_t)p * L.total, L, prob, tid, nthr, x0_g, Qd_g, q_g, xu_g, lam_g, d_g, OBS ? P.obs : nullptr);
     }
   }
   cp_async_commit();
@@ -1141,7 +1146,7 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
       S* nb = smem + (size_t)(cur ^ 1) * buf_elems;
       for (int p = 0; p < pls; ++p) {
         const int prob = nxt * pls + p;
-        if (prob < P.B) ls_stage_async<NX, NU, S>(nb + (size_t)p * L.total, L, prob, tid, nthr, x0_g, Qd_g, q_g, xu_g, lam_g, d_g, P.obs);
+        if (prob < P.B) ls_stage_async<NX, NU, S>(nb + (size_t)p * L.total, L, prob, tid, nthr, x0_g, Qd_g, q_g, xu_g, lam_g, d_g, OBS ? P.obs : nullptr);
       }
     }
     cp_async_commit();
@@ -1156,7 +1161,7 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
     S* part = const_cast<S*>(sp) + L.part;
     const int kk = it / (T - 1), t = it - kk * (T - 1);
     S cost, s2, sl;
-    ls_item<M, S>(sp, L, P, T, kk, t, cost, s2, sl);
+    ls_item<M, S, OBS>(sp, L, P, T, kk, t, cost, s2, sl);
     part[it * 3 + 0] = cost;
     part[it * 3 + 1] = s2;
     part[it * 3 + 2] = sl;
@@ -1265,7 +1270,7 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
 // rounds, no idle lanes); the T-1 stage items of a candidate sit in adjacent lanes, so candidate totals are
 // segmented shuffle reductions and there is no CTA barrier and no partial-sum traffic in the loop.
 // ------------------------------------------------------------------------------------------------
-template <class M, typename S, int TM1, int WPB>
+template <class M, typename S, int TM1, int WPB, bool OBS>
 __global__ void __launch_bounds__(WPB * 32, ALMPC_LS_MINB)
 k_line_search_warp(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__ Qd_g,
                    const S* __restrict__ q_g, S* xu_g, const S* __restrict__ lam_g, const S* __restrict__ rho_g,
@@ -1285,7 +1290,7 @@ k_line_search_warp(const KParams<S> P, const S* __restrict__ x0_g, const S* __re
   if (mode == MODE_DONE) return;
   const int al_a = ctl->a, nk = ctl->k;
   constexpr int T = TM1 + 1;
-  const LsLayout<NX, NU> L(T, P.n_obs);
+  const LsLayout<NX, NU> L(T, OBS ? P.n_obs : 0);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int stride = L.part;  // staged scalars per problem (the partial-sum area of the CTA variant is unused)
@@ -1300,7 +1305,7 @@ k_line_search_warp(const KParams<S> P, const S* __restrict__ x0_g, const S* __re
 #pragma unroll
     for (int p = 0; p < PW; ++p) {
       if (prob0 + p < P.B)
-        ls_stage_async<NX, NU, S>(wsm + (size_t)p * stride, L, prob0 + p, lane, 32, x0_g, Qd_g, q_g, xu_g, lam_g, d_g, P.obs);
+        ls_stage_async<NX, NU, S>(wsm + (size_t)p * stride, L, prob0 + p, lane, 32, x0_g, Qd_g, q_g, xu_g, lam_g, d_g, OBS ? P.obs : nullptr);
     }
     cp_async_commit();
     // per-problem scalars travel in registers while the copies are in flight
@@ -1328,7 +1333,7 @@ k_line_search_warp(const KParams<S> P, const S* __restrict__ x0_g, const S* __re
       const int kk = it / TM1, t = it - kk * TM1;
       const bool valid = prob0 + p < P.B;
       S cost = S(0), s2 = S(0), sl = S(0);
-      if (valid) ls_item<M, S>(wsm + (size_t)p * stride, L, P, T, kk, t, cost, s2, sl);
+      if (valid) ls_item<M, S, OBS>(wsm + (size_t)p * stride, L, P, T, kk, t, cost, s2, sl);
       // candidate totals: the TM1 stage items of a candidate are adjacent lanes; fixed summation order t=0..TM1-1
       S c_tot = S(0), s_tot = S(0), l_tot = S(0);
 #pragma unroll
@@ -1419,7 +1424,7 @@ k_line_search_warp(const KParams<S> P, const S* __restrict__ x0_g, const S* __re
 // final dual update + outputs (always runs once at the end of a forward solve)
 //   lam <- lam + rho c(xu), clamp ; rho <- 10 rho ; dyn_res = ||c+|| ; x,u -> fp32     AL_mpc.py:315-338
 // ------------------------------------------------------------------------------------------------
-template <class M, typename S, int WPB>
+template <class M, typename S, int WPB, bool OBS>
 __global__ void __launch_bounds__(WPB * 32)
 k_final_dual(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__ xu_g, S* __restrict__ lam_g,
              S* __restrict__ rho_g, float* __restrict__ x_out, float* __restrict__ u_out, S* __restrict__ dyn_res_g,
@@ -1427,7 +1432,9 @@ k_final_dual(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict
   constexpr int NX = M::NX, NU = M::NU, NN = NX + NU;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = P.T;
-  const Layout<NX, NU> L(T, P.n_obs);
+  const int n_obs = OBS ? P.n_obs : 0;
+  const Layout<NX, NU> L(T, n_obs);
+  const int SI = OBS ? L.SI : 2 * NU;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int prob = blockIdx.x * WPB + warp;
   grid_dep_wait();
@@ -1462,10 +1469,10 @@ k_final_dual(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict
     if (upd) lamp[i] += rho * ci;
     s2 += ci * ci;
   }
-  const S* obs = P.n_obs ? P.obs + (size_t)prob * T * P.n_obs * 3 : nullptr;
+  const S* obs = OBS ? P.obs + (size_t)prob * T * n_obs * 3 : nullptr;
   for (int i = lane; i < L.nin; i += 32) {
-    const int t = i / L.SI, s = i - t * L.SI;
-    const S ci = ineq_res<NX, NU, S>(xu + t * NN, s, P.ulo, P.uhi, obs + (size_t)t * P.n_obs * 3, P.obs_r2);
+    const int t = i / SI, s = i - t * SI;
+    const S ci = ineq_res<NX, NU, S>(xu + t * NN, s, P.ulo, P.uhi, OBS ? obs + (size_t)t * n_obs * 3 : nullptr, P.obs_r2);
     if (upd) lamp[L.neq + i] = fmax0(lamp[L.neq + i] + rho * ci);
     S cp = fmax0(ci);
     s2 += cp * cp;
@@ -1727,11 +1734,11 @@ constexpr int kWLS = 4;  // warps per CTA of the warp-synchronous line search
 
 struct LsWarpCfg { const void* fn; int grid_cap; size_t smem; int pw; };
 
-template <class M, typename S, int TM1>
+template <class M, typename S, int TM1, bool OBS>
 static cudaError_t ls_warp_cfg(LsWarpCfg& c, int n_sm, int n_obs) {
   constexpr int PW = (8 / TM1) > 0 ? (8 / TM1) : 1;
   const LsLayout<M::NX, M::NU> LL(TM1 + 1, n_obs);
-  auto k = k_line_search_warp<M, S, TM1, kWLS>;
+  auto k = k_line_search_warp<M, S, TM1, kWLS, OBS>;
   size_t smem = (size_t)kWLS * PW * LL.part * sizeof(S);
   if (smem < (size_t)kWLS * 32 * 3 * sizeof(double)) smem = (size_t)kWLS * 32 * 3 * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1746,7 +1753,7 @@ static cudaError_t ls_warp_cfg(LsWarpCfg& c, int n_sm, int n_obs) {
   return cudaSuccess;
 }
 
-template <class M, typename S>
+template <class M, typename S, bool OBS>
 static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* q, S* xu, S* lam, S* rho, S* factor,
                         float* x_out, float* u_out, S* dyn_res_out, int32_t* status_out, int32_t* info_out,
                         S* debug_out, void* workspace, cudaStream_t st) {
@@ -1755,7 +1762,7 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   if (!x0 || !Qd || !q || !xu || !lam || !rho || !factor || !info_out || !workspace)
     return set_err(-10, "null buffer");
   const int T = d->T, B = d->B;
-  const int n_obs = d->obstacles ? d->n_obs : 0;
+  const int n_obs = OBS ? d->n_obs : 0;
   const Layout<NX, NU> L(T, n_obs);
   const LsLayout<NX, NU> LL(T, n_obs);
   const LsGeom lg = ls_geom(B, T);
@@ -1767,9 +1774,9 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   if (smem_fac + 1024 > 227 * 1024 || smem_ls + 1024 > 227 * 1024)
     return set_err(-11, "horizon too long for the shared-memory layout");
   auto kjac = k_jacobian<M, S>;
-  auto kfac = k_factor_solve<NX, NU, S, kWPB>;
-  auto kls = k_line_search<M, S>;
-  auto kfin = k_final_dual<M, S, kWPB>;
+  auto kfac = k_factor_solve<NX, NU, S, kWPB, OBS>;
+  auto kls = k_line_search<M, S, OBS>;
+  auto kfin = k_final_dual<M, S, kWPB, OBS>;
   cudaError_t e;
   e = cudaFuncSetAttribute(kfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fac);
   if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(factor_solve)");
@@ -1791,12 +1798,12 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   LsWarpCfg lw{nullptr, 0, 0, 1};
   if (!getenv("ALMPC_LS_CTA")) {
     switch (T - 1) {
-      case 1: e = ls_warp_cfg<M, S, 1>(lw, n_sm, n_obs); break;
-      case 2: e = ls_warp_cfg<M, S, 2>(lw, n_sm, n_obs); break;
-      case 4: e = ls_warp_cfg<M, S, 4>(lw, n_sm, n_obs); break;
-      case 8: e = ls_warp_cfg<M, S, 8>(lw, n_sm, n_obs); break;
-      case 16: e = ls_warp_cfg<M, S, 16>(lw, n_sm, n_obs); break;
-      case 32: e = ls_warp_cfg<M, S, 32>(lw, n_sm, n_obs); break;
+      case 1: e = ls_warp_cfg<M, S, 1, OBS>(lw, n_sm, n_obs); break;
+      case 2: e = ls_warp_cfg<M, S, 2, OBS>(lw, n_sm, n_obs); break;
+      case 4: e = ls_warp_cfg<M, S, 4, OBS>(lw, n_sm, n_obs); break;
+      case 8: e = ls_warp_cfg<M, S, 8, OBS>(lw, n_sm, n_obs); break;
+      case 16: e = ls_warp_cfg<M, S, 16, OBS>(lw, n_sm, n_obs); break;
+      case 32: e = ls_warp_cfg<M, S, 32, OBS>(lw, n_sm, n_obs); break;
       default: break;
     }
     if (e != cudaSuccess) return cuda_err(e, "line-search (warp) configuration");
@@ -2013,8 +2020,16 @@ static int forward_any(const almpc_desc* d, const S* x0, const S* Qd, const S* q
   int rc = check_desc(d);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  ALMPC_DISPATCH(d->dyn_id, (forward_impl<M, S>(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out,
-                                                status_out, info_out, debug_out, workspace, st)))
+  if (d->obstacles && d->n_obs > 0) {
+    // sphere-avoidance rows act on the position x[0..2]; compiled for the one reference env that uses them
+    // (FlyingCartpole_obstacles, deqmpc/policies.py:1180)
+    if (d->dyn_id != ALMPC_DYN_FLYING_CARTPOLE)
+      return set_err(-8, "obstacle constraints are compiled for the flying-cartpole model only");
+    return forward_impl<FlyingCartpole, S, true>(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out,
+                                                 status_out, info_out, debug_out, workspace, st);
+  }
+  ALMPC_DISPATCH(d->dyn_id, (forward_impl<M, S, false>(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out,
+                                                       status_out, info_out, debug_out, workspace, st)))
 }
 
 template <typename S>

@@ -106,7 +106,11 @@ def test_solve_matches_reference_golden(name):
         if ci == 0:
             ctrl.reinitialize(c["x_ref"].to(DEV))
         if gold.stream_after == ci:
-            ctrl.warm_start_initialize(ctrl.x_init, ctrl.u_init, types.SimpleNamespace(rho_init_max=gold.rho_init_max))
+            # Tracking_MPC.warm_start_initialize (policies.py:1305-1310): last stage of the warm start <- reference
+            xi, ui = ctrl.x_init, ctrl.u_init
+            ui[:, -1:] = c["u_ref"][:, -1:].to(DEV)
+            xi[:, -1:] = c["x_ref"][:, -1:].to(DEV)
+            ctrl.warm_start_initialize(xi, ui, types.SimpleNamespace(rho_init_max=gold.rho_init_max))
         if "obs_pos" in c:  # the nearest-obstacle selection must match the reference's
             assert torch.equal(ctrl.obstacles[0].cpu(), c["obs_pos"]), f"{name} call {ci}: obstacle selection"
         # call-level parity: start from the reference's own state

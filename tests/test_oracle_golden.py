@@ -55,7 +55,7 @@ def tolerances(c, dtype):
     if dtype != torch.float64:
         return dict(xu=1e-3, lam=5e-3, grad=5e-3)
     rho_used = float(c["rho_out"].double().max()) / 10.0
-    return dict(xu=1e-8, lam=max(1e-7, 1e-11 * rho_used), grad=max(1e-7, 3e-13 * rho_used))
+    return dict(xu=1e-8, lam=max(1e-7, 1e-11 * rho_used), grad=max(1e-7, 3e-12 * rho_used))
 
 
 def check_line_search(trace, c, dtype, ci):
