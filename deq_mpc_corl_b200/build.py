@@ -28,21 +28,37 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Two translation units (fp64 / fp32 entry points) compiled in parallel, then linked."""
     if not force and not needs_build():
         return OUT
-    cmd = [
-        nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-        "-shared", "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xcompiler", "-O2",
-        "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "csrc"), "-o", OUT, SRC,
-    ]
+    import concurrent.futures
+
+    common = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "csrc")]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        common += ["-Xptxas", "-v"]
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    units = [("f64", ["-DALMPC_BUILD_F64=1", "-DALMPC_BUILD_F32=0"]), ("f32", ["-DALMPC_BUILD_F64=0", "-DALMPC_BUILD_F32=1"])]
+
+    def compile_unit(u):
+        name, defs = u
+        obj = os.path.join(objdir, f"almpc_{name}.o")
+        cmd = common + defs + ["-c", SRC, "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=2) as ex:
+        results = list(ex.map(compile_unit, units))
+    if verbose:
+        for _, err in results:
+            print(err)
+    link = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + [o for o, _ in results]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + res.stdout + res.stderr)
     return OUT
 
 

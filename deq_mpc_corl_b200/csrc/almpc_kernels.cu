@@ -34,6 +34,14 @@
 #include "almpc.h"
 #include "almpc_models.cuh"
 
+// The library is compiled as two translation units (fp64 / fp32 entry points) built in parallel; the common
+// entry points live in the fp64 unit.
+#ifndef ALMPC_BUILD_F64
+#define ALMPC_BUILD_F64 1
+#endif
+#ifndef ALMPC_BUILD_F32
+#define ALMPC_BUILD_F32 1
+#endif
 #ifndef ALMPC_NO_VEC2
 #define ALMPC_NO_VEC2 0
 #endif
@@ -1629,7 +1637,11 @@ __global__ void k_fma_peak(int iters, S* sink) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static thread_local char g_err[512] = "";
+#if ALMPC_BUILD_F64
+thread_local char g_err[512] = "";
+#else
+extern thread_local char g_err[512];
+#endif
 static int set_err(int code, const char* what) {
   snprintf(g_err, sizeof(g_err), "%s", what);
   return code;
@@ -1671,8 +1683,14 @@ constexpr int kWPB = 4;
 constexpr int kMaxParts = 4;
 
 // optional per-kernel timing (bench.py): events around every launch of one forward call
-static int g_profile_on = 0;
-static double g_profile[8] = {0};  // ms: [0] jacobian [1] factor_solve [2] line_search [3] final_dual, [4..7] launch counts
+// (shared by the two translation units: defined in the fp64 unit)
+#if ALMPC_BUILD_F64
+int g_profile_on = 0;
+double g_profile[8] = {0};  // ms: [0] jacobian [1] factor_solve [2] line_search [3] final_dual, [4..7] launch counts
+#else
+extern int g_profile_on;
+extern double g_profile[8];
+#endif
 struct ProfEv { cudaEvent_t a, b; int kind; };
 
 static int n_blocks(int B) { return (B + kWPB - 1) / kWPB; }
@@ -2092,6 +2110,7 @@ using namespace almpc;
 
 extern "C" {
 
+#if ALMPC_BUILD_F64
 int almpc_model_dims(int32_t dyn_id, int32_t* nx, int32_t* nu) {
   int x, u;
   switch (dyn_id) {
@@ -2125,61 +2144,87 @@ size_t almpc_debug_elems(const almpc_desc* d) {
   if (!d || almpc_model_dims(d->dyn_id, &nx, &nu)) return 0;
   return 2 * (size_t)d->T * (nx + nu) + 24;
 }
+#endif  // common entry points (fp64 unit)
 
+#if ALMPC_BUILD_F64
 int almpc_forward_f64(const almpc_desc* d, const double* x0, const double* Qd, const double* q, double* xu,
                       double* lam, double* rho, double* factor, float* x_out, float* u_out, double* dyn_res_out,
                       int32_t* status_out, int32_t* info_out, double* debug_out, void* workspace, void* stream) {
   return forward_any<double>(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out, status_out, info_out,
                              debug_out, workspace, stream);
 }
+#endif
+#if ALMPC_BUILD_F32
 int almpc_forward_f32(const almpc_desc* d, const float* x0, const float* Qd, const float* q, float* xu, float* lam,
                       float* rho, float* factor, float* x_out, float* u_out, float* dyn_res_out, int32_t* status_out,
                       int32_t* info_out, float* debug_out, void* workspace, void* stream) {
   return forward_any<float>(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out, status_out, info_out,
                             debug_out, workspace, stream);
 }
+#endif
+#if ALMPC_BUILD_F64
 int almpc_backward_f64(const almpc_desc* d, const double* factor, const double* xu, const double* grad_xu,
                        double* grad_Q, double* grad_q, void* stream) {
   return backward_any<double>(d, factor, xu, grad_xu, grad_Q, grad_q, stream);
 }
+#endif
+#if ALMPC_BUILD_F32
 int almpc_backward_f32(const almpc_desc* d, const float* factor, const float* xu, const float* grad_xu,
                        float* grad_Q, float* grad_q, void* stream) {
   return backward_any<float>(d, factor, xu, grad_xu, grad_Q, grad_q, stream);
 }
+#endif
+#if ALMPC_BUILD_F64
 int almpc_dynamics_f64(const almpc_desc* d, int64_t R, const double* x, const double* u, double* xn, double* Jx,
                        double* Ju, void* stream) {
   return dynamics_any<double>(d, R, x, u, xn, Jx, Ju, stream);
 }
+#endif
+#if ALMPC_BUILD_F32
 int almpc_dynamics_f32(const almpc_desc* d, int64_t R, const float* x, const float* u, float* xn, float* Jx,
                        float* Ju, void* stream) {
   return dynamics_any<float>(d, R, x, u, xn, Jx, Ju, stream);
 }
+#endif
+#if ALMPC_BUILD_F64
 int almpc_fma_peak_f64(int32_t blocks, int32_t iters, double* sink, double* flops, void* stream) {
   return fma_peak<double>(blocks, iters, sink, flops, stream);
 }
+#endif
+#if ALMPC_BUILD_F32
 int almpc_fma_peak_f32(int32_t blocks, int32_t iters, float* sink, double* flops, void* stream) {
   return fma_peak<float>(blocks, iters, sink, flops, stream);
 }
+#endif
+#if ALMPC_BUILD_F64
 int almpc_tracking_cost_f64(int32_t B, int32_t T, int32_t nx, int32_t nu, const double* Q0, const float* x_ref,
                             const float* u_ref, const float* scale, double* Qd, double* q, void* stream) {
   return tracking_cost<double>(B, T, nx, nu, Q0, x_ref, u_ref, scale, Qd, q, stream);
 }
+#endif
+#if ALMPC_BUILD_F32
 int almpc_tracking_cost_f32(int32_t B, int32_t T, int32_t nx, int32_t nu, const float* Q0, const float* x_ref,
                             const float* u_ref, const float* scale, float* Qd, float* q, void* stream) {
   return tracking_cost<float>(B, T, nx, nu, Q0, x_ref, u_ref, scale, Qd, q, stream);
 }
+#endif
+#if ALMPC_BUILD_F64
 int almpc_tracking_cost_bwd_f64(int32_t B, int32_t T, int32_t nx, int32_t nu, const double* Q0, const float* x_ref,
                                 const float* u_ref, const float* scale, const double* grad_Q, const double* grad_q,
                                 float* grad_x_ref, float* grad_u_ref, float* grad_scale, void* stream) {
   return tracking_cost_bwd<double>(B, T, nx, nu, Q0, x_ref, u_ref, scale, grad_Q, grad_q, grad_x_ref, grad_u_ref,
                                    grad_scale, stream);
 }
+#endif
+#if ALMPC_BUILD_F32
 int almpc_tracking_cost_bwd_f32(int32_t B, int32_t T, int32_t nx, int32_t nu, const float* Q0, const float* x_ref,
                                 const float* u_ref, const float* scale, const float* grad_Q, const float* grad_q,
                                 float* grad_x_ref, float* grad_u_ref, float* grad_scale, void* stream) {
   return tracking_cost_bwd<float>(B, T, nx, nu, Q0, x_ref, u_ref, scale, grad_Q, grad_q, grad_x_ref, grad_u_ref,
                                   grad_scale, stream);
 }
+#endif
+#if ALMPC_BUILD_F64
 void almpc_set_profiling(int32_t on) { g_profile_on = on; }
 void almpc_get_profile(double* out8) {
   for (int k = 0; k < 8; ++k) out8[k] = g_profile[k];
@@ -2187,4 +2232,5 @@ void almpc_get_profile(double* out8) {
 const char* almpc_last_error(void) { return g_err; }
 const char* almpc_version(void) { return "almpc 0.1 (sm_100a)"; }
 
+#endif
 }  // extern "C"
