@@ -59,6 +59,8 @@ def build(force=False, verbose=False):
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + res.stdout + res.stderr)
+    for o, _ in results:  # objects are not needed once linked (keeps the gpurun snapshot small)
+        os.remove(o)
     return OUT
 
 
