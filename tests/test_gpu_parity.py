@@ -388,3 +388,47 @@ def test_tracking_mpc_fused_cost_and_chain_rule():
     tm.warm_start_initialize(xr.detach(), ur.detach())
     x3, u3, st3 = tm(x0, None, xr.detach(), ur.detach(), al_iters=2)
     assert tm.ctrl.warm_starting and isinstance(st3, bool) and torch.isfinite(x3).all()
+
+
+def test_forward_backward_are_cuda_graph_capturable():
+    """include/almpc.h promises no host synchronisation and no allocation inside the library: capture a whole
+    forward + backward in a CUDA graph, replay it on fresh inputs, compare with the eager result."""
+    from deq_mpc_corl_b200.solver import SolveConfig, raw_backward, raw_forward
+
+    model, T, B = "rex_quadrotor", 5, 512
+    spec = MODEL_SPECS[model]
+    n, m = spec["nx"] + spec["nu"], T * spec["nx"] + 2 * T * spec["nu"]
+    dyn = make_dyn(model)
+    inpA, inpB = make_inputs(model, T, B, 31), make_inputs(model, T, B, 32)
+    cfg = SolveConfig(dyn=dyn, T=T, u_lower=inpA["u_lower"].tolist(), u_upper=inpA["u_upper"].tolist(), al_iter=2, rho_f32=True)
+
+    def tensors(inp):
+        Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"])
+        return (inp["x0"].double().to(DEV), Qd.to(DEV), q.to(DEV),
+                torch.cat([inp["x_ref"], inp["u_ref"]], -1).double().to(DEV).contiguous())
+
+    def eager(inp):
+        x0, Qd, q, xu = tensors(inp)
+        lam, rho = torch.zeros(B, m, dtype=torch.float64, device=DEV), torch.ones(B, dtype=torch.float64, device=DEV)
+        out = raw_forward(cfg, x0, Qd, q, xu, lam, rho)
+        _, gq = raw_backward(cfg, out["factor"], xu, torch.ones_like(xu), need_Q=False)
+        return xu, lam, gq, out["info"]
+
+    # static buffers of the graph
+    x0, Qd, q, xu0 = tensors(inpA)
+    xu, lam, rho = xu0.clone(), torch.zeros(B, m, dtype=torch.float64, device=DEV), torch.ones(B, dtype=torch.float64, device=DEV)
+    gsrc = torch.ones_like(xu)
+    eager(inpA)  # warm-up outside capture (lazy module loading, attribute calls)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = raw_forward(cfg, x0, Qd, q, xu, lam, rho)
+        _, gq = raw_backward(cfg, out["factor"], xu, gsrc, need_Q=False)
+    for inp in (inpA, inpB):
+        a, b, c, d = tensors(inp)
+        x0.copy_(a); Qd.copy_(b); q.copy_(c); xu.copy_(d); lam.zero_(); rho.fill_(1.0)
+        graph.replay()
+        torch.cuda.synchronize()
+        xu_e, lam_e, gq_e, info_e = eager(inp)
+        assert torch.equal(xu, xu_e) and torch.equal(lam, lam_e) and torch.equal(gq, gq_e)
+        assert torch.equal(out["info"], info_e)
