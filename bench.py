@@ -366,6 +366,46 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = e2e_ms.item()
+    # ---- e2e one level up: Tracking_MPC (the reference's actual caller, policies.py:1117-1315): host inputs are
+    # the fp32 network outputs (x0, x_ref, u_ref) + output grads; the cost build and its chain rule run fused
+    import types as _types
+    from deq_mpc_corl_b200.tracking import Tracking_MPC
+
+    targs = _types.SimpleNamespace(T=T, bsz=B, Q=torch.tensor(spec["Q"]), R=torch.tensor(spec["R"]),
+                                   dtype="double" if dtype == torch.float64 else "float", device=dev,
+                                   solver_type="al", env=model, rho_init_max=1e4)
+    tenv = _types.SimpleNamespace(nx=nx, nu=nu, nq=None, dt=spec["dt"], dynamics=dyn, dynamics_derivatives=dyn,
+                                  action_space=_types.SimpleNamespace(low=inp["u_lower"].numpy(), high=inp["u_upper"].numpy()))
+    tm = Tracking_MPC(targs, tenv)
+    th = dict(x0=h["x0"], x_ref=h["x_ref"], u_ref=h["u_ref"], gx=h["gx"], gu=h["gu"])
+    tout = dict(x=out_h["x"], u=out_h["u"], gxr=torch.empty(B, T, nx).pin_memory(), gur=torch.empty(B, T, nu).pin_memory())
+    t_h2d = sum(t.numel() * t.element_size() for t in th.values())
+    t_d2h = sum(t.numel() * t.element_size() for t in tout.values())
+
+    def e2e_tracking_step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in th.items()}
+        xr, ur = d["x_ref"].requires_grad_(True), d["u_ref"].requires_grad_(True)
+        tm.reinitialize(xr.detach(), None)
+        x, u, _ = tm(d["x0"], None, xr, ur, al_iters=2)
+        gxr, gur = torch.autograd.grad((x, u), (xr, ur), (d["gx"], d["gu"]))
+        tout["x"].copy_(x.detach(), non_blocking=True)
+        tout["u"].copy_(u.detach(), non_blocking=True)
+        tout["gxr"].copy_(gxr, non_blocking=True)
+        tout["gur"].copy_(gur, non_blocking=True)
+
+    for _ in range(2):
+        e2e_tracking_step()
+    barrier()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record()
+    for _ in range(k_e2e):
+        e2e_tracking_step()
+    e5.record()
+    barrier()
+    e2e_t_ms = torch.tensor([e4.elapsed_time(e5)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t_ms, op=dist.ReduceOp.MAX)
+    e2e_t_ms = e2e_t_ms.item()
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -401,7 +441,10 @@ def main():
             "e2e": {"value": k_e2e * B * world / (e2e_ms * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / k_e2e,
                     "api": "deq_mpc_corl_b200.al_mpc.MPC.forward + autograd backward, pinned host buffers"},
-            "gpu_launches": args.steps * (cfg.al_iter * cfg.max_newton * 3 + 2),
+            "e2e_tracking": {"value": k_e2e * B * world / (e2e_t_ms * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": t_h2d,
+                             "d2h_bytes_per_step": t_d2h, "ms_per_step": e2e_t_ms / k_e2e,
+                             "api": "deq_mpc_corl_b200.tracking.Tracking_MPC.forward (fused cost build) + autograd backward to x_ref/u_ref"},
+            "gpu_launches": args.steps * (cfg.al_iter * cfg.max_newton * 3 + 2),  # 3 kernels per Newton-step slot + final dual + backward
             "roofline": {
                 # dominant kernel by time, against whichever of its two rooflines it sits closer to
                 "kernel": dom, "bound": (fma_name if dom_fma else "hbm"),
