@@ -783,62 +783,54 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
       }
       __syncwarp();
     }
-    // rows into registers: L rows | rhs | -rho G_t rows
+    // rows into registers: L rows | rhs | -rho G_t rows.  One uniform load loop with a per-lane row pointer
+    // (three divergent loops cost three times the LSU instructions).
     S a[NN];
-    if (lane < NN) {
+    {
+      const int ei = lane - NN - 1;
+      const bool e_act = (ei >= 0) && (ei < NX) && has_G;
+      const S* rowp = (lane < NN) ? (scr + 64 + lane * LD) : ((lane == NN) ? (dv + t * NN) : (X + (e_act ? ei : 0) * LB));
+      const S scale = (lane <= NN) ? S(1) : (e_act ? -rho : S(0));
+      const int last = (lane < NN) ? lane : NN - 1;  // L rows: lower triangle only
 #pragma unroll
-      for (int c = 0; c < NN; ++c) a[c] = (c <= lane) ? scr[64 + lane * LD + c] : S(0);
-    } else if (lane == NN) {
-#pragma unroll
-      for (int c = 0; c < NN; ++c) a[c] = dv[t * NN + c];
-    } else {
-      const int i = lane - NN - 1;
-      const bool act = (i < NX) && has_G;
-#pragma unroll
-      for (int c = 0; c < NN; ++c) a[c] = act ? -rho * X[i * LB + c] : S(0);
+      for (int c = 0; c < NN; ++c) {
+        const S v = rowp[c] * scale;
+        a[c] = (c <= last) ? v : S(0);
+      }
     }
     __syncwarp();  // Y (E_{t-1}) has no reader left: prefetch G_{t+1} into it behind the pivot chain
     if (t + 1 < T - 1) warp_copy_block_async<NX, NN, LB>(Y, Gp + (size_t)(t + 1) * NX * NN, lane);
     cp_async_commit();
     ok = eliminate<NN, true>(a, lane, scr) && ok;
     __syncwarp();
-    if (lane < NN) {
-      if constexpr (NN % 2 == 0) {  // rows are 16-byte aligned: 128-bit stores
-#pragma unroll
-        for (int c = 0; c < NN; c += 2) {
-          Vec2<S> v;
-          v.x = (c <= lane) ? a[c] : S(0);
-          v.y = (c + 1 <= lane) ? a[c + 1] : S(0);
-          *reinterpret_cast<Vec2<S>*>(Lg + lane * NN + c) = v;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < NN; ++c) Lg[lane * NN + c] = (c <= lane) ? a[c] : S(0);
-      }
-      if (NX > EX0 && has_G) {  // publish L for the second elimination pass
-#pragma unroll
-        for (int c = 0; c < NN; ++c) scr[64 + lane * LD + c] = a[c];
-      }
-    } else if (lane == NN) {
-#pragma unroll
-      for (int c = 0; c < NN; ++c) dv[t * NN + c] = a[c];
-    } else {
-      const int i = lane - NN - 1;
-      if (i < NX && has_G && NX <= EX0) {
-#pragma unroll
-        for (int c = 0; c < NN; ++c) X[i * LB + c] = a[c];
-        if constexpr (NN % 2 == 0) {
+    {
+      // write-outs with per-lane destinations: L rows -> global factor; rhs -> dv (y_t); E rows -> X + global factor
+      const int ei = lane - NN - 1;
+      const bool e_wr = (ei >= 0) && (ei < NX) && has_G && (NX <= EX0);
+      const int last = (lane < NN) ? lane : NN - 1;
+      S* gdst = (lane < NN) ? (Lg + lane * NN) : (e_wr ? (Eg + ei * NN) : nullptr);
+      S* sdst = (lane == NN) ? (dv + t * NN) : (e_wr ? (X + ei * LB) : nullptr);
+      if (gdst) {
+        if constexpr (NN % 2 == 0) {  // rows are 16-byte aligned: 128-bit stores
 #pragma unroll
           for (int c = 0; c < NN; c += 2) {
             Vec2<S> v;
-            v.x = a[c];
-            v.y = a[c + 1];
-            *reinterpret_cast<Vec2<S>*>(Eg + i * NN + c) = v;
+            v.x = (c <= last) ? a[c] : S(0);
+            v.y = (c + 1 <= last) ? a[c + 1] : S(0);
+            *reinterpret_cast<Vec2<S>*>(gdst + c) = v;
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < NN; ++c) Eg[i * NN + c] = a[c];
+          for (int c = 0; c < NN; ++c) gdst[c] = (c <= last) ? a[c] : S(0);
         }
+      }
+      if (sdst) {
+#pragma unroll
+        for (int c = 0; c < NN; ++c) sdst[c] = a[c];
+      }
+      if (lane < NN && NX > EX0 && has_G) {  // publish L for the second elimination pass
+#pragma unroll
+        for (int c = 0; c < NN; ++c) scr[64 + lane * LD + c] = a[c];
       }
     }
     if (NX > EX0 && has_G) {  // sub-diagonal rows that did not fit (flying cartpole: nx=14, n=18)
