@@ -209,7 +209,11 @@ def solve_both(model, T, B, seed, dtype, al_iter=2):
 
 @pytest.mark.parametrize("model,T,B", [("rex_quadrotor", 5, 192), ("pendulum", 5, 200), ("cartpole1l", 5, 256),
                                        ("cartpole1l", 10, 64), ("pendulum", 20, 33), ("flying_cartpole", 10, 48),
-                                       ("rex_quadrotor", 10, 32), ("cartpole2l", 5, 40)])
+                                       ("rex_quadrotor", 10, 32), ("cartpole2l", 5, 40),
+                                       # every warp-synchronous line-search instantiation ((T-1) | 32) and ragged batches
+                                       ("pendulum", 2, 37), ("cartpole1l", 3, 45), ("cartpole2l", 9, 21),
+                                       ("pendulum", 17, 19), ("cartpole1l", 33, 5), ("rex_quadrotor", 9, 13),
+                                       ("flying_cartpole", 5, 31), ("rex_quadrotor", 3, 7), ("pendulum", 5, 1)])
 def test_cuda_matches_oracle_f64(model, T, B):
     r = solve_both(model, T, B, 4242 + T, torch.float64)
     assert r["c"]["steps"] == r["o"]["steps"]
