@@ -1504,22 +1504,100 @@ __global__ void __launch_bounds__(WPB * 32)
 k_backward(int B, int T, const S* __restrict__ fac_g, const S* __restrict__ xu_g, const S* __restrict__ grad_g,
            S* __restrict__ gQ_g, S* __restrict__ gq_g) {
   constexpr int NN = NX + NU;
+  constexpr int LB = NN | 1;  // odd row stride of the staged blocks: rows AND columns per lane are conflict free
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int prob = blockIdx.x * WPB + warp;
   if (prob >= B) return;
   const int N = T * NN;
-  S* sm = reinterpret_cast<S*>(smem_raw) + (size_t)warp * (N + NX * NN);
+  const int per_warp = ((N + 3) & ~3) + 2 * NN * LB + 2 * NX * LB;
+  S* sm = reinterpret_cast<S*>(smem_raw) + (size_t)warp * per_warp;
   S* dv = sm;
-  S* Etmp = sm + N;
+  S* Lb[2] = {sm + ((N + 3) & ~3), sm + ((N + 3) & ~3) + NN * LB};
+  S* Eb[2] = {Lb[1] + NN * LB, Lb[1] + NN * LB + NX * LB};
   const size_t pN = (size_t)prob * N;
-  for (int i = lane; i < N; i += 32) dv[i] = grad_g[pN + i];
-  __syncwarp();
   const S* fac = fac_g + (size_t)prob * factor_elems<NX, NU>(T);
-  forward_sweep_stored<NX, NU, S>(dv, Etmp, T, lane, fac);
-  backward_sweep<NX, NU, S>(dv, nullptr, Etmp, T, lane, fac);
+  const S* facE = fac + (size_t)T * NN * NN;
+  // both sweeps stream the factor through shared memory with cp.async, one stage ahead of the substitution
+  warp_copy_block_async<NN, NN, LB>(Lb[0], fac, lane);
+  cp_async_commit();
+  for (int i = lane; i < N; i += 32) dv[i] = grad_g[pN + i];
+  // ---- forward: y = L^{-1} grad   (row per lane; stage t needs L_tt and E_{t-1})
+  for (int t = 0; t < T; ++t) {
+    const int cur = t & 1, nxt = cur ^ 1;
+    cp_async_wait_all();
+    __syncwarp();
+    if (t + 1 < T) {
+      warp_copy_block_async<NN, NN, LB>(Lb[nxt], fac + (size_t)(t + 1) * NN * NN, lane);
+      warp_copy_block_async<NX, NN, LB>(Eb[nxt], facE + (size_t)t * NX * NN, lane);  // E_t, used by stage t+1
+    }
+    cp_async_commit();
+    if (t > 0 && lane < NX) {
+      const S* E = Eb[cur];
+      S s0 = S(0), s1 = S(0);
+#pragma unroll
+      for (int k = 0; k + 1 < NN; k += 2) {
+        s0 += E[lane * LB + k] * dv[(t - 1) * NN + k];
+        s1 += E[lane * LB + k + 1] * dv[(t - 1) * NN + k + 1];
+      }
+      if (NN & 1) s0 += E[lane * LB + NN - 1] * dv[(t - 1) * NN + NN - 1];
+      dv[t * NN + lane] -= s0 + s1;
+    }
+    __syncwarp();
+    S a[NN];
+    if (lane < NN) {
+#pragma unroll
+      for (int c = 0; c < NN; ++c) a[c] = Lb[cur][lane * LB + c];
+    }
+    S b = (lane < NN) ? dv[t * NN + lane] : S(0);
+#pragma unroll
+    for (int k = 0; k < NN; ++k) {
+      const S yk = __shfl_sync(FULL, b * a[k], k);  // lane k: a[k] = 1/L_kk
+      b = (lane == k) ? yk : ((lane > k) ? (b - a[k] * yk) : b);
+    }
+    if (lane < NN) dv[t * NN + lane] = b;
+  }
+  // ---- backward: gbar = -L^{-T} y   (column per lane; stage t needs L_tt and E_t)
+  // after the forward loop Lb[(T-1)&1] still holds L_{T-1}
+  int cur = (T - 1) & 1;
+  cp_async_wait_all();
+  __syncwarp();
+  for (int t = T - 1; t >= 0; --t) {
+    const int nxt = cur ^ 1;
+    if (t > 0) {
+      warp_copy_block_async<NN, NN, LB>(Lb[nxt], fac + (size_t)(t - 1) * NN * NN, lane);
+      warp_copy_block_async<NX, NN, LB>(Eb[nxt], facE + (size_t)(t - 1) * NX * NN, lane);  // E_{t-1}, used by stage t-1
+    }
+    cp_async_commit();
+    S l[NN];
+    if (lane < NN) {
+#pragma unroll
+      for (int r = 0; r < NN; ++r) l[r] = (r >= lane) ? Lb[cur][r * LB + lane] : S(0);
+    }
+    S b = (lane < NN) ? dv[t * NN + lane] : S(0);
+    if (t < T - 1 && lane < NN) {
+      const S* E = Eb[cur];  // E_t (staged one iteration ago)
+      S s0 = S(0), s1 = S(0);
+#pragma unroll
+      for (int i = 0; i + 1 < NX; i += 2) {
+        s0 += E[i * LB + lane] * dv[(t + 1) * NN + i];
+        s1 += E[(i + 1) * LB + lane] * dv[(t + 1) * NN + i + 1];
+      }
+      if (NX & 1) s0 += E[(NX - 1) * LB + lane] * dv[(t + 1) * NN + NX - 1];
+      b -= s0 + s1;
+    }
+#pragma unroll
+    for (int r = NN - 1; r >= 0; --r) {
+      const S dr = __shfl_sync(FULL, b * l[r], r);
+      b = (lane == r) ? dr : (b - l[r] * dr);
+    }
+    if (lane < NN) dv[t * NN + lane] = b;
+    cp_async_wait_all();
+    __syncwarp();
+    cur = nxt;
+  }
   for (int i = lane; i < N; i += 32) {
-    S g = -dv[i];
+    const S g = -dv[i];
     gq_g[pN + i] = g;
     if (gQ_g) gQ_g[pN + i] = g * xu_g[pN + i];
   }
@@ -1990,7 +2068,8 @@ static int backward_impl(const almpc_desc* d, const S* factor, const S* xu, cons
   if (d->B == 0) return 0;
   if (!factor || !xu || !grad_xu || !grad_q) return set_err(-10, "null buffer");
   constexpr int NN = NX + NU;
-  const size_t smem = (size_t)kWPB * (d->T * NN + NX * NN) * sizeof(S);
+  constexpr int LBb = NN | 1;
+  const size_t smem = (size_t)kWPB * (((d->T * NN + 3) & ~3) + 2 * NN * LBb + 2 * NX * LBb) * sizeof(S);
   auto kern = k_backward<NX, NU, S, kWPB>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
