@@ -85,6 +85,12 @@ def algorithmic_bytes(model, T, esize):
     return dict(fwd=fwd * esize, bwd=bwd * esize, newton_launch=(nx + 3 * N + m + 2 + N + factor + 2) * esize)
 
 
+# DRAM traffic per launch measured once with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum),
+# profiles/r01_v6_three_kernels_ncu_full_summary.csv — only valid for the exact workload it was captured on.
+NCU_TRAFFIC = {("rex_quadrotor", 5, 65536, "f64"): {"k_jacobian": 48.37e6 + 375.15e6, "k_factor_solve": 665.39e6 + 1075.69e6,
+                                                    "k_line_search": 228.87e6 + 31.84e6}}
+
+
 class ClockSampler:
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -426,7 +432,9 @@ def main():
             tf = kw[kn]["flops"] * B / (ms * 1e-3) / 1e12
             gb = kw[kn]["bytes"] * B / (ms * 1e-3) / 1e9
             kernels[kn] = {"avg_launch_ms": ms, "flops_per_problem": kw[kn]["flops"], "bytes_per_problem": kw[kn]["bytes"],
-                           "fma_tflops": tf, "fma_frac": tf / peak_tflops, "hbm_gbs": gb, "hbm_frac": gb / hbm_peak}
+                           "fma_tflops": tf, "fma_frac": tf / peak_tflops, "hbm_gbs": gb, "hbm_frac": gb / hbm_peak,
+                           "algorithmic_bytes_per_launch": kw[kn]["bytes"] * B,
+                           "traffic": NCU_TRAFFIC.get((model, T, B, args.dtype), {}).get(kn)}
         dom = max(kernel_ms, key=kernel_ms.get)
         dk = kernels[dom]
         dom_fma = dk["fma_frac"] >= dk["hbm_frac"]
@@ -451,7 +459,7 @@ def main():
                 "achieved": dk["fma_tflops"] if dom_fma else dk["hbm_gbs"],
                 "peak": peak_tflops if dom_fma else hbm_peak, "unit": "TFLOP/s" if dom_fma else "GB/s",
                 "frac": dk["fma_frac"] if dom_fma else dk["hbm_frac"], "avg_launch_ms": dk["avg_launch_ms"],
-                "traffic": None,
+                "traffic": dk["traffic"],
                 "peak_source": {"fma": "measured in this run by almpc_fma_peak (8 independent FMA chains/thread); MEASURED_PEAKS.json has no FP64/FP32 FMA figure",
                                 "hbm": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
                 "kernels": kernels,
