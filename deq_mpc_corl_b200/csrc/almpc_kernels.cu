@@ -303,12 +303,6 @@ __host__ __device__ inline size_t factor_elems(int T) {
   return (size_t)T * NN * NN + (size_t)(T - 1) * NX * NN;
 }
 
-// ------------------------------------------------------------------------------------------------
-// forward sweep: factor H (block tridiagonal) and solve L y = g.  On entry dv = g, G = Jacobians.
-// On exit dv = y, G slots hold E_t = H_{t+1,t} L_tt^{-T}, factor (global) holds L_tt and E_t.
-// BUILD=true  : build D_t from G, Qd, rho and the active set, factor, stream to `fac`
-// BUILD=false : (backward pass) read L_tt / E_t from `fac` and only do the substitution.
-// ------------------------------------------------------------------------------------------------
 // D(8x8) += A(8x4) B(4x8), FP64 tensor-core MMA (legacy mma.sync path; on B200 it runs at the DFMA rate
 // but replaces 8 DFMA + their shared-memory operand loads per lane by one instruction).
 // Fragment layout (PTX ISA, m8n8k4 .f64): g = lane>>2, q = lane&3:  a = A[g][q], b = B[q][g],
@@ -439,85 +433,6 @@ __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, 
       }
       scr[r * LD + c] = v;
     }
-  }
-}
-
-// forward substitution only, from a stored factor (backward pass): dv = L^{-1} dv
-template <int NX, int NU, typename S>
-__device__ __forceinline__ void forward_sweep_stored(S* dv, S* Esm, int T, int lane, const S* fac) {
-  constexpr int NN = NX + NU;
-  for (int t = 0; t < T; ++t) {
-    if (t > 0) {
-      // dv_t[r] -= sum_k E_{t-1}[r][k] y_{t-1}[k]
-      const S* Eg = fac + (size_t)T * NN * NN + (size_t)(t - 1) * NX * NN;
-      for (int idx = lane; idx < NX * NN; idx += 32) Esm[idx] = Eg[idx];
-      __syncwarp();
-      for (int r = lane; r < NX; r += 32) {
-        S s = S(0);
-#pragma unroll
-        for (int k = 0; k < NN; ++k) s += Esm[r * NN + k] * dv[(t - 1) * NN + k];
-        dv[t * NN + r] -= s;
-      }
-      __syncwarp();
-    }
-    // row-per-lane substitution: y_k = b_k * inv_k ; b_r -= L[r][k] y_k
-    S a[NN];
-    const S* Lg = fac + (size_t)t * NN * NN;
-    if (lane < NN) {
-#pragma unroll
-      for (int c = 0; c < NN; ++c) a[c] = Lg[lane * NN + c];
-    }
-    S b = (lane < NN) ? dv[t * NN + lane] : S(0);
-#pragma unroll
-    for (int k = 0; k < NN; ++k) {
-      S yk = __shfl_sync(FULL, b * a[k], k);  // lane k: a[k] = 1/L_kk
-      if (lane == k) b = yk;
-      else if (lane > k) b -= a[k] * yk;
-    }
-    if (lane < NN) dv[t * NN + lane] = b;
-    __syncwarp();
-  }
-}
-
-// backward sweep: dv = L^{-T} dv, with L_tt read from global (column per lane) and E_t either from
-// shared memory (Esm_all != nullptr: all blocks resident, forward solve) or from global.
-template <int NX, int NU, typename S>
-__device__ __forceinline__ void backward_sweep(S* dv, const S* Esm_all, S* Etmp, int T, int lane,
-                                               const S* fac) {  // NOT restrict/nc: written earlier by this warp
-  constexpr int NN = NX + NU;
-  for (int t = T - 1; t >= 0; --t) {
-    S l[NN];
-    const S* Lg = fac + (size_t)t * NN * NN;
-    if (lane < NN) {
-#pragma unroll
-      for (int r = 0; r < NN; ++r) l[r] = (r >= lane) ? Lg[r * NN + lane] : S(0);
-    }
-    S b = (lane < NN) ? dv[t * NN + lane] : S(0);
-    if (t < T - 1) {
-      const S* Et;
-      if (Esm_all) {
-        Et = Esm_all + (size_t)t * NX * NN;
-      } else {
-        const S* Eg = fac + (size_t)T * NN * NN + (size_t)t * NX * NN;
-        for (int idx = lane; idx < NX * NN; idx += 32) Etmp[idx] = Eg[idx];
-        __syncwarp();
-        Et = Etmp;
-      }
-      if (lane < NN) {
-        S s = S(0);
-#pragma unroll
-        for (int i = 0; i < NX; ++i) s += Et[i * NN + lane] * dv[(t + 1) * NN + i];
-        b -= s;
-      }
-    }
-#pragma unroll
-    for (int r = NN - 1; r >= 0; --r) {
-      S dr = __shfl_sync(FULL, b * l[r], r);  // lane r: l[r] = 1/L_rr
-      if (lane == r) b = dr;
-      else if (lane < r) b -= l[r] * dr;
-    }
-    if (lane < NN) dv[t * NN + lane] = b;
-    __syncwarp();
   }
 }
 
