@@ -828,8 +828,11 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
     S* tmp = Ecur; Ecur = Enext; Enext = tmp;
   }
   __syncwarp();
+  // A non-positive pivot (never seen in fp64; routine in fp32 once rho/R exceeds ~1e10) leaves no
+  // usable direction: the step is skipped (d = 0 keeps the iterate) and the problem is flagged, instead of the
+  // backend-specific garbage direction the reference would push through its line search.
   for (int i = lane; i < L.N; i += 32) {
-    const S d = -dv[i];
+    const S d = ok ? -dv[i] : S(0);
     d_g[pN + i] = d;
     if (dbg) dbg[L.N + i] = d;
   }
@@ -1511,8 +1514,12 @@ k_backward(int B, int T, const S* __restrict__ fac_g, const S* __restrict__ xu_g
     __syncwarp();
     cur = nxt;
   }
+  // a factor with non-positive pivots (flagged in the forward status) yields no gradient instead of NaNs
+  bool fin = true;
+  for (int i = lane; i < N; i += 32) fin = fin && finite_(dv[i]);
+  fin = __all_sync(FULL, fin);
   for (int i = lane; i < N; i += 32) {
-    const S g = -dv[i];
+    const S g = fin ? -dv[i] : S(0);
     gq_g[pN + i] = g;
     if (gQ_g) gQ_g[pN + i] = g * xu_g[pN + i];
   }
