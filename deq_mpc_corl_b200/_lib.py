@@ -47,6 +47,7 @@ class Desc(ctypes.Structure):
 
 
 FLAG_SKIP_FINAL_DUAL = 1
+FLAG_STATE_ESTIMATOR = 2
 
 _lib = None
 

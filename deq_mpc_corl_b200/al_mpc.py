@@ -39,8 +39,8 @@ class MPC(Module):
         assert max_linesearch_iter > 0
         if u_lower is None:
             raise _lib.AlmpcError("MPC needs control bounds (the reference dereferences them unconditionally, AL_mpc.py:152)")
-        if state_estimator or add_goal_constraint or ineqG is not None or not diag_cost:
-            raise _lib.AlmpcError("state_estimator / goal constraint / ineqG / dense cost are outside the fused AL-MPC path")
+        if add_goal_constraint or ineqG is not None or not diag_cost:
+            raise _lib.AlmpcError("goal constraint / ineqG / dense cost are outside the fused AL-MPC path")
         self.dtype = dtype
         self.n_state, self.n_ctrl, self.T = n_state, n_ctrl, T
         self.u_lower = _detach_maybe(torch.as_tensor(u_lower).to(dtype))
@@ -57,8 +57,10 @@ class MPC(Module):
         self.slew_rate_penalty, self.solver_type = slew_rate_penalty, solver_type
         self.state_estimator, self.diag_cost = state_estimator, diag_cost
         self.al_iter = al_iter
-        self.neq = n_state * T
-        self.nineq = 2 * n_ctrl * T
+        # state_estimator=True (AL_mpc.py:186-199; merit / Hessian of qpth/al_utils_se.py): the T-1 dynamics blocks
+        # only, no control bounds — the controls are data and only the states are estimated
+        self.neq = n_state * (T - 1) if state_estimator else n_state * T
+        self.nineq = 0 if state_estimator else 2 * n_ctrl * T
         self.rho_prev = 1.0
         self.rho_max = 1e8
         self.max_newton_steps = 4
@@ -122,7 +124,7 @@ class MPC(Module):
             dyn=dyn, T=self.T, u_lower=self._bounds_host[0], u_upper=self._bounds_host[1], al_iter=int(self.al_iter),
             max_newton=self.max_newton_steps, stream_mode=bool(self.warm_starting),
             rho_f32=(rho_dtype == torch.float32 and self.dtype == torch.float64), rho_max=self.rho_max,
-            **self._extra_constraints(dev))
+            state_estimator=bool(self.state_estimator), **self._extra_constraints(dev))
         xu0 = torch.cat([x.to(self.dtype), u.to(self.dtype)], dim=2)
         xo, uo, xu, lam_new, rho_new, dyn_res, status, info, _ = ALSolve.apply(
             Qd, q, x0.to(self.dtype), xu0, lam.to(dev).to(self.dtype), rho.to(dev).to(self.dtype).reshape(-1), cfg)
@@ -196,6 +198,8 @@ class Obstacle_MPC(MPC):
 
     def __init__(self, n_state, n_ctrl, T, *args, env=None, **kwargs):
         super().__init__(n_state, n_ctrl, T, *args, **kwargs)
+        if self.state_estimator:
+            raise _lib.AlmpcError("Obstacle_MPC has no state-estimator variant")
         self.n_obstacle_constraints = 4
         self.nineq += self.n_obstacle_constraints * T
         # the reference turns the radius into a default-dtype (fp32) tensor first (AL_mpc_custom.py:60)

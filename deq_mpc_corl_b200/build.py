@@ -28,7 +28,8 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Two translation units (fp64 / fp32 entry points) compiled in parallel, then linked."""
+    """Four translation units ((fp64 | fp32) x (entry points | state-estimator variant)) compiled in parallel,
+    then linked."""
     if not force and not needs_build():
         return OUT
     import concurrent.futures
@@ -39,7 +40,9 @@ def build(force=False, verbose=False):
         common += ["-Xptxas", "-v"]
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    units = [("f64", ["-DALMPC_BUILD_F64=1", "-DALMPC_BUILD_F32=0"]), ("f32", ["-DALMPC_BUILD_F64=0", "-DALMPC_BUILD_F32=1"])]
+    units = [("f64", ["-DALMPC_BUILD_F64=1", "-DALMPC_BUILD_F32=0"]), ("f32", ["-DALMPC_BUILD_F64=0", "-DALMPC_BUILD_F32=1"]),
+             ("f64_se", ["-DALMPC_BUILD_F64=1", "-DALMPC_BUILD_F32=0", "-DALMPC_BUILD_SE=1"]),
+             ("f32_se", ["-DALMPC_BUILD_F64=0", "-DALMPC_BUILD_F32=1", "-DALMPC_BUILD_SE=1"])]
 
     def compile_unit(u):
         name, defs = u
@@ -50,7 +53,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
         return obj, res.stderr
 
-    with concurrent.futures.ThreadPoolExecutor(max_workers=2) as ex:
+    with concurrent.futures.ThreadPoolExecutor(max_workers=4) as ex:
         results = list(ex.map(compile_unit, units))
     if verbose:
         for _, err in results:

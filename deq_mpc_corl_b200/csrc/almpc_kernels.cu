@@ -34,13 +34,17 @@
 #include "almpc.h"
 #include "almpc_models.cuh"
 
-// The library is compiled as two translation units (fp64 / fp32 entry points) built in parallel; the common
-// entry points live in the fp64 unit.
+// The library is compiled as four translation units built in parallel: (fp64 | fp32) x (entry points with the
+// plain / obstacle variants | the state-estimator variant, ALMPC_BUILD_SE=1); the common entry points live in
+// the fp64 unit.
 #ifndef ALMPC_BUILD_F64
 #define ALMPC_BUILD_F64 1
 #endif
 #ifndef ALMPC_BUILD_F32
 #define ALMPC_BUILD_F32 1
+#endif
+#ifndef ALMPC_BUILD_SE
+#define ALMPC_BUILD_SE 0
 #endif
 #ifndef ALMPC_NO_VEC2
 #define ALMPC_NO_VEC2 0
@@ -190,9 +194,11 @@ struct Layout {
   static constexpr int NN = NX + NU;
   int N, neq, nin, m, SI;
   int xu, dv, w, Gt, Ep, scr, total;
-  __host__ __device__ Layout(int T, int nobs = 0) {
-    SI = 2 * NU + nobs;  // inequality rows per stage: control bounds, then obstacle rows
-    N = T * NN; neq = T * NX; nin = T * SI; m = neq + nin;
+  __host__ __device__ Layout(int T, int nobs = 0, bool se = false) {
+    // inequality rows per stage: control bounds, then obstacle rows.  State-estimator variant
+    // (al_utils_se.py): the T-1 dynamics blocks only
+    SI = se ? 0 : 2 * NU + nobs;
+    N = T * NN; neq = se ? (T - 1) * NX : T * NX; nin = T * SI; m = neq + nin;
     int o = 0;
     auto take = [&](int cnt) { int at = o; o += (cnt + 3) & ~3; return at; };  // regions 16-byte aligned for float and double
     xu = take(N);
@@ -212,9 +218,9 @@ struct LsLayout {
   static constexpr int LS = NN | 1;  // odd stage stride: lanes working on different stages hit different banks
   int N, neq, nin, m, SI;
   int xu, d, lam, Qd, q, x0, obs, part, total;
-  __host__ __device__ LsLayout(int T, int nobs = 0) {
-    SI = 2 * NU + nobs;
-    N = T * NN; neq = T * NX; nin = T * SI; m = neq + nin;
+  __host__ __device__ LsLayout(int T, int nobs = 0, bool se = false) {
+    SI = se ? 0 : 2 * NU + nobs;
+    N = T * NN; neq = se ? (T - 1) * NX : T * NX; nin = T * SI; m = neq + nin;
     int o = 0;
     auto take = [&](int cnt) { int at = o; o += (cnt + 3) & ~3; return at; };  // regions 16-byte aligned for float and double
     xu = take(T * LS);
@@ -321,7 +327,8 @@ struct ScrLd {
 // D_t = diag(Qd_t) + rho (G_t^T G_t + I_x + active bounds) - E_{t-1} E_{t-1}^T   (lower tiles) -> scr
 template <int NX, int NU, typename S>
 __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, const S* Ep, bool has_G, bool has_E,
-                                            int lane, S rho, const S* __restrict__ Qd_t, const S* ulo, const S* uhi) {
+                                            int lane, S rho, const S* __restrict__ Qd_t, const S* ulo, const S* uhi,
+                                            bool add_ix = true, bool bounds = true) {
   constexpr int NN = NX + NU;
   constexpr int LD = ScrLd<NN>::LD;
   constexpr int LB = NN | 1;  // row stride of the staged G / E blocks
@@ -381,8 +388,8 @@ __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, 
           double v = acc[rt][ct][e];
           if (r == c) {
             if (r < NX) {
-              v += 1.0;
-            } else if (r < NN) {
+              if (add_ix) v += 1.0;
+            } else if (r < NN && bounds) {
               const double u = xu_t[r];
               v += ((u - uhi[r - NX]) >= 0.0 ? 1.0 : 0.0) + ((ulo[r - NX] - u) >= 0.0 ? 1.0 : 0.0);
             }
@@ -413,8 +420,8 @@ __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, 
       S v = v0 + v1;
       if (r == c) {
         if (r < NX) {
-          v += S(1);
-        } else {
+          if (add_ix) v += S(1);
+        } else if (bounds) {
           const S u = xu_t[r];
           v += ((u - uhi[r - NX]) >= S(0) ? S(1) : S(0)) + ((ulo[r - NX] - u) >= S(0) ? S(1) : S(0));
         }
@@ -440,7 +447,7 @@ __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, 
 // kernel 1/3: dynamics + Jacobian columns.  1 thread = 1 (problem, stage t, column j of G_t = [A_t B_t]).
 //   G_g[prob][t][i][j] = d f_i / d z_j at (x_t,u_t) ; c_g[prob][t*nx+i] = x_{t+1,i} - f_i ; last block: x_0 - x0
 // ------------------------------------------------------------------------------------------------
-template <class M, typename S>
+template <class M, typename S, int V>
 __global__ void __launch_bounds__(128)
 k_jacobian(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__ xu_g, S* __restrict__ G_g,
            S* __restrict__ c_g, const Ctl* __restrict__ ctl) {
@@ -457,6 +464,14 @@ k_jacobian(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__
   const int it = (int)(gid - (long)prob * IT);
   const int t = it / NC, jj = it - t * NC, j = jj + NTRIV;
   const S* xz = xu_g + (size_t)prob * T * NN + (size_t)t * NN;
+  constexpr bool SE = (V == 2);
+  const int neq = SE ? (T - 1) * NX : T * NX;
+  if (SE && j >= NX) {  // controls are data: their Jacobian columns are zero (al_utils_se.py:153)
+    S* Gz = G_g + ((size_t)prob * (T - 1) + t) * NX * NN;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) Gz[i * NN + j] = S(0);
+    return;
+  }
   Dual<S> xd[NX], ud[NU], xn[NX];
 #pragma unroll
   for (int i = 0; i < NX; ++i) xd[i] = Dual<S>(xz[i], (i == j) ? S(1) : S(0));
@@ -466,7 +481,7 @@ k_jacobian(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__
   S* Gp = G_g + ((size_t)prob * (T - 1) + t) * NX * NN;
 #pragma unroll
   for (int i = 0; i < NX; ++i) Gp[i * NN + j] = xn[i].d;
-  S* cp = c_g + (size_t)prob * T * NX;
+  S* cp = c_g + (size_t)prob * neq;
   if (jj == 0) {
 #pragma unroll
     for (int i = 0; i < NX; ++i) cp[t * NX + i] = xz[NN + i] - xn[i].v;
@@ -475,7 +490,7 @@ k_jacobian(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__
 #pragma unroll
       for (int c = 0; c < NTRIV; ++c) Gp[i * NN + c] = (i == c) ? S(1) : S(0);
   }
-  if (it == IT - 1) {  // the x_0 - x0 block (al_utils.py:219)
+  if (!SE && it == IT - 1) {  // the x_0 - x0 block (al_utils.py:219)
     const S* z0 = xu_g + (size_t)prob * T * NN;
 #pragma unroll
     for (int i = 0; i < NX; ++i) cp[(T - 1) * NX + i] = z0[i] - x0_g[(size_t)prob * NX + i];
@@ -486,7 +501,7 @@ k_jacobian(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__
 // kernel 2/3: residual statistics, dual update, merit, gradient, block-tridiagonal factor + solve.
 // 1 warp = 1 problem.
 // ------------------------------------------------------------------------------------------------
-template <int NX, int NU, typename S, int WPB, bool OBS>
+template <int NX, int NU, typename S, int WPB, int V>
 __global__ void __launch_bounds__(WPB * 32, ALMPC_FAC_MINB)
 k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restrict__ q_g, const S* __restrict__ xu_g,
                S* __restrict__ lam_g, S* __restrict__ rho_g, S* fac_g, const S* __restrict__ G_g,
@@ -497,13 +512,14 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
   constexpr int EX0 = 32 - NN - 1;  // sub-diagonal rows that fit next to the L rows and the rhs row
   constexpr int CW = CopyWidth<NX, NU, S>::W;
   constexpr int LB = NN | 1;  // odd row stride of the staged G / E blocks (bank-conflict free rows)
+  constexpr bool OBS = (V == 1), SE = (V == 2);  // variant: 0 plain, 1 obstacle rows, 2 state estimator
   extern __shared__ __align__(16) unsigned char smem_raw[];
   grid_dep_wait();
   const int mode = ctl->mode;
   if (mode == MODE_DONE) return;
   const int T = P.T;
   const int n_obs = OBS ? P.n_obs : 0;
-  const Layout<NX, NU> L(T, n_obs);
+  const Layout<NX, NU> L(T, n_obs, SE);
   const int SI = OBS ? L.SI : 2 * NU;  // compile-time constant without obstacle rows
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int prob = blockIdx.x * WPB + warp;
@@ -605,8 +621,10 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
         const int i = base + lane + 32 * u;
         if (i < L.N) {
           const S z = xu[i];
-          cost += S(0.5) * (z * Qv[u] * z) + qq[u] * z;
-          dv[i] = Qv[u] * z + qq[u];  // cost gradient (al_utils.py:438-446), completed per stage below
+          // state estimator: cost and cost gradient see the states only (al_utils_se.py:272-305)
+          const bool in_cost = !SE || (i % NN) < NX;
+          if (in_cost) cost += S(0.5) * (z * Qv[u] * z) + qq[u] * z;
+          dv[i] = in_cost ? Qv[u] * z + qq[u] : S(0);  // cost gradient (al_utils.py:438-446), completed per stage below
         }
       }
     }
@@ -662,8 +680,9 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
         g -= s0 + s1;
       }
       if (j < NX) {
-        g += has_E ? wv[(t - 1) * NX + j] : wv[(T - 1) * NX + j];
-      } else {
+        if (has_E) g += wv[(t - 1) * NX + j];
+        else if (!SE) g += wv[(T - 1) * NX + j];  // the x_0 - x0 block
+      } else if (!SE) {
         const int sidx = j - NX;
         const S u = xu[idx];
         const S cu = u - P.uhi[sidx], cl = P.ulo[sidx] - u;
@@ -687,7 +706,8 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
       }
       dv[idx] = g;
     }
-    build_block<NX, NU, S>(scr + 64, xu + t * NN, X, Y, has_G, has_E, lane, rho, Qd + t * NN, P.ulo, P.uhi);
+    build_block<NX, NU, S>(scr + 64, xu + t * NN, X, Y, has_G, has_E, lane, rho, Qd + t * NN, P.ulo, P.uhi,
+                           !SE || has_E, !SE);
     __syncwarp();
     if constexpr (OBS) {  // + rho sum_k active J_k^T J_k on the position block (lower part)
       if (lane < 6) {
@@ -902,7 +922,7 @@ __device__ __forceinline__ void steer_solve(const KParams<S>& P, Ctl* ctl, int* 
 // One line-search item: candidate alpha = 2^-kk, stage t.  Evaluates the stage's share of the merit
 // (al_utils.py:52-77): cost, sum c+^2 and lam.c of the dynamics residual x_{t+1} - f(x_t,u_t), the control
 // bounds of stage t (and of the last stage for t = T-2) and the initial-state residual (t = 0).
-template <class M, typename S, bool OBS>
+template <class M, typename S, int V>
 __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU>& L, const KParams<S>& P, int T,
                                         int kk, int t, S& cost, S& s2, S& sl) {
   constexpr int NX = M::NX, NU = M::NU, NN = NX + NU, LS = NN | 1;
@@ -912,6 +932,7 @@ __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU
   const S* Qd = sp + L.Qd;
   const S* qv = sp + L.q;
   const S* x0 = sp + L.x0;
+  constexpr bool OBS = (V == 1), SE = (V == 2);
   const int n_obs = OBS ? P.n_obs : 0;
   const int SI = OBS ? L.SI : 2 * NU;
     const S alpha = (S)ldexpf(1.0f, -kk);
@@ -927,13 +948,15 @@ __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU
     for (int i = 0; i < NU; ++i) {
       const S z = xu[t * LS + NX + i] + alpha * dv[t * LS + NX + i];
       us[i] = z;
-      cost += S(0.5) * (z * Qd[t * LS + NX + i] * z) + qv[t * LS + NX + i] * z;
-      const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
-      sl += lam[L.neq + t * SI + i] * cu + lam[L.neq + t * SI + NU + i] * cl;
-      const S pu = fmax0(cu), pl = fmax0(cl);
-      s2 += pu * pu + pl * pl;
+      if (!SE) {
+        cost += S(0.5) * (z * Qd[t * LS + NX + i] * z) + qv[t * LS + NX + i] * z;
+        const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
+        sl += lam[L.neq + t * SI + i] * cu + lam[L.neq + t * SI + NU + i] * cl;
+        const S pu = fmax0(cu), pl = fmax0(cl);
+        s2 += pu * pu + pl * pl;
+      }
     }
-    if (t == 0) {
+    if (!SE && t == 0) {
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         const S ci = xs[i] - x0[i];
@@ -961,7 +984,7 @@ __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU
       if (OBS && i < 3) zlast[i] = z1;
       if (t == T - 2) cost += S(0.5) * (z1 * Qd[(t + 1) * LS + i] * z1) + qv[(t + 1) * LS + i] * z1;
     }
-    if (t == T - 2) {
+    if (!SE && t == T - 2) {
 #pragma unroll
       for (int i = 0; i < NU; ++i) {
         const int e = (T - 1) * LS + NX + i;
@@ -1022,7 +1045,7 @@ __device__ __forceinline__ void ls_stage_async(S* sp, const LsLayout<NX, NU>& L,
   if (obs_g) copy(sp + L.obs, obs_g + (size_t)prob * (L.nin / L.SI) * (L.SI - 2 * NU) * 3, (L.nin / L.SI) * (L.SI - 2 * NU) * 3);
 }
 
-template <class M, typename S, bool OBS>
+template <class M, typename S, int V>
 __global__ void __launch_bounds__(256, 2)
 k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, const S* __restrict__ Qd_g,
               const S* __restrict__ q_g, S* xu_g, const S* __restrict__ lam_g,
@@ -1038,7 +1061,8 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
   if (mode == MODE_DONE) return;
   const int al_a = ctl->a, nk = ctl->k;
   const int T = P.T;
-  const LsLayout<NX, NU> L(T, OBS ? P.n_obs : 0);
+  constexpr bool OBS = (V == 1), SE = (V == 2);
+  const LsLayout<NX, NU> L(T, OBS ? P.n_obs : 0, SE);
   const int IT = NLS * (T - 1);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -1079,7 +1103,7 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
     S* part = const_cast<S*>(sp) + L.part;
     const int kk = it / (T - 1), t = it - kk * (T - 1);
     S cost, s2, sl;
-    ls_item<M, S, OBS>(sp, L, P, T, kk, t, cost, s2, sl);
+    ls_item<M, S, V>(sp, L, P, T, kk, t, cost, s2, sl);
     part[it * 3 + 0] = cost;
     part[it * 3 + 1] = s2;
     part[it * 3 + 2] = sl;
@@ -1188,7 +1212,7 @@ k_line_search(const KParams<S> P, const int pls, const S* __restrict__ x0_g, con
 // rounds, no idle lanes); the T-1 stage items of a candidate sit in adjacent lanes, so candidate totals are
 // segmented shuffle reductions and there is no CTA barrier and no partial-sum traffic in the loop.
 // ------------------------------------------------------------------------------------------------
-template <class M, typename S, int TM1, int WPB, bool OBS>
+template <class M, typename S, int TM1, int WPB, int V>
 __global__ void __launch_bounds__(WPB * 32, ALMPC_LS_MINB)
 k_line_search_warp(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__ Qd_g,
                    const S* __restrict__ q_g, S* xu_g, const S* __restrict__ lam_g, const S* __restrict__ rho_g,
@@ -1208,7 +1232,8 @@ k_line_search_warp(const KParams<S> P, const S* __restrict__ x0_g, const S* __re
   if (mode == MODE_DONE) return;
   const int al_a = ctl->a, nk = ctl->k;
   constexpr int T = TM1 + 1;
-  const LsLayout<NX, NU> L(T, OBS ? P.n_obs : 0);
+  constexpr bool OBS = (V == 1), SE = (V == 2);
+  const LsLayout<NX, NU> L(T, OBS ? P.n_obs : 0, SE);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int stride = L.part;  // staged scalars per problem (the partial-sum area of the CTA variant is unused)
@@ -1251,7 +1276,7 @@ k_line_search_warp(const KParams<S> P, const S* __restrict__ x0_g, const S* __re
       const int kk = it / TM1, t = it - kk * TM1;
       const bool valid = prob0 + p < P.B;
       S cost = S(0), s2 = S(0), sl = S(0);
-      if (valid) ls_item<M, S, OBS>(wsm + (size_t)p * stride, L, P, T, kk, t, cost, s2, sl);
+      if (valid) ls_item<M, S, V>(wsm + (size_t)p * stride, L, P, T, kk, t, cost, s2, sl);
       // candidate totals: the TM1 stage items of a candidate are adjacent lanes; fixed summation order t=0..TM1-1
       S c_tot = S(0), s_tot = S(0), l_tot = S(0);
 #pragma unroll
@@ -1342,7 +1367,7 @@ k_line_search_warp(const KParams<S> P, const S* __restrict__ x0_g, const S* __re
 // final dual update + outputs (always runs once at the end of a forward solve)
 //   lam <- lam + rho c(xu), clamp ; rho <- 10 rho ; dyn_res = ||c+|| ; x,u -> fp32     AL_mpc.py:315-338
 // ------------------------------------------------------------------------------------------------
-template <class M, typename S, int WPB, bool OBS>
+template <class M, typename S, int WPB, int V>
 __global__ void __launch_bounds__(WPB * 32)
 k_final_dual(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__ xu_g, S* __restrict__ lam_g,
              S* __restrict__ rho_g, float* __restrict__ x_out, float* __restrict__ u_out, S* __restrict__ dyn_res_g,
@@ -1350,8 +1375,9 @@ k_final_dual(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict
   constexpr int NX = M::NX, NU = M::NU, NN = NX + NU;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = P.T;
+  constexpr bool OBS = (V == 1), SE = (V == 2);
   const int n_obs = OBS ? P.n_obs : 0;
-  const Layout<NX, NU> L(T, n_obs);
+  const Layout<NX, NU> L(T, n_obs, SE);
   const int SI = OBS ? L.SI : 2 * NU;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int prob = blockIdx.x * WPB + warp;
@@ -1376,7 +1402,8 @@ k_final_dual(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict
 #pragma unroll
     for (int i = 0; i < NX; ++i) cres[t * NX + i] = xu[(t + 1) * NN + i] - xn[i];
   }
-  for (int i = lane; i < NX; i += 32) cres[(T - 1) * NX + i] = xu[i] - x0_g[(size_t)prob * NX + i];
+  if (!SE)
+    for (int i = lane; i < NX; i += 32) cres[(T - 1) * NX + i] = xu[i] - x0_g[(size_t)prob * NX + i];
   __syncwarp();
   const S rho = rho_g[prob];
   S* lamp = lam_g + (size_t)prob * L.m;
@@ -1629,7 +1656,7 @@ __global__ void k_fma_peak(int iters, S* sink) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-#if ALMPC_BUILD_F64
+#if ALMPC_BUILD_F64 && !ALMPC_BUILD_SE
 thread_local char g_err[512] = "";
 #else
 extern thread_local char g_err[512];
@@ -1676,7 +1703,7 @@ constexpr int kMaxParts = 4;
 
 // optional per-kernel timing (bench.py): events around every launch of one forward call
 // (shared by the two translation units: defined in the fp64 unit)
-#if ALMPC_BUILD_F64
+#if ALMPC_BUILD_F64 && !ALMPC_BUILD_SE
 int g_profile_on = 0;
 double g_profile[8] = {0};  // ms: [0] jacobian [1] factor_solve [2] line_search [3] final_dual, [4..7] launch counts
 #else
@@ -1744,11 +1771,11 @@ constexpr int kWLS = 4;  // warps per CTA of the warp-synchronous line search
 
 struct LsWarpCfg { const void* fn; int grid_cap; size_t smem; int pw; };
 
-template <class M, typename S, int TM1, bool OBS>
+template <class M, typename S, int TM1, int V>
 static cudaError_t ls_warp_cfg(LsWarpCfg& c, int n_sm, int n_obs) {
   constexpr int PW = (8 / TM1) > 0 ? (8 / TM1) : 1;
-  const LsLayout<M::NX, M::NU> LL(TM1 + 1, n_obs);
-  auto k = k_line_search_warp<M, S, TM1, kWLS, OBS>;
+  const LsLayout<M::NX, M::NU> LL(TM1 + 1, n_obs, V == 2);
+  auto k = k_line_search_warp<M, S, TM1, kWLS, V>;
   size_t smem = (size_t)kWLS * PW * LL.part * sizeof(S);
   if (smem < (size_t)kWLS * 32 * 3 * sizeof(double)) smem = (size_t)kWLS * 32 * 3 * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1763,7 +1790,7 @@ static cudaError_t ls_warp_cfg(LsWarpCfg& c, int n_sm, int n_obs) {
   return cudaSuccess;
 }
 
-template <class M, typename S, bool OBS>
+template <class M, typename S, int V>
 static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* q, S* xu, S* lam, S* rho, S* factor,
                         float* x_out, float* u_out, S* dyn_res_out, int32_t* status_out, int32_t* info_out,
                         S* debug_out, void* workspace, cudaStream_t st) {
@@ -1772,9 +1799,10 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   if (!x0 || !Qd || !q || !xu || !lam || !rho || !factor || !info_out || !workspace)
     return set_err(-10, "null buffer");
   const int T = d->T, B = d->B;
+  constexpr bool OBS = (V == 1), SE = (V == 2);
   const int n_obs = OBS ? d->n_obs : 0;
-  const Layout<NX, NU> L(T, n_obs);
-  const LsLayout<NX, NU> LL(T, n_obs);
+  const Layout<NX, NU> L(T, n_obs, SE);
+  const LsLayout<NX, NU> LL(T, n_obs, SE);
   const LsGeom lg = ls_geom(B, T);
   size_t smem_fac = (size_t)kWPB * L.total * sizeof(S);
   if (const char* pad = getenv("ALMPC_FAC_SMEM_PAD")) smem_fac += (size_t)atoi(pad);  // occupancy experiments
@@ -1783,10 +1811,10 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   const size_t smem_fin = (size_t)kWPB * (L.N + L.neq) * sizeof(S);
   if (smem_fac + 1024 > 227 * 1024 || smem_ls + 1024 > 227 * 1024)
     return set_err(-11, "horizon too long for the shared-memory layout");
-  auto kjac = k_jacobian<M, S>;
-  auto kfac = k_factor_solve<NX, NU, S, kWPB, OBS>;
-  auto kls = k_line_search<M, S, OBS>;
-  auto kfin = k_final_dual<M, S, kWPB, OBS>;
+  auto kjac = k_jacobian<M, S, V>;
+  auto kfac = k_factor_solve<NX, NU, S, kWPB, V>;
+  auto kls = k_line_search<M, S, V>;
+  auto kfin = k_final_dual<M, S, kWPB, V>;
   cudaError_t e;
   e = cudaFuncSetAttribute(kfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fac);
   if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(factor_solve)");
@@ -1808,12 +1836,12 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   LsWarpCfg lw{nullptr, 0, 0, 1};
   if (!getenv("ALMPC_LS_CTA")) {
     switch (T - 1) {
-      case 1: e = ls_warp_cfg<M, S, 1, OBS>(lw, n_sm, n_obs); break;
-      case 2: e = ls_warp_cfg<M, S, 2, OBS>(lw, n_sm, n_obs); break;
-      case 4: e = ls_warp_cfg<M, S, 4, OBS>(lw, n_sm, n_obs); break;
-      case 8: e = ls_warp_cfg<M, S, 8, OBS>(lw, n_sm, n_obs); break;
-      case 16: e = ls_warp_cfg<M, S, 16, OBS>(lw, n_sm, n_obs); break;
-      case 32: e = ls_warp_cfg<M, S, 32, OBS>(lw, n_sm, n_obs); break;
+      case 1: e = ls_warp_cfg<M, S, 1, V>(lw, n_sm, n_obs); break;
+      case 2: e = ls_warp_cfg<M, S, 2, V>(lw, n_sm, n_obs); break;
+      case 4: e = ls_warp_cfg<M, S, 4, V>(lw, n_sm, n_obs); break;
+      case 8: e = ls_warp_cfg<M, S, 8, V>(lw, n_sm, n_obs); break;
+      case 16: e = ls_warp_cfg<M, S, 16, V>(lw, n_sm, n_obs); break;
+      case 32: e = ls_warp_cfg<M, S, 32, V>(lw, n_sm, n_obs); break;
       default: break;
     }
     if (e != cudaSuccess) return cuda_err(e, "line-search (warp) configuration");
@@ -2024,6 +2052,32 @@ static int dynamics_impl(const almpc_desc* d, int64_t R, const S* x, const S* u,
     default: return set_err(-2, "unknown dyn_id");                      \
   }
 
+// state-estimator variant: instantiated in its own translation units (ALMPC_BUILD_SE=1)
+int forward_se_f64(const almpc_desc* d, const double* x0, const double* Qd, const double* q, double* xu, double* lam,
+                   double* rho, double* factor, float* x_out, float* u_out, double* dyn_res_out, int32_t* status_out,
+                   int32_t* info_out, double* debug_out, void* workspace, cudaStream_t st);
+int forward_se_f32(const almpc_desc* d, const float* x0, const float* Qd, const float* q, float* xu, float* lam,
+                   float* rho, float* factor, float* x_out, float* u_out, float* dyn_res_out, int32_t* status_out,
+                   int32_t* info_out, float* debug_out, void* workspace, cudaStream_t st);
+#if ALMPC_BUILD_SE
+#if ALMPC_BUILD_F64
+int forward_se_f64(const almpc_desc* d, const double* x0, const double* Qd, const double* q, double* xu, double* lam,
+                   double* rho, double* factor, float* x_out, float* u_out, double* dyn_res_out, int32_t* status_out,
+                   int32_t* info_out, double* debug_out, void* workspace, cudaStream_t st) {
+  ALMPC_DISPATCH(d->dyn_id, (forward_impl<M, double, 2>(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out,
+                                                        status_out, info_out, debug_out, workspace, st)))
+}
+#endif
+#if ALMPC_BUILD_F32
+int forward_se_f32(const almpc_desc* d, const float* x0, const float* Qd, const float* q, float* xu, float* lam,
+                   float* rho, float* factor, float* x_out, float* u_out, float* dyn_res_out, int32_t* status_out,
+                   int32_t* info_out, float* debug_out, void* workspace, cudaStream_t st) {
+  ALMPC_DISPATCH(d->dyn_id, (forward_impl<M, float, 2>(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out,
+                                                       status_out, info_out, debug_out, workspace, st)))
+}
+#endif
+#else  // !ALMPC_BUILD_SE
+
 template <typename S>
 static int forward_any(const almpc_desc* d, const S* x0, const S* Qd, const S* q, S* xu, S* lam, S* rho, S* factor,
                        float* x_out, float* u_out, S* dyn_res_out, int32_t* status_out, int32_t* info_out,
@@ -2031,15 +2085,24 @@ static int forward_any(const almpc_desc* d, const S* x0, const S* Qd, const S* q
   int rc = check_desc(d);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (d->flags & ALMPC_FLAG_STATE_ESTIMATOR) {
+    if (d->obstacles && d->n_obs > 0) return set_err(-8, "the state-estimator variant has no obstacle rows");
+    if constexpr (sizeof(S) == 8)
+      return forward_se_f64(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out, status_out, info_out,
+                            debug_out, workspace, st);
+    else
+      return forward_se_f32(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out, status_out, info_out,
+                            debug_out, workspace, st);
+  }
   if (d->obstacles && d->n_obs > 0) {
     // sphere-avoidance rows act on the position x[0..2]; compiled for the one reference env that uses them
     // (FlyingCartpole_obstacles, deqmpc/policies.py:1180)
     if (d->dyn_id != ALMPC_DYN_FLYING_CARTPOLE)
       return set_err(-8, "obstacle constraints are compiled for the flying-cartpole model only");
-    return forward_impl<FlyingCartpole, S, true>(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out,
+    return forward_impl<FlyingCartpole, S, 1>(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out,
                                                  status_out, info_out, debug_out, workspace, st);
   }
-  ALMPC_DISPATCH(d->dyn_id, (forward_impl<M, S, false>(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out,
+  ALMPC_DISPATCH(d->dyn_id, (forward_impl<M, S, 0>(d, x0, Qd, q, xu, lam, rho, factor, x_out, u_out, dyn_res_out,
                                                        status_out, info_out, debug_out, workspace, st)))
 }
 
@@ -2094,8 +2157,11 @@ static int tracking_cost_bwd(int B, int T, int nx, int nu, const S* Q0, const fl
   return cuda_err(cudaGetLastError(), "almpc_tracking_cost_bwd launch");
 }
 
+#endif  // !ALMPC_BUILD_SE
+
 }  // namespace almpc
 
+#if !ALMPC_BUILD_SE
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
@@ -2227,3 +2293,4 @@ const char* almpc_version(void) { return "almpc 0.1 (sm_100a)"; }
 
 #endif
 }  // extern "C"
+#endif  // !ALMPC_BUILD_SE

@@ -31,13 +31,15 @@ class SolveConfig:
     debug: bool = False
     obstacles: object = None      # device tensor [B,T,n_obs,3] in the solver dtype (Obstacle_MPC)
     obs_radius: float = 0.0
+    state_estimator: bool = False  # MPC(state_estimator=True): dynamics rows only, controls are data (al_utils_se.py)
 
     def desc(self, B):
         d = _lib.Desc()
         d.B, d.T, d.dyn_id = B, self.T, self.dyn.dyn_id
         d.al_iter, d.max_newton = self.al_iter, self.max_newton
         d.stream_mode, d.rho_f32 = int(self.stream_mode), int(self.rho_f32)
-        d.flags = _lib.FLAG_SKIP_FINAL_DUAL if self.skip_final_dual else 0
+        d.flags = (_lib.FLAG_SKIP_FINAL_DUAL if self.skip_final_dual else 0) | (
+            _lib.FLAG_STATE_ESTIMATOR if self.state_estimator else 0)
         d.rho_mult, d.rho_max = self.rho_mult, self.rho_max
         for i, v in enumerate(self.dyn.param_block()):
             d.dyn_params[i] = v
@@ -74,7 +76,9 @@ def raw_forward(cfg: SolveConfig, x0, Qd, q, xu, lam, rho):
         if ob.dtype != xu.dtype or not ob.is_contiguous() or ob.dim() != 4 or ob.shape[0] != B or ob.shape[1] != T or ob.shape[3] != 3:
             raise _lib.AlmpcError("obstacles must be a contiguous [B,T,n_obs,3] tensor of the solver dtype")
         n_obs = ob.shape[2]
-    m = T * nx + T * (2 * nu + n_obs)
+    m = (T - 1) * nx if cfg.state_estimator else T * nx + T * (2 * nu + n_obs)
+    if cfg.state_estimator and n_obs:
+        raise _lib.AlmpcError("the state-estimator variant has no obstacle rows")
     if x0.shape != (B, nx) or Qd.shape != (B, T, n) or q.shape != (B, T, n) or lam.shape != (B, m) or rho.numel() != B:
         raise _lib.AlmpcError("inconsistent AL-MPC buffer shapes")
     dev, dt = xu.device, xu.dtype

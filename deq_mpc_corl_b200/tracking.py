@@ -10,7 +10,8 @@ Mirror of deqmpc/policies.py:1117-1315 (`Tracking_MPC`): same constructor (`args
   `p = -(Q * xu_ref).sum(-1)`, `f` with a handful of elementwise kernels (policies.py:1285-1297); here
   `almpc_tracking_cost_*` writes `Qd[B,T,n]` and `q[B,T,n]` in one pass from the fp32 network outputs, and the
   backward maps the solver's `(Q_grad, q_grad)` straight to `x_ref.grad`, `u_ref.grad`, `q_scaling.grad`;
-* only the AL solver (`solver_type == "al"`) without obstacles exists on this path.
+* only the AL solver (`solver_type == "al"`) without obstacles exists on this path; `state_estimator=True`
+  (policies.py:321) selects the dynamics-rows-only variant of qpth/al_utils_se.py.
 
 `env` needs `nx, nu, dt, dynamics` (anything `dynamics.resolve` accepts) and `action_space.low/high`;
 `args` needs `T, bsz, Q, R, dtype ("double"|"float"), device` and, for streaming, `rho_init_max`.
@@ -78,8 +79,6 @@ class Tracking_MPC(torch.nn.Module):
         super().__init__()
         if getattr(args, "solver_type", "al") != "al" or "obstacles" in str(getattr(args, "env", "")):
             raise _lib.AlmpcError("only the AL solver without obstacles is on the fused path")
-        if state_estimator:
-            raise _lib.AlmpcError("state_estimator is outside the fused AL-MPC path")
         self.args = args
         self.nu, self.nx = env.nu, env.nx
         self.nq = getattr(env, "nq", None)
@@ -104,7 +103,7 @@ class Tracking_MPC(torch.nn.Module):
         self.x_init = None
         self.ctrl = MPC(self.nx, self.nu, self.T, u_lower=self.u_lower, u_upper=self.u_upper, exit_unconverged=False,
                         eps=1e-2, n_batch=self.bsz, backprop=False, verbose=0, u_init=self.u_init, solver_type="dense",
-                        dtype=self.dtype, state_estimator=False)
+                        dtype=self.dtype, state_estimator=state_estimator)
 
     def forward(self, x0, xu_ref, x_ref, u_ref, q_scaling=None, model_call=None, al_iters=2):
         if self.x_init is None:  # policies.py:1242-1244

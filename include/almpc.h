@@ -58,6 +58,11 @@ enum almpc_dyn_id {
 
 /* desc.flags: leave lam/rho untouched at the end (NewtonAL-only use: al_utils.py:449 has no dual update) */
 #define ALMPC_FLAG_SKIP_FINAL_DUAL 1
+/* desc.flags: MPC(state_estimator=True) (qpth/AL_mpc.py:186-199,426-442,508-509 -> qpth/al_utils_se.py): the
+ * constraints are the T-1 dynamics blocks only (lam has (T-1)*nx entries), the controls are data (their
+ * Jacobian columns are zeroed, al_utils_se.py:153; u_lower/u_upper are ignored) and the merit's cost and
+ * its gradient see the states only (al_utils_se.py:272-305); the Hessian keeps diag(Q) on the controls. */
+#define ALMPC_FLAG_STATE_ESTIMATOR 2
 
 typedef struct almpc_desc {
   int32_t B;          /* problems in the batch */

@@ -52,17 +52,21 @@ class SolveTrace:
 class Problem:
     """Static description of one batched problem family (dims, dynamics, bounds)."""
 
-    def __init__(self, model, T, u_lower, u_upper, dtype=torch.float64, obstacles=None):
-        """obstacles = (positions [B,T,K,3], radius tensor) for Obstacle_MPC (qpth/AL_mpc_custom.py), else None."""
+    def __init__(self, model, T, u_lower, u_upper, dtype=torch.float64, obstacles=None, state_estimator=False):
+        """obstacles = (positions [B,T,K,3], radius tensor) for Obstacle_MPC (qpth/AL_mpc_custom.py), else None.
+        state_estimator = the ``MPC(state_estimator=True)`` variant (qpth/al_utils_se.py, AL_mpc.py:186-199,
+        426-442, 508-509): only the T-1 dynamics rows, controls are data (their Jacobian columns are zeroed,
+        al_utils_se.py:153), the cost and its gradient see the states only (al_utils_se.py:272-305)."""
         self.model = model
         self.T = T
         self.nx, self.nu = model.nx, model.nu
         self.n = self.nx + self.nu
         self.N = T * self.n
-        self.neq = T * self.nx
+        self.se = state_estimator
+        self.neq = (T - 1) * self.nx if state_estimator else T * self.nx
         self.obstacles = obstacles
         self.n_obs = 0 if obstacles is None else obstacles[0].shape[2]
-        self.nineq = T * (2 * self.nu + self.n_obs)
+        self.nineq = 0 if state_estimator else T * (2 * self.nu + self.n_obs)
         self.m = self.neq + self.nineq
         self.dtype = dtype
         self.u_lower = torch.as_tensor(u_lower).to(dtype)
@@ -79,6 +83,8 @@ def residuals(pb: Problem, xu, x0):
     x, u = xu[..., :nx], xu[..., nx:]
     xn = pb.model.step(x[:, :-1].reshape(-1, nx), u[:, :-1].reshape(-1, pb.nu)).view(B, pb.T - 1, nx)
     c_dyn = (x[:, 1:] - xn).reshape(B, -1)
+    if pb.se:  # al_utils_se.py:247-258
+        return c_dyn, c_dyn
     c_init = x[:, 0] - x0
     c_in = _ineq_rows(pb, x, u).reshape(B, -1)
     c = torch.cat([c_dyn, c_init, c_in], dim=1)
@@ -99,8 +105,10 @@ def _ineq_rows(pb, x, u):
     return rows
 
 
-def cost_value(xu, Qd, q):
-    """al_utils.py:425-435 with diag cost and f=0."""
+def cost_value(xu, Qd, q, nx=None):
+    """al_utils.py:425-435 with diag cost and f=0 (nx given: states only, al_utils_se.py:272-289)."""
+    if nx is not None:
+        xu, Qd, q = xu[..., :nx], Qd[..., :nx], q[..., :nx]
     return (0.5 * (xu * Qd * xu).sum(-1) + (q * xu).sum(-1)).sum(-1)
 
 
@@ -111,7 +119,7 @@ def merit(pb: Problem, xu, x0, Qd, q, lam, rho):
         rep = lambda a: a[None].expand(K, *a.shape).reshape(K * B, *a.shape[1:])
         return merit(pb, xu.reshape(K * B, pb.T, pb.n), rep(x0), rep(Qd), rep(q), rep(lam), rep(rho)).view(K, B)
     c, c_plus = residuals(pb, xu, x0)
-    return cost_value(xu, Qd, q) + 0.5 * rho[:, 0] * (c_plus * c_plus).sum(1) + (lam * c).sum(1)
+    return cost_value(xu, Qd, q, pb.nx if pb.se else None) + 0.5 * rho[:, 0] * (c_plus * c_plus).sum(1) + (lam * c).sum(1)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -122,12 +130,15 @@ def constraint_jacobian(pb: Problem, xu, x0):
     B, T, n, nx, nu = xu.shape[0], pb.T, pb.n, pb.nx, pb.nu
     x, u = xu[..., :nx], xu[..., nx:]
     xn, (Jx, Ju) = pb.model.step_jac(x[:, :-1].reshape(-1, nx), u[:, :-1].reshape(-1, nu))
-    G = torch.cat([Jx.reshape(B, T - 1, nx, nx), Ju.reshape(B, T - 1, nx, nu)], dim=-1)
+    G = torch.cat([Jx.reshape(B, T - 1, nx, nx), Ju.reshape(B, T - 1, nx, nu) * (0.0 if pb.se else 1.0)], dim=-1)
     J = torch.zeros(B, pb.m, pb.N, dtype=xu.dtype)
     eye = torch.eye(nx, dtype=xu.dtype)
     for t in range(T - 1):
         J[:, t * nx : (t + 1) * nx, t * n : (t + 1) * n] = -G[:, t]
         J[:, t * nx : (t + 1) * nx, (t + 1) * n : (t + 1) * n + nx] = eye
+    if pb.se:  # al_utils_se.py:97-109,143-187: dynamics rows only
+        c_dyn = (x[:, 1:] - xn.view(B, T - 1, nx)).reshape(B, -1)
+        return c_dyn, c_dyn, J, J
     J[:, (T - 1) * nx : T * nx, :nx] = eye
     c_in = _ineq_rows(pb, x, u).reshape(B, -1)
     SI = 2 * nu + pb.n_obs
@@ -154,8 +165,11 @@ def grad_hess(pb: Problem, xu, x0, Qd, q, lam, rho):
     """al_utils.py:80-123: grad = Qd*z + q + J^T lam + rho Jc^T c+ ; H = diag(Qd) + rho Jc^T Jc."""
     B = xu.shape[0]
     c, c_plus, J, Jc = constraint_jacobian(pb, xu, x0)
+    gc = Qd * xu + q
+    if pb.se:  # al_utils_se.py:292-305: the control entries of the cost gradient are zeroed
+        gc = torch.cat([gc[..., : pb.nx], torch.zeros_like(gc[..., pb.nx :])], -1)
     g = (
-        (Qd * xu + q).reshape(B, -1)
+        gc.reshape(B, -1)
         + (lam[..., None] * J).sum(-2)
         + rho * (c_plus[..., None] * Jc).sum(-2)
     )
@@ -255,8 +269,8 @@ class OracleMPC:
     rho_max = 1e8
 
     def __init__(self, model, T, u_lower, u_upper, n_batch, dtype=torch.float64, al_iter=2, obstacle_positions=None,
-                 obstacle_radius=None):
-        self.pb = Problem(model, T, u_lower, u_upper, dtype)
+                 obstacle_radius=None, state_estimator=False):
+        self.pb = Problem(model, T, u_lower, u_upper, dtype, state_estimator=state_estimator)
         self.obstacle_positions = obstacle_positions  # [n_obstacles,3]: Obstacle_MPC (AL_mpc_custom.py:22-135)
         self.obstacle_radius = None if obstacle_radius is None else torch.tensor(obstacle_radius).to(dtype)
         if obstacle_positions is not None:

@@ -75,7 +75,7 @@ class CasadiDx:
 # synthetic inputs — shared with tests/ and bench.py through oracle/problem_gen.py
 # --------------------------------------------------------------------------------------------------
 def run_scenario(name, model_name, T, B, dtype_name, calls, seed, stream_after=None, rho_init_max=1e4,
-                 obstacle_radius=None):
+                 obstacle_radius=None, state_estimator=False):
     """calls = list of al_iter per MPC.forward call; state (lam, rho, warm start) carries across calls
     exactly as in the DEQ loop (policies.py:147-171).  stream_after = index of the call before which
     warm_start_initialize is invoked (policies.py:1305-1310)."""
@@ -106,7 +106,16 @@ def run_scenario(name, model_name, T, B, dtype_name, calls, seed, stream_after=N
     Qd1 = inp["Qd"].to(dtype)  # [n]
     Qfull = torch.diag(Qd1).repeat(B, T, 1, 1)
 
-    if obstacle_radius is None:
+    if state_estimator:
+        # MPC(state_estimator=True) (policies.py:321,1215): the controls are data ("u_gt_est", policies.py:378),
+        # drawn inside the bounds; only the states are estimated
+        from qpth import al_utils_se
+
+        g1 = torch.Generator().manual_seed(seed + 13)
+        lo, hi = torch.tensor(om.u_lower), torch.tensor(om.u_upper)
+        u_ref = (lo + (hi - lo) * torch.rand(B, T, nu, generator=g1)).to(u_ref.dtype)
+        ctrl = AL_mpc.MPC(nx, nu, T, u_lower=lo, u_upper=hi, n_batch=B, dtype=dtype, state_estimator=True)
+    elif obstacle_radius is None:
         ctrl = AL_mpc.MPC(nx, nu, T, u_lower=torch.tensor(om.u_lower), u_upper=torch.tensor(om.u_upper),
                           n_batch=B, dtype=dtype)
     else:
@@ -159,6 +168,15 @@ def run_scenario(name, model_name, T, B, dtype_name, calls, seed, stream_after=N
             return out
 
     al_utils.merit_grad_hessian, al_utils.line_search_newton, al_utils.NewtonAL = mgh, ls, NewtonProxy
+    if state_estimator:
+        orig_mgh_se = al_utils_se.merit_grad_hessian
+
+        def mgh_se(*a, **k):
+            o = orig_mgh_se(*a, **k)
+            rec["grad"].append(o[0].detach().clone())
+            return o
+
+        al_utils_se.merit_grad_hessian = mgh_se
     out = {}
     try:
         g = torch.Generator().manual_seed(seed + 7)
@@ -205,6 +223,8 @@ def run_scenario(name, model_name, T, B, dtype_name, calls, seed, stream_after=N
             x_ref[:, 0] = x0
     finally:
         al_utils.merit_grad_hessian, al_utils.line_search_newton, al_utils.NewtonAL = orig_mgh, orig_ls, orig_newton
+        if state_estimator:
+            al_utils_se.merit_grad_hessian = orig_mgh_se
 
     if obstacle_radius is not None:
         out["obstacle_positions"] = env.obstacle_positions
@@ -212,7 +232,7 @@ def run_scenario(name, model_name, T, B, dtype_name, calls, seed, stream_after=N
     out.update({"x0": x0, "Qd": Qd1, "u_lower": torch.tensor(om.u_lower), "u_upper": torch.tensor(om.u_upper),
                 "n_calls": np.int64(len(calls)), "T": np.int64(T), "B": np.int64(B), "seed": np.int64(seed),
                 "stream_after": np.int64(-1 if stream_after is None else stream_after),
-                "rho_init_max": np.float64(rho_init_max)})
+                "rho_init_max": np.float64(rho_init_max), "state_estimator": np.bool_(state_estimator)})
     meta = dict(model=model_name, dtype=dtype_name, torch=torch.__version__)
     npz = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
     npz["meta_model"] = np.array(meta["model"])
@@ -235,6 +255,9 @@ SCENARIOS = {
     "quad_T5_f64_lastqp": ("rex_quadrotor", 5, 4, "f64", [10], 1033, None),
     # Obstacle_MPC (qpth/AL_mpc_custom.py): flying cartpole, 4 nearest-sphere rows per stage, 3 cold calls + 1 streaming
     "flying_obs_T5_f64": ("flying_cartpole", 5, 6, "f64", [2, 2, 2, 2], 1043, 3, 1e4, 0.5),
+    # MPC(state_estimator=True) (qpth/al_utils_se.py): dynamics rows only, controls are data
+    "quad_se_T5_f64_chain": ("rex_quadrotor", 5, 6, "f64", [2, 2, 2], 1053, None, 1e4, None, True),
+    "cartpole1l_se_T9_f64": ("cartpole1l", 9, 8, "f64", [2, 2], 1063, None, 1e4, None, True),
 }
 
 if __name__ == "__main__":

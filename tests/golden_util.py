@@ -22,6 +22,7 @@ class Golden:
         self.n_calls = int(z["n_calls"])
         self.stream_after = int(z["stream_after"])
         self.rho_init_max = float(z["rho_init_max"])
+        self.state_estimator = bool(z["state_estimator"]) if "state_estimator" in z.files else False
 
     def t(self, key):
         return torch.from_numpy(np.asarray(self.z[key]))

@@ -89,7 +89,7 @@ def make_ctrl(gold):
                             n_batch=gold.B, dtype=gold.dtype, env=env)
     else:
         ctrl = MPC(spec["nx"], spec["nu"], gold.T, u_lower=gold.t("u_lower"), u_upper=gold.t("u_upper"),
-                   n_batch=gold.B, dtype=gold.dtype)
+                   n_batch=gold.B, dtype=gold.dtype, state_estimator=gold.state_estimator)
     return ctrl, dyn, spec
 
 
@@ -145,7 +145,8 @@ def test_solve_matches_reference_golden(name):
         assert rel_err(ctrl.dyn_res_prev.cpu(), c["dyn_res"]) < max(tol["lam"] * 100, 1e-5)
 
 
-@pytest.mark.parametrize("name", ["quad_T5_f64_cold", "pendulum_T5_f64_chain", "flying_T10_f64_cold", "cartpole1l_T5_f64_stream"] if cuda else [])
+@pytest.mark.parametrize("name", ["quad_T5_f64_cold", "pendulum_T5_f64_chain", "flying_T10_f64_cold", "cartpole1l_T5_f64_stream",
+                                  "quad_se_T5_f64_chain", "cartpole1l_se_T9_f64"] if cuda else [])
 def test_first_newton_step_trace(name):
     """Step-level parity: gradient, Newton direction, the 20 merits, argmin and accept of the first
     Newton step against the reference's own intermediate values."""
@@ -156,7 +157,7 @@ def test_first_newton_step_trace(name):
     spec = MODEL_SPECS[gold.model]
     dyn = make_dyn(gold.model, dt=spec["dt"])
     cfg = SolveConfig(dyn=dyn, T=gold.T, u_lower=gold.t("u_lower").tolist(), u_upper=gold.t("u_upper").tolist(),
-                      al_iter=1, max_newton=1, debug=True, skip_final_dual=True)
+                      al_iter=1, max_newton=1, debug=True, skip_final_dual=True, state_estimator=gold.state_estimator)
     dt = gold.dtype
     B, T, n = gold.B, gold.T, spec["nx"] + spec["nu"]
     xu = c["xu_init"].to(dt).to(DEV).contiguous()
@@ -176,16 +177,21 @@ def test_first_newton_step_trace(name):
 # --------------------------------------------------------------------------------------------------
 # CUDA vs the CPU oracle on seeded synthetic batches
 # --------------------------------------------------------------------------------------------------
-def solve_both(model, T, B, seed, dtype, al_iter=2):
+def solve_both(model, T, B, seed, dtype, al_iter=2, state_estimator=False):
     from oracle import almpc_oracle as orc
     from oracle.problem_gen import make_oracle_model
 
     inp = make_inputs(model, T, B, seed)
     spec = MODEL_SPECS[model]
+    if state_estimator:  # the controls are data: drawn inside the bounds (policies.py:378, u_gt_est)
+        g1 = torch.Generator().manual_seed(seed + 13)
+        lo, hi = torch.as_tensor(inp["u_lower"]), torch.as_tensor(inp["u_upper"])
+        inp["u_ref"] = (lo + (hi - lo) * torch.rand(B, T, spec["nu"], generator=g1)).to(inp["u_ref"].dtype)
     Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"], dtype)
     # oracle
     om = make_oracle_model(model)
-    ompc = orc.OracleMPC(om, T, inp["u_lower"], inp["u_upper"], B, dtype=dtype, al_iter=al_iter)
+    ompc = orc.OracleMPC(om, T, inp["u_lower"], inp["u_upper"], B, dtype=dtype, al_iter=al_iter,
+                         state_estimator=state_estimator)
     ompc.reinitialize(inp["x_ref"])
     ompc.x_init, ompc.u_init = inp["x_ref"].clone(), inp["u_ref"].clone()
     tr = orc.SolveTrace()
@@ -195,7 +201,8 @@ def solve_both(model, T, B, seed, dtype, al_iter=2):
     Qg_o, qg_o = ompc.backward(gx, gu)
     # CUDA
     dyn = make_dyn(model, dt=spec["dt"])
-    ctrl = MPC(spec["nx"], spec["nu"], T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B, dtype=dtype)
+    ctrl = MPC(spec["nx"], spec["nu"], T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B, dtype=dtype,
+               state_estimator=state_estimator)
     ctrl.reinitialize(inp["x_ref"].to(DEV))
     ctrl.x_init, ctrl.u_init = inp["x_ref"].to(DEV), inp["u_ref"].to(DEV)
     ctrl.al_iter = al_iter
@@ -222,6 +229,22 @@ def test_cuda_matches_oracle_f64(model, T, B):
     assert rel_err(r["c"]["lam"], r["o"]["lam"]) < 1e-6
     assert rel_err(r["c"]["qg"], r["o"]["qg"]) < 1e-6
     assert rel_err(r["c"]["Qg"], r["o"]["Qg"]) < 1e-6
+
+
+@pytest.mark.parametrize("model,T,B", [("rex_quadrotor", 5, 96), ("pendulum", 5, 70), ("cartpole1l", 9, 33),
+                                       ("cartpole2l", 3, 17), ("flying_cartpole", 10, 24), ("rex_quadrotor", 7, 9)])
+def test_state_estimator_matches_oracle_f64(model, T, B):
+    """MPC(state_estimator=True) (qpth/al_utils_se.py): dynamics rows only, controls are data."""
+    r = solve_both(model, T, B, 515 + T, torch.float64, state_estimator=True)
+    assert r["c"]["steps"] == r["o"]["steps"]
+    assert rel_err(r["c"]["xu"], r["o"]["xu"]) < 1e-6
+    assert max_rel_err_rows(r["c"]["xu"], r["o"]["xu"]) < 1e-5
+    assert rel_err(r["c"]["lam"], r["o"]["lam"]) < 1e-6
+    assert rel_err(r["c"]["qg"], r["o"]["qg"]) < 1e-6
+    assert rel_err(r["c"]["Qg"], r["o"]["Qg"]) < 1e-6
+    nx = MODEL_SPECS[model]["nx"]
+    # the controls never move
+    assert torch.equal(r["c"]["xu"][..., nx:], r["o"]["xu"][..., nx:])
 
 
 @pytest.mark.parametrize("model,T,B", [("rex_quadrotor", 5, 128), ("cartpole1l", 5, 128)])

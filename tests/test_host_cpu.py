@@ -106,7 +106,12 @@ def test_mpc_state_semantics_and_cpu_refusal():
     with pytest.raises(_lib.AlmpcError, match="CUDA only"):
         ctrl(inp["x0"], QuadCost(Qd, q, None), make_dyn("cartpole1l"), None)
     with pytest.raises(_lib.AlmpcError):
-        MPC(4, 1, 5, u_lower=inp["u_lower"], u_upper=inp["u_upper"], state_estimator=True)
+        MPC(4, 1, 5, u_lower=inp["u_lower"], u_upper=inp["u_upper"], add_goal_constraint=True)
+    # state-estimator variant (AL_mpc.py:186-199): the T-1 dynamics blocks only, no bound rows
+    se = MPC(4, 1, 5, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=6, state_estimator=True)
+    assert se.neq == 16 and se.nineq == 0
+    se.reinitialize(inp["x_ref"], None)
+    assert se.lamda_prev.shape == (6, 16)
 
 
 def test_resolve_recognises_reference_style_objects():

@@ -15,7 +15,8 @@ def replay(gold, resync=True):
     obs_kw = {}
     if "obstacle_positions" in gold.z.files:  # Obstacle_MPC scenario
         obs_kw = dict(obstacle_positions=gold.t("obstacle_positions"), obstacle_radius=float(gold.z["obstacle_radius"]))
-    mpc = orc.OracleMPC(model, gold.T, gold.t("u_lower"), gold.t("u_upper"), gold.B, dtype=gold.dtype, **obs_kw)
+    mpc = orc.OracleMPC(model, gold.T, gold.t("u_lower"), gold.t("u_upper"), gold.B, dtype=gold.dtype,
+                        state_estimator=gold.state_estimator, **obs_kw)
     x0 = gold.t("x0")
     Qd1 = gold.t("Qd").to(gold.dtype)
     out = []
