@@ -95,6 +95,10 @@ def load():
         f = getattr(lib, "almpc_tracking_cost_bwd_" + sfx)
         f.argtypes = [i32] * 4 + [vp] * 10
         f.restype = ctypes.c_int
+    for sfx in ("f64", "f32"):
+        f = getattr(lib, "almpc_blocktri_" + sfx)
+        f.argtypes = [i32] * 5 + [vp] * 8
+        f.restype = ctypes.c_int
     lib.almpc_set_profiling.argtypes = [i32]
     lib.almpc_set_profiling.restype = None
     lib.almpc_get_profile.argtypes = [ctypes.POINTER(dbl)]
@@ -108,6 +112,7 @@ EXPORTS = [
     "almpc_forward_f64", "almpc_forward_f32", "almpc_backward_f64", "almpc_backward_f32",
     "almpc_dynamics_f64", "almpc_dynamics_f32", "almpc_fma_peak_f64", "almpc_fma_peak_f32",
     "almpc_tracking_cost_f64", "almpc_tracking_cost_f32", "almpc_tracking_cost_bwd_f64", "almpc_tracking_cost_bwd_f32",
+    "almpc_blocktri_f64", "almpc_blocktri_f32",
     "almpc_set_profiling", "almpc_get_profile", "almpc_last_error", "almpc_version",
 ]
 

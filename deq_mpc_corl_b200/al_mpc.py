@@ -6,8 +6,10 @@ x_init=None) -> (x, u, status)`` and the same mutable state the caller touches
 ``reinitialize``, ``warm_start_initialize``) — see deqmpc/policies.py:1200-1216,1236-1310 for the
 call sites.  Differences, all deliberate:
 
-* the dynamics callable must resolve to a native CUDA functor (``dynamics.resolve``); there is no
-  CPU fallback and no generic-callable path yet — anything else raises;
+* a dynamics object that resolves to a native CUDA functor (``dynamics.resolve``) runs on the fused kernels;
+  any other pair of callables ``dx`` / ``dx_jac`` (qpth/al_utils.py:237-248 convention) runs in the
+  generic-callable mode (``generic.py``: the callables are evaluated by torch on the GPU, the linear algebra by
+  the block-tridiagonal CUDA kernel); CPU tensors raise — there is no CPU fallback;
 * the al_iter x Newton loop runs as one stream-ordered sequence of kernel launches with the
   batch-global decisions taken on the device, so ``forward`` only synchronises with the host in
   streaming mode, where the reference's own ``status`` is a Python bool (AL_mpc.py:420-423);
@@ -19,6 +21,7 @@ from torch.nn import Module
 from . import _lib
 from .al_utils import LinDx, QuadCost  # noqa: F401  (re-exported like the reference module)
 from .dynamics import resolve
+from .generic import GenericALSolve, GenericConfig
 from .solver import ALSolve, SolveConfig
 
 
@@ -79,8 +82,8 @@ class MPC(Module):
         n_batch = self.n_batch if self.n_batch is not None else cost.C.size(0)
         assert x0.ndimension() == 2 and x0.size(0) == n_batch
         _lib.require_cuda(x0, "MPC.forward(x0)")
-        dyn = resolve(dx)
-        if dyn.nx != self.n_state or dyn.nu != self.n_ctrl:
+        dyn = self._resolve(dx, dx_jac)
+        if dyn is not None and (dyn.nx != self.n_state or dyn.nu != self.n_ctrl):
             raise _lib.AlmpcError("dynamics dimensions do not match n_state / n_ctrl")
         dev = x0.device
 
@@ -97,7 +100,7 @@ class MPC(Module):
         if x_init is not None:
             x = x_init
         elif self.x_init is None:
-            x = self.rollout(x0, u, dyn)
+            x = self.rollout(x0, u, dyn if dyn is not None else dx)
         else:
             x = self.x_init
         if x.ndimension() == 2:
@@ -120,13 +123,23 @@ class MPC(Module):
         if not torch.is_tensor(rho):
             rho = torch.full((n_batch, 1), float(rho), dtype=self.dtype, device=dev)
         rho_dtype = rho.dtype
-        cfg = SolveConfig(
-            dyn=dyn, T=self.T, u_lower=self._bounds_host[0], u_upper=self._bounds_host[1], al_iter=int(self.al_iter),
-            max_newton=self.max_newton_steps, stream_mode=bool(self.warm_starting),
-            rho_f32=(rho_dtype == torch.float32 and self.dtype == torch.float64), rho_max=self.rho_max,
-            state_estimator=bool(self.state_estimator), **self._extra_constraints(dev))
+        common = dict(T=self.T, al_iter=int(self.al_iter), max_newton=self.max_newton_steps,
+                      stream_mode=bool(self.warm_starting),
+                      rho_f32=(rho_dtype == torch.float32 and self.dtype == torch.float64), rho_max=self.rho_max,
+                      state_estimator=bool(self.state_estimator))
+        extra = self._extra_constraints(dev)
+        if dyn is not None:
+            solve = ALSolve
+            cfg = SolveConfig(dyn=dyn, u_lower=self._bounds_host[0], u_upper=self._bounds_host[1], **common, **extra)
+        else:
+            if extra:
+                raise _lib.AlmpcError("obstacle constraints need a native dynamics functor")
+            solve = GenericALSolve
+            cfg = GenericConfig(dx=dx, dx_jac=dx_jac, nx=self.n_state, nu=self.n_ctrl,
+                                u_lower=self.u_lower.to(dev).to(self.dtype), u_upper=self.u_upper.to(dev).to(self.dtype),
+                                **common)
         xu0 = torch.cat([x.to(self.dtype), u.to(self.dtype)], dim=2)
-        xo, uo, xu, lam_new, rho_new, dyn_res, status, info, _ = ALSolve.apply(
+        xo, uo, xu, lam_new, rho_new, dyn_res, status, info, _ = solve.apply(
             Qd, q, x0.to(self.dtype), xu0, lam.to(dev).to(self.dtype), rho.to(dev).to(self.dtype).reshape(-1), cfg)
 
         # ---- state kept for the next call (AL_mpc.py:333-336, 256-257)
@@ -146,10 +159,25 @@ class MPC(Module):
         """Hook for subclasses (Obstacle_MPC): extra SolveConfig fields."""
         return {}
 
+    @staticmethod
+    def _resolve(dx, dx_jac):
+        """Native functor descriptor, or None -> generic-callable mode (both callables are then required)."""
+        try:
+            return resolve(dx)
+        except _lib.AlmpcError:
+            if callable(dx) and callable(dx_jac):
+                return None
+            raise
+
     # ------------------------------------------------------------------------------------------
     def rollout(self, x, actions, dynamics):
-        """AL_mpc.py:521-534 with the native functor."""
-        dyn = resolve(dynamics)
+        """AL_mpc.py:521-534 with the native functor (or the user's callable in generic mode)."""
+        try:
+            dyn = resolve(dynamics)
+        except _lib.AlmpcError:
+            if not callable(dynamics):
+                raise
+            dyn = dynamics
         xs = [x]
         for t in range(self.T - 1):
             xs.append(dyn(xs[t].contiguous(), actions[:, t].contiguous()))

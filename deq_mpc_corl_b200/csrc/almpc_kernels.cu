@@ -1552,6 +1552,152 @@ k_backward(int B, int T, const S* __restrict__ fac_g, const S* __restrict__ xu_g
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// generic-callable dynamics mode: block-tridiagonal factor + solve with RUN-TIME dimensions.
+// When the dynamics are a user's Python callable, the host loop (deq_mpc_corl_b200/generic.py) evaluates
+// it with torch and hands this kernel the dynamics Jacobians; it is the one piece of the Newton step the
+// reference does densely (H[N,N], cholesky_ex + cholesky_solve, al_utils.py:510-513,586-590).
+//   H = diag(dD) + rho * sum_t [ -G_t | I ]^T [ -G_t | I ]   restricted to the G^T G and -rho G_t blocks
+//       (every diagonal contribution, incl. the rho I of the identity blocks, is in dD)
+//   sol = -H^{-1} rhs ;  factor layout = the fused path's (T blocks L_tt with 1/L_ii on the diagonal, then E_t)
+// 1 warp = 1 problem; row per lane, blocks in shared memory (n = nx+nu <= 32).
+// ------------------------------------------------------------------------------------------------
+template <typename S, int WPB>
+__global__ void __launch_bounds__(WPB * 32)
+k_blocktri(int B, int T, int nx, int nu, int do_factor, const S* __restrict__ G_g, const S* __restrict__ dD_g,
+           const S* __restrict__ rho_g, S* fac_g, const S* __restrict__ rhs_g, S* __restrict__ sol_g,
+           int* __restrict__ status_g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = nx + nu, LD = n | 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int prob = blockIdx.x * WPB + warp;
+  if (prob >= B) return;
+  const int per_warp = n * LD + 2 * nx * LD + T * n;
+  S* Dm = reinterpret_cast<S*>(smem_raw) + (size_t)warp * per_warp;  // D_t, then L_tt (diag = 1/L_ii)
+  S* Gm = Dm + n * LD;                                               // G_t
+  S* Em = Gm + nx * LD;                                              // E_{t-1}, then E_t
+  S* yv = Em + nx * LD;                                              // rhs -> y -> solution
+  const size_t FE = (size_t)T * n * n + (size_t)(T - 1) * nx * n;
+  S* fac = fac_g + (size_t)prob * FE;
+  S* facE = fac + (size_t)T * n * n;
+  const S* Gp = G_g ? G_g + (size_t)prob * (T - 1) * nx * n : nullptr;
+  const S rho = do_factor ? rho_g[prob] : S(0);
+  for (int i = lane; i < T * n; i += 32) yv[i] = rhs_g[(size_t)prob * T * n + i];
+  bool ok = true;
+  for (int t = 0; t < T; ++t) {
+    const bool has_G = t < T - 1, has_E = t > 0;
+    S* Lg = fac + (size_t)t * n * n;
+    __syncwarp();
+    if (do_factor) {
+      if (has_G)
+        for (int e = lane; e < nx * n; e += 32) Gm[(e / n) * LD + (e % n)] = Gp[(size_t)t * nx * n + e];
+      __syncwarp();
+      for (int idx = lane; idx < n * n; idx += 32) {
+        const int r = idx / n, c = idx - r * n;
+        if (c > r) continue;
+        S v = (r == c) ? dD_g[((size_t)prob * T + t) * n + r] : S(0);
+        if (has_G) {
+          S a = S(0);
+          for (int i = 0; i < nx; ++i) a += Gm[i * LD + r] * Gm[i * LD + c];
+          v += rho * a;
+        }
+        if (has_E && r < nx) {
+          S a = S(0);
+          for (int k = 0; k < n; ++k) a += Em[r * LD + k] * Em[c * LD + k];
+          v -= a;
+        }
+        Dm[r * LD + c] = v;
+      }
+      __syncwarp();
+      for (int k = 0; k < n; ++k) {  // right-looking Cholesky, row per lane
+        const S dkk = Dm[k * LD + k];
+        ok = ok && (dkk > S(0));
+        const S inv = S(1) / sqrt(dkk);
+        __syncwarp();
+        if (lane == k) Dm[k * LD + k] = inv;
+        else if (lane > k && lane < n) Dm[lane * LD + k] *= inv;
+        __syncwarp();
+        if (lane > k && lane < n) {
+          const S lrk = Dm[lane * LD + k];
+          for (int c = k + 1; c <= lane; ++c) Dm[lane * LD + c] -= lrk * Dm[c * LD + k];
+        }
+        __syncwarp();
+      }
+      for (int idx = lane; idx < n * n; idx += 32) {
+        const int r = idx / n, c = idx - r * n;
+        Lg[idx] = (c <= r) ? Dm[r * LD + c] : S(0);
+      }
+    } else {
+      for (int idx = lane; idx < n * n; idx += 32) Dm[(idx / n) * LD + (idx % n)] = Lg[idx];
+      if (has_E)
+        for (int e = lane; e < nx * n; e += 32) Em[(e / n) * LD + (e % n)] = facE[(size_t)(t - 1) * nx * n + e];
+      __syncwarp();
+    }
+    // y_t = L^{-1} (rhs_t - E_{t-1} y_{t-1})
+    S b = (lane < n) ? yv[t * n + lane] : S(0);
+    if (has_E && lane < nx) {
+      S a = S(0);
+      for (int k = 0; k < n; ++k) a += Em[lane * LD + k] * yv[(t - 1) * n + k];
+      b -= a;
+    }
+    for (int k = 0; k < n; ++k) {
+      const S yk = __shfl_sync(FULL, b * Dm[k * LD + k], k);
+      if (lane == k) b = yk;
+      else if (lane > k && lane < n) b -= Dm[lane * LD + k] * yk;
+    }
+    __syncwarp();
+    if (lane < n) yv[t * n + lane] = b;
+    // E_t = -rho G_t L^{-T}  (row per lane), kept for stage t+1 and stored for the backward sweep
+    if (do_factor && has_G) {
+      __syncwarp();
+      if (lane < nx) {
+        for (int k = 0; k < n; ++k) {
+          S a = -rho * Gm[lane * LD + k];
+          for (int j = 0; j < k; ++j) a -= Em[lane * LD + j] * Dm[k * LD + j];
+          Em[lane * LD + k] = a * Dm[k * LD + k];
+        }
+      }
+      __syncwarp();
+      for (int e = lane; e < nx * n; e += 32) facE[(size_t)t * nx * n + e] = Em[(e / n) * LD + (e % n)];
+    }
+  }
+  ok = __all_sync(FULL, ok);
+  __syncwarp();
+  // backward sweep: d_t = L^{-T} (y_t - E_t^T d_{t+1}), factor read back from global memory
+  for (int t = T - 1; t >= 0; --t) {
+    const S* Lg = fac + (size_t)t * n * n;
+    __syncwarp();
+    for (int idx = lane; idx < n * n; idx += 32) Dm[(idx / n) * LD + (idx % n)] = Lg[idx];
+    if (t < T - 1)
+      for (int e = lane; e < nx * n; e += 32) Em[(e / n) * LD + (e % n)] = facE[(size_t)t * nx * n + e];
+    __syncwarp();
+    S b = (lane < n) ? yv[t * n + lane] : S(0);
+    if (t < T - 1 && lane < n) {
+      S a = S(0);
+      for (int i = 0; i < nx; ++i) a += Em[i * LD + lane] * yv[(t + 1) * n + i];
+      b -= a;
+    }
+    for (int r = n - 1; r >= 0; --r) {
+      const S dr = __shfl_sync(FULL, b * Dm[r * LD + r], r);
+      if (lane == r) b = dr;
+      else if (lane < r) b -= Dm[r * LD + lane] * dr;
+    }
+    __syncwarp();
+    if (lane < n) yv[t * n + lane] = b;
+  }
+  __syncwarp();
+  bool fin = true;
+  for (int i = lane; i < T * n; i += 32) fin = fin && finite_(yv[i]);
+  fin = __all_sync(FULL, fin) && ok;  // failed pivot / non-finite: no direction (same policy as k_factor_solve)
+  for (int i = lane; i < T * n; i += 32) sol_g[(size_t)prob * T * n + i] = fin ? -yv[i] : S(0);
+  if (status_g && lane == 0 && do_factor) {
+    int st = status_g[prob];
+    if (!ok) st &= ~ALMPC_STATUS_CHOL_OK;
+    status_g[prob] = st;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // stand-alone dynamics (+ Jacobian): one thread per (row, tangent)
 // ------------------------------------------------------------------------------------------------
@@ -2123,6 +2269,23 @@ static int dynamics_any(const almpc_desc* d, int64_t R, const S* x, const S* u, 
   ALMPC_DISPATCH(d->dyn_id, (dynamics_impl<M, S>(d, R, x, u, xn, Jx, Ju, st)))
 }
 
+
+template <typename S>
+static int blocktri(int B, int T, int nx, int nu, int do_factor, const S* G, const S* dD, const S* rho, S* factor,
+                    const S* rhs, S* sol, int32_t* status, void* stream) {
+  if (B < 0 || T < 2 || nx < 1 || nu < 0 || nx + nu > 32) return set_err(-3, "blocktri: need T >= 2, 1 <= nx, nx + nu <= 32");
+  if (B == 0) return 0;
+  if (!factor || !rhs || !sol || (do_factor && (!G || !dD || !rho))) return set_err(-10, "null buffer");
+  const int n = nx + nu, LD = n | 1;
+  const size_t smem = (size_t)kWPB * ((size_t)n * LD + 2 * (size_t)nx * LD + (size_t)T * n) * sizeof(S);
+  if (smem + 1024 > 227 * 1024) return set_err(-11, "horizon too long for the shared-memory layout");
+  auto kern = k_blocktri<S, kWPB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(blocktri)");
+  kern<<<n_blocks(B), kWPB * 32, smem, (cudaStream_t)stream>>>(B, T, nx, nu, do_factor, G, dD, rho, factor, rhs, sol, status);
+  return cuda_err(cudaGetLastError(), "almpc_blocktri launch");
+}
+
 template <typename S>
 static int fma_peak(int blocks, int iters, S* sink, double* flops, void* stream) {
   if (blocks <= 0 || iters <= 0 || !sink) return set_err(-1, "bad fma_peak arguments");
@@ -2281,6 +2444,20 @@ int almpc_tracking_cost_bwd_f32(int32_t B, int32_t T, int32_t nx, int32_t nu, co
                                 float* grad_x_ref, float* grad_u_ref, float* grad_scale, void* stream) {
   return tracking_cost_bwd<float>(B, T, nx, nu, Q0, x_ref, u_ref, scale, grad_Q, grad_q, grad_x_ref, grad_u_ref,
                                   grad_scale, stream);
+}
+#endif
+#if ALMPC_BUILD_F64
+int almpc_blocktri_f64(int32_t B, int32_t T, int32_t nx, int32_t nu, int32_t do_factor, const double* G,
+                       const double* diagD, const double* rho, double* factor, const double* rhs, double* sol,
+                       int32_t* status, void* stream) {
+  return blocktri<double>(B, T, nx, nu, do_factor, G, diagD, rho, factor, rhs, sol, status, stream);
+}
+#endif
+#if ALMPC_BUILD_F32
+int almpc_blocktri_f32(int32_t B, int32_t T, int32_t nx, int32_t nu, int32_t do_factor, const float* G,
+                       const float* diagD, const float* rho, float* factor, const float* rhs, float* sol,
+                       int32_t* status, void* stream) {
+  return blocktri<float>(B, T, nx, nu, do_factor, G, diagD, rho, factor, rhs, sol, status, stream);
 }
 #endif
 #if ALMPC_BUILD_F64

@@ -146,6 +146,22 @@ int almpc_tracking_cost_bwd_f32(int32_t B, int32_t T, int32_t nx, int32_t nu, co
                                 const float* u_ref, const float* scale, const float* grad_Q, const float* grad_q,
                                 float* grad_x_ref, float* grad_u_ref, float* grad_scale, void* stream);
 
+/* Generic-callable dynamics mode: when `dx` / `dx_jac` are arbitrary host-language callables
+ * (qpth/al_utils.py:237-248 convention), the host evaluates them itself and calls this for the part of the Newton
+ * step the reference does with dense [N,N] LAPACK calls (al_utils.py:510-513 forward, :586-590 backward):
+ *   H = diag(diagD) + rho * (G_t^T G_t on the stage blocks, -rho G_t below them),   sol = -H^{-1} rhs
+ * Run-time dimensions, nx + nu <= 32.  G [B][T-1][nx][n] with G_t = [d f/d x | d f/d u] at stage t;
+ * diagD [B][T][n] carries EVERY diagonal term (diag(Q), rho on the states coupled by an identity block, rho per
+ * active bound); factor has the layout of almpc_forward_* (almpc_factor_elems with the same nx, nu, T).
+ * do_factor = 1: build + factor + solve (G, diagD, rho required; status bit ALMPC_STATUS_CHOL_OK is cleared on
+ * a non-positive pivot and sol = 0);  do_factor = 0: solve with an existing factor (backward pass). */
+int almpc_blocktri_f64(int32_t B, int32_t T, int32_t nx, int32_t nu, int32_t do_factor, const double* G,
+                       const double* diagD, const double* rho, double* factor, const double* rhs, double* sol,
+                       int32_t* status, void* stream);
+int almpc_blocktri_f32(int32_t B, int32_t T, int32_t nx, int32_t nu, int32_t do_factor, const float* G,
+                       const float* diagD, const float* rho, float* factor, const float* rhs, float* sol,
+                       int32_t* status, void* stream);
+
 /* FMA-pipe micro-benchmark used by bench.py to measure the FP64 / FP32 roofline denominators:
  * launches `blocks` x 256 threads, each doing `iters` x 8 independent FMAs; returns via *flops the
  * number of floating-point operations performed (2 per FMA). */

@@ -247,6 +247,111 @@ def test_state_estimator_matches_oracle_f64(model, T, B):
     assert torch.equal(r["c"]["xu"][..., nx:], r["o"]["xu"][..., nx:])
 
 
+# --------------------------------------------------------------------------------------------------
+# generic-callable dynamics mode (arbitrary Python dx / dx_jac)
+# --------------------------------------------------------------------------------------------------
+def run_mpc(dx, dx_jac, nx, nu, T, inp, Qd, q, gx, gu, dtype, al_iter=2, state_estimator=False):
+    B = inp["x0"].shape[0]
+    ctrl = MPC(nx, nu, T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B, dtype=dtype,
+               state_estimator=state_estimator)
+    ctrl.reinitialize(inp["x_ref"].to(DEV))
+    ctrl.x_init, ctrl.u_init = inp["x_ref"].to(DEV), inp["u_ref"].to(DEV)
+    ctrl.al_iter = al_iter
+    Qdl = Qd.to(DEV).requires_grad_(True)
+    ql = q.to(DEV).requires_grad_(True)
+    x, u, _ = ctrl(inp["x0"].to(DEV), QuadCost(Qdl, ql, None), dx, dx_jac)
+    Qg, qg = torch.autograd.grad((x, u), (Qdl, ql), (gx.to(DEV), gu.to(DEV)))
+    assert x.dtype == torch.float32 and u.dtype == torch.float32
+    return dict(xu=ctrl.last_xu.cpu(), lam=ctrl.lamda_prev.cpu(), rho=ctrl.rho_prev.cpu(), Qg=Qg.cpu(), qg=qg.cpu(),
+                steps=ctrl.newton_steps(), status=ctrl.last_status.cpu(), dyn_res=ctrl.dyn_res_prev.cpu())
+
+
+@pytest.mark.parametrize("model,T,B,se", [("rex_quadrotor", 5, 64, False), ("cartpole1l", 7, 33, False),
+                                          ("pendulum", 5, 50, False), ("flying_cartpole", 5, 17, False),
+                                          ("cartpole2l", 4, 9, False), ("cartpole1l", 5, 21, True)])
+def test_generic_callable_mode_matches_fused_path(model, T, B, se):
+    """The same dynamics passed (a) as a native functor -> fused kernels and (b) as opaque Python callables ->
+    generic mode (torch host loop + almpc_blocktri) must agree: identical Newton-step counts, iterates to 1e-9."""
+    spec = MODEL_SPECS[model]
+    inp = make_inputs(model, T, B, 9090 + T)
+    Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"], torch.float64)
+    g = torch.Generator().manual_seed(3)
+    gx, gu = torch.randn(B, T, spec["nx"], generator=g), torch.randn(B, T, spec["nu"], generator=g)
+    native = make_dyn(model, dt=spec["dt"])
+    calls = {"dx": 0, "jac": 0}
+
+    def dx(x, u):
+        calls["dx"] += 1
+        return native(x, u)
+
+    def dx_jac(x, u):
+        calls["jac"] += 1
+        return native.jacobian(x, u)
+
+    fused = run_mpc(native, native, spec["nx"], spec["nu"], T, inp, Qd, q, gx, gu, torch.float64, state_estimator=se)
+    gen = run_mpc(dx, dx_jac, spec["nx"], spec["nu"], T, inp, Qd, q, gx, gu, torch.float64, state_estimator=se)
+    assert calls["jac"] == sum(gen["steps"]) and calls["dx"] > 0
+    assert gen["steps"] == fused["steps"]
+    assert (gen["status"] == 3).all()
+    assert torch.equal(gen["rho"], fused["rho"])
+    assert rel_err(gen["xu"], fused["xu"]) < 1e-9
+    assert rel_err(gen["lam"], fused["lam"]) < 1e-8
+    assert rel_err(gen["qg"], fused["qg"]) < 1e-8 and rel_err(gen["Qg"], fused["Qg"]) < 1e-8
+    assert rel_err(gen["dyn_res"], fused["dyn_res"]) < 1e-6
+
+
+class _Unicycle:
+    """A model the library has no functor for (nx=3, nu=2): Euler-discretised unicycle with drag."""
+    nx, nu, dt = 3, 2, 0.1
+
+    def step(self, x, u):
+        px, py, th = x[:, 0], x[:, 1], x[:, 2]
+        v, om = u[:, 0], u[:, 1]
+        return torch.stack([px + self.dt * v * torch.cos(th), py + self.dt * v * torch.sin(th),
+                            th + self.dt * (om - 0.1 * torch.sin(th) * v * v)], dim=1)
+
+    def step_jac(self, x, u):
+        from torch.func import jacrev, vmap
+
+        f = lambda xi, ui: self.step(xi[None], ui[None])[0]
+        Jx = vmap(jacrev(f, 0))(x, u)
+        Ju = vmap(jacrev(f, 1))(x, u)
+        return self.step(x, u), (Jx, Ju)
+
+
+@pytest.mark.parametrize("T,B,dtype", [(6, 40, torch.float64), (9, 25, torch.float64), (6, 40, torch.float32)])
+def test_generic_callable_mode_user_model_matches_oracle(T, B, dtype):
+    """A pure-torch user model with no compiled functor: generic mode vs the CPU oracle on the same callables."""
+    from oracle import almpc_oracle as orc
+
+    m = _Unicycle()
+    g = torch.Generator().manual_seed(77 + T)
+    x0 = torch.randn(B, 3, generator=g, dtype=torch.float64)
+    x_ref = x0[:, None, :] * torch.linspace(1.0, 0.5, T, dtype=torch.float64)[None, :, None] + 0.05 * torch.randn(B, T, 3, generator=g, dtype=torch.float64)
+    x_ref[:, 0] = x0
+    u_ref = torch.zeros(B, T, 2, dtype=torch.float64)
+    x0, x_ref, u_ref = x0.to(dtype), x_ref.to(dtype), u_ref.to(dtype)
+    inp = dict(x0=x0, x_ref=x_ref, u_ref=u_ref, u_lower=torch.tensor([-1.0, -2.0]), u_upper=torch.tensor([1.0, 2.0]))
+    Qd, q, _ = tracking_cost(torch.tensor([10.0, 10.0, 1.0, 1e-2, 1e-2]), x_ref, u_ref, dtype)
+    q = q.to(dtype)
+    gx, gu = torch.randn(B, T, 3, generator=g), torch.randn(B, T, 2, generator=g)
+    ompc = orc.OracleMPC(m, T, inp["u_lower"], inp["u_upper"], B, dtype=dtype, al_iter=2)
+    ompc.reinitialize(x_ref)
+    ompc.x_init, ompc.u_init = x_ref.clone(), u_ref.clone()
+    tr = orc.SolveTrace()
+    _, _, _, xuo = ompc.solve(x0, Qd, q, trace=tr)
+    Qg_o, qg_o = ompc.backward(gx, gu)
+    gen = run_mpc(m.step, m.step_jac, 3, 2, T, inp, Qd, q, gx, gu, dtype)
+    if dtype == torch.float64:
+        assert gen["steps"] == tr.newton_steps
+        assert rel_err(gen["xu"], xuo) < 1e-6 and max_rel_err_rows(gen["xu"], xuo) < 1e-5
+        assert rel_err(gen["lam"], ompc.lamda_prev) < 1e-6
+        assert rel_err(gen["qg"], qg_o) < 1e-6 and rel_err(gen["Qg"], Qg_o) < 1e-6
+    else:
+        assert abs(sum(gen["steps"]) - sum(tr.newton_steps)) <= 1
+        assert rel_err(gen["xu"], xuo) < 3e-2
+
+
 @pytest.mark.parametrize("model,T,B", [("rex_quadrotor", 5, 128), ("cartpole1l", 5, 128)])
 def test_cuda_matches_oracle_f32(model, T, B):
     """fp32 solver vs the fp32 oracle: both sit on the fp32 noise floor of the algorithm
