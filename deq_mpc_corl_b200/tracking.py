@@ -10,8 +10,9 @@ Mirror of deqmpc/policies.py:1117-1315 (`Tracking_MPC`): same constructor (`args
   `p = -(Q * xu_ref).sum(-1)`, `f` with a handful of elementwise kernels (policies.py:1285-1297); here
   `almpc_tracking_cost_*` writes `Qd[B,T,n]` and `q[B,T,n]` in one pass from the fp32 network outputs, and the
   backward maps the solver's `(Q_grad, q_grad)` straight to `x_ref.grad`, `u_ref.grad`, `q_scaling.grad`;
-* only the AL solver (`solver_type == "al"`) without obstacles exists on this path; `state_estimator=True`
-  (policies.py:321) selects the dynamics-rows-only variant of qpth/al_utils_se.py.
+* only the AL solver (`solver_type == "al"`) exists on this path; `"obstacles" in args.env` selects
+  `Obstacle_MPC` (policies.py:1180-1198), `state_estimator=True` (policies.py:321) the dynamics-rows-only
+  variant of qpth/al_utils_se.py.
 
 `env` needs `nx, nu, dt, dynamics` (anything `dynamics.resolve` accepts) and `action_space.low/high`;
 `args` needs `T, bsz, Q, R, dtype ("double"|"float"), device` and, for streaming, `rho_init_max`.
@@ -21,7 +22,7 @@ import ctypes
 import torch
 
 from . import _lib
-from .al_mpc import MPC
+from .al_mpc import MPC, Obstacle_MPC
 from .al_utils import QuadCost
 from .dynamics import resolve
 
@@ -77,8 +78,8 @@ class _TrackingCost(torch.autograd.Function):
 class Tracking_MPC(torch.nn.Module):
     def __init__(self, args, env, state_estimator=False):
         super().__init__()
-        if getattr(args, "solver_type", "al") != "al" or "obstacles" in str(getattr(args, "env", "")):
-            raise _lib.AlmpcError("only the AL solver without obstacles is on the fused path")
+        if getattr(args, "solver_type", "al") != "al":
+            raise _lib.AlmpcError("only the AL solver (solver_type == 'al') is on the fused path")
         self.args = args
         self.nu, self.nx = env.nu, env.nx
         self.nq = getattr(env, "nq", None)
@@ -101,9 +102,13 @@ class Tracking_MPC(torch.nn.Module):
         self.Q = torch.cat([torch.as_tensor(Q), torch.as_tensor(R)], dim=0).to(self.dtype).to(self.device).contiguous()
         self.u_init = torch.randn(self.bsz, self.T, self.nu, dtype=self.dtype, device=self.device)
         self.x_init = None
-        self.ctrl = MPC(self.nx, self.nu, self.T, u_lower=self.u_lower, u_upper=self.u_upper, exit_unconverged=False,
-                        eps=1e-2, n_batch=self.bsz, backprop=False, verbose=0, u_init=self.u_init, solver_type="dense",
-                        dtype=self.dtype, state_estimator=state_estimator)
+        kw = dict(u_lower=self.u_lower, u_upper=self.u_upper, exit_unconverged=False, eps=1e-2, n_batch=self.bsz,
+                  backprop=False, verbose=0, u_init=self.u_init, solver_type="dense", dtype=self.dtype,
+                  state_estimator=state_estimator)
+        if "obstacles" in str(getattr(args, "env", "")):  # policies.py:1180-1198
+            self.ctrl = Obstacle_MPC(self.nx, self.nu, self.T, env=env, **kw)
+        else:
+            self.ctrl = MPC(self.nx, self.nu, self.T, **kw)
 
     def forward(self, x0, xu_ref, x_ref, u_ref, q_scaling=None, model_call=None, al_iters=2):
         if self.x_init is None:  # policies.py:1242-1244

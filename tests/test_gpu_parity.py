@@ -522,6 +522,50 @@ def test_tracking_mpc_fused_cost_and_chain_rule():
     assert tm.ctrl.warm_starting and isinstance(st3, bool) and torch.isfinite(x3).all()
 
 
+def test_tracking_mpc_obstacle_and_state_estimator_routes():
+    """Tracking_MPC picks Obstacle_MPC for `"obstacles" in args.env` (policies.py:1180-1198) and forwards
+    state_estimator=True (policies.py:321); both must equal the corresponding MPC called directly."""
+    from deq_mpc_corl_b200.al_mpc import Obstacle_MPC
+    from deq_mpc_corl_b200.tracking import Tracking_MPC
+
+    model, T, B = "flying_cartpole", 5, 24
+    spec = MODEL_SPECS[model]
+    nx, nu = spec["nx"], spec["nu"]
+    inp = make_inputs(model, T, B, 91)
+    dyn = make_dyn(model)
+    g = torch.Generator().manual_seed(8)
+    obstacles = 2.0 * torch.randn(40, 3, generator=g, dtype=torch.float64)
+    x_ref = inp["x_ref"].clone()
+    x_ref[:, :, :3] = obstacles[torch.randint(0, 40, (B,), generator=g)][:, None] + 0.3 * torch.randn(B, T, 3, generator=g, dtype=torch.float64)
+    x0 = x_ref[:, 0].clone()
+    mk_args = lambda env_name: types.SimpleNamespace(T=T, bsz=B, Q=torch.tensor(spec["Q"]), R=torch.tensor(spec["R"]),
+                                                     dtype="double", device=DEV, solver_type="al", env=env_name,
+                                                     rho_init_max=1e4)
+    env = types.SimpleNamespace(nx=nx, nu=nu, nq=8, dt=spec["dt"], dynamics=dyn, dynamics_derivatives=dyn,
+                                obstacle_positions=obstacles, obstacle_radius=0.5,
+                                action_space=types.SimpleNamespace(low=inp["u_lower"].numpy(), high=inp["u_upper"].numpy()))
+    Qd, q, _ = tracking_cost(inp["Qd"], x_ref, inp["u_ref"], torch.float64)
+    # ---- obstacles
+    tm = Tracking_MPC(mk_args("FlyingCartpole_obstacles-v0"), env)
+    assert isinstance(tm.ctrl, Obstacle_MPC)
+    tm.reinitialize(x_ref.to(DEV), None)
+    x, u, _ = tm(x0.to(DEV), None, x_ref.to(DEV), inp["u_ref"].to(DEV), al_iters=2)
+    ctrl = Obstacle_MPC(nx, nu, T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B, env=env)
+    ctrl.reinitialize(x_ref.to(DEV), None)
+    ctrl.x_init, ctrl.u_init = x_ref.to(DEV), inp["u_ref"].to(DEV)
+    x2, u2, _ = ctrl(x0.to(DEV), QuadCost(Qd.to(DEV), q.to(DEV), None), dyn, dyn)
+    assert torch.equal(x, x2) and torch.equal(u, u2)
+    assert (tm.ctrl.lamda_prev[:, T * nx + T * 2 * nu:] > 0).any(), "no obstacle row became active: weak test"
+    # ---- state estimator
+    se = Tracking_MPC(mk_args("FlyingCartpole-v0"), env, state_estimator=True)
+    assert se.ctrl.state_estimator and se.ctrl.neq == (T - 1) * nx and se.ctrl.nineq == 0
+    u_data = (0.1 * torch.rand(B, T, nu, generator=g, dtype=torch.float64)).to(DEV)
+    se.reinitialize(x_ref.to(DEV), None)
+    xs, us, _ = se(x0.to(DEV), None, x_ref.to(DEV), u_data, al_iters=2)
+    assert torch.equal(us, u_data.float()) and torch.isfinite(xs).all()
+    assert se.ctrl.lamda_prev.shape == (B, (T - 1) * nx)
+
+
 def test_forward_backward_are_cuda_graph_capturable():
     """include/almpc.h promises no host synchronisation and no allocation inside the library: capture a whole
     forward + backward in a CUDA graph, replay it on fresh inputs, compare with the eager result."""
