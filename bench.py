@@ -215,7 +215,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.cpu_sample is None:
-        args.cpu_sample = 2048 if args.impl == "b200" else 1024
+        args.cpu_sample = 6144 if args.impl == "b200" else 1024
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
