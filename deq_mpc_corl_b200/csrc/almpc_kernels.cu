@@ -346,7 +346,9 @@ __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, 
       for (int tl = 0; tl < NT; ++tl)
 #pragma unroll
         for (int ch = 0; ch < KG; ++ch) {
-          const int col = tl * 8 + g, row = 4 * ch + q4;
+          // the contraction index may be visited in any order as long as both operands agree: row = KG*q4 + ch
+          // (instead of 4*ch + q4) halves the bank conflicts of these fragment loads for the odd stride LB
+          const int col = tl * 8 + g, row = KG * q4 + ch;
           f[tl][ch] = (col < NN && row < NX) ? (double)Gt[row * LB + col] : 0.0;
         }
 #pragma unroll
@@ -367,7 +369,7 @@ __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, 
       for (int tl = 0; tl < NTX; ++tl)
 #pragma unroll
         for (int ch = 0; ch < KE; ++ch) {
-          const int row = tl * 8 + g, k = 4 * ch + q4;
+          const int row = tl * 8 + g, k = KE * q4 + ch;  // permuted contraction index: conflict-free for LB = 17
           f[tl][ch] = (row < NX && k < NN) ? (double)Ep[row * LB + k] : 0.0;
         }
 #pragma unroll
