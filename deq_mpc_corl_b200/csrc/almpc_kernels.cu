@@ -93,7 +93,9 @@ struct KParams {
 //   r = 1 - x y^2 ;  x^-1/2 = y (1 + r/2 + 3 r^2/8 + O(r^3)).  Pivots outside the fp32 range are flagged by
 // the caller (d < 1e30) and never occur for rho <= 1e12.
 __device__ __forceinline__ double rsqrt_(double x) {
-  const double y = (double)rsqrtf((float)x);
+  float y32;  // raw MUFU.RSQ: rsqrtf() wraps it in denormal / range handling that the pivots never need
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y32) : "f"((float)x));
+  const double y = (double)y32;
   const double r = fma(-x * y, y, 1.0);
   const double p = fma(0.375, r, 0.5);
   return fma(y * r, p, y);
@@ -204,7 +206,12 @@ struct Layout {
     xu = take(N);
     dv = take(N);
     w = take(neq);
+    // n = 16 (row stride 17): the nx staged rows of G / E sit on nx consecutive 8-byte bank pairs; place both
+    // buffers so that the right-hand-side row (dv + t*n), moved by the same instructions, lands on the next one
+    constexpr bool kAlign = (NN % 16 == 0) && (NX % 4 == 0) && (NX < 16);
+    if (kAlign) while ((o + NX) % 16 != dv % 16) o += 4;
     Gt = take(NX * (NN | 1));
+    if (kAlign) while (o % 16 != Gt % 16) o += 4;
     Ep = take(NX * (NN | 1));
     scr = take(64 + NN * (NN | 1));
     total = o;
@@ -335,6 +342,10 @@ __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, 
   if constexpr (sizeof(S) == 8) {
     constexpr int NT = (NN + 7) / 8, KG = (NX + 3) / 4, NTX = (NX + 7) / 8, KE = (NN + 3) / 4;
     const int g = lane >> 2, q4 = lane & 3;
+    // diagonal cost entries this lane will add in the epilogue: issued now, their latency hides under the MMAs
+    double qd[NT];
+#pragma unroll
+    for (int rt = 0; rt < NT; ++rt) qd[rt] = (rt * 8 + g < NN) ? (double)Qd_t[rt * 8 + g] : 0.0;
     double acc[NT][NT][2];
 #pragma unroll
     for (int rt = 0; rt < NT; ++rt)
@@ -397,7 +408,7 @@ __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, 
             }
           }
           v *= rho;
-          if (r == c && r < NN) v += Qd_t[r];
+          if (r == c && r < NN) v += qd[rt];
           if (rt < NTX && ct < NTX) v -= sy[rt][ct][e];
           if (r < NN && c < NN) scr[r * LD + c] = v;
         }
@@ -728,12 +739,10 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
       const bool e_act = (ei >= 0) && (ei < NX) && has_G;
       const S* rowp = (lane < NN) ? (scr + 64 + lane * LD) : ((lane == NN) ? (dv + t * NN) : (X + (e_act ? ei : 0) * LB));
       const S scale = (lane <= NN) ? S(1) : (e_act ? -rho : S(0));
-      const int last = (lane < NN) ? lane : NN - 1;  // L rows: lower triangle only
+      // entries above the diagonal of an L row are never read by another lane (the pivot column is consumed
+      // from row k+1 on and the write-out masks them), so they are loaded as they are
 #pragma unroll
-      for (int c = 0; c < NN; ++c) {
-        const S v = rowp[c] * scale;
-        a[c] = (c <= last) ? v : S(0);
-      }
+      for (int c = 0; c < NN; ++c) a[c] = rowp[c] * scale;
     }
     __syncwarp();  // Y (E_{t-1}) has no reader left: prefetch G_{t+1} into it behind the pivot chain
     if (t + 1 < T - 1) warp_copy_block_async<NX, NN, LB>(Y, Gp + (size_t)(t + 1) * NX * NN, lane);
@@ -822,7 +831,7 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
     S l[NN];
     if (lane < NN) {
 #pragma unroll
-      for (int r = 0; r < NN; ++r) l[r] = (r >= lane) ? Lsm[r * NN + lane] : S(0);
+      for (int r = 0; r < NN; ++r) l[r] = Lsm[r * NN + lane];  // stored factor: zeros above the diagonal
     }
     S b = (lane < NN) ? dv[t * NN + lane] : S(0);
     if (t < T - 1 && lane < NN) {

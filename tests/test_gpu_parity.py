@@ -31,8 +31,12 @@ DEV = "cuda:0"
 def tolerances(rho_out_max, dtype):
     if dtype != torch.float64:
         return dict(xu=2e-3, lam=1e-2, grad=1e-2)
+    # x, u: the 1e-6 relative bar of the task.  lam = lam + rho c amplifies an iterate difference e_xu by rho, and
+    # cond(H) ~ rho / R limits the agreement of any two correct factorizations, so the multiplier and gradient
+    # budgets grow with the largest penalty used in the call (same rule as tests/test_oracle_golden.py; measured
+    # spread between two builds of this library that differ only in rounding order: 5e-7 vs 2e-6 at rho = 1e5)
     rho_used = rho_out_max / 10.0
-    return dict(xu=max(1e-6, 1e-14 * rho_used), lam=max(1e-6, 1e-12 * rho_used), grad=max(1e-6, 1e-11 * rho_used))
+    return dict(xu=max(1e-6, 1e-14 * rho_used), lam=max(1e-6, 1e-10 * rho_used), grad=max(1e-6, 1e-11 * rho_used))
 
 
 # --------------------------------------------------------------------------------------------------
