@@ -383,6 +383,22 @@ def test_empty_and_ragged_batches():
         assert torch.isfinite(x).all() and torch.isfinite(u).all()
 
 
+def test_horizon_limits():
+    """Longest supported horizon (T = 64, check_desc) against the oracle, and the loud failure one past it."""
+    r = solve_both("pendulum", 64, 3, 321, torch.float64)
+    assert r["c"]["steps"] == r["o"]["steps"]
+    assert rel_err(r["c"]["xu"], r["o"]["xu"]) < 1e-6 and rel_err(r["c"]["qg"], r["o"]["qg"]) < 1e-6
+    r = solve_both("cartpole1l", 2, 9, 322, torch.float64)  # shortest horizon: one dynamics block
+    assert r["c"]["steps"] == r["o"]["steps"] and rel_err(r["c"]["xu"], r["o"]["xu"]) < 1e-6
+    inp = make_inputs("pendulum", 65, 2, 5)
+    Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"])
+    ctrl = MPC(2, 1, 65, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=2)
+    ctrl.reinitialize(inp["x_ref"].to(DEV))
+    ctrl.x_init, ctrl.u_init = inp["x_ref"].to(DEV), inp["u_ref"].to(DEV)
+    with pytest.raises(_lib.AlmpcError, match="horizon"):
+        ctrl(inp["x0"].to(DEV), QuadCost(Qd.to(DEV), q.to(DEV), None), make_dyn("pendulum"), None)
+
+
 def test_unregistered_dynamics_and_cpu_tensors_fail_loudly():
     inp = make_inputs("pendulum", 5, 4, 3)
     Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"])
