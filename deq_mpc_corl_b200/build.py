@@ -10,7 +10,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "almpc_kernels.cu")
 OUT = os.path.join(HERE, "libalmpc.so")
-DEPS = [SRC, os.path.join(HERE, "csrc", "almpc_models.cuh"), os.path.join(ROOT, "include", "almpc.h")]
+DEPS = [SRC, os.path.join(ROOT, "include", "almpc.h")] + [
+    os.path.join(HERE, "csrc", h) for h in ("almpc_models.cuh", "almpc_common.cuh", "almpc_dynamics_kernels.cuh",
+                                            "almpc_factor.cuh", "almpc_linesearch.cuh")]
 
 
 def nvcc_path():

@@ -177,8 +177,12 @@ def test_tracking_mpc_refuses_non_al_paths():
     base = dict(T=5, bsz=4, Q=torch.ones(2), R=torch.ones(1) * 1e-3, dtype="double", device="cpu")
     with pytest.raises(_lib.AlmpcError):
         Tracking_MPC(types.SimpleNamespace(solver_type="ip", env="pendulum", **base), env)
-    with pytest.raises(_lib.AlmpcError):
-        Tracking_MPC(types.SimpleNamespace(solver_type="al", env="FlyingCartpole_obstacles", **base), env)
+    # "obstacles" in args.env selects Obstacle_MPC (policies.py:1180-1198); the state-estimator variant too
+    env_obs = types.SimpleNamespace(obstacle_positions=torch.zeros(40, 3), obstacle_radius=0.5, **vars(env))
+    to = Tracking_MPC(types.SimpleNamespace(solver_type="al", env="FlyingCartpole_obstacles", **base), env_obs)
+    assert type(to.ctrl).__name__ == "Obstacle_MPC" and to.ctrl.nineq == 5 * (2 + 4)
+    se = Tracking_MPC(types.SimpleNamespace(solver_type="al", env="pendulum", **base), env, state_estimator=True)
+    assert se.ctrl.state_estimator and se.ctrl.neq == 8 and se.ctrl.nineq == 0
     tm = Tracking_MPC(types.SimpleNamespace(solver_type="al", env="pendulum", **base), env)
     # fp32 R rounded like the reference does (policies.py:1148: cat of fp32 tensors, then .to(dtype))
     assert tm.Q.tolist() == [1.0, 1.0, float(torch.tensor(1e-3))] and tm.ctrl.neq == 10 and tm.ctrl.nineq == 10

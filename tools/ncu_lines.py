@@ -55,7 +55,7 @@ def main():
         agg = defaultdict(lambda: [0, 0])
         for key, (s, e) in per_line.items():
             name = "other/" + key[0]
-            if key[0] == "almpc_kernels.cu":
+            if key[0].startswith("almpc_"):
                 for nm, lo, hi in ph:
                     if lo <= key[1] <= hi:
                         name = nm

@@ -18,7 +18,7 @@ agg = defaultdict(lambda: [0] * 5)
 for k in range(min(len(inst), len(lines))):
     key = lines[k][1]
     name = 'other'
-    if key and key[0] == 'almpc_kernels.cu':
+    if key and key[0].startswith('almpc_'):
         for nm, lo, hi in regions:
             if lo <= key[1] <= hi:
                 name = nm
