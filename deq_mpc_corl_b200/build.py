@@ -40,7 +40,9 @@ def build(force=False, verbose=False):
               "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "csrc")]
     if verbose:
         common += ["-Xptxas", "-v"]
-    objdir = os.path.join(HERE, "build")
+    common += os.environ.get("ALMPC_NVCC_FLAGS", "").split()  # experiment builds (-D switches)
+    out = os.environ.get("ALMPC_OUT", OUT)
+    objdir = os.path.join(HERE, "build" + os.environ.get("ALMPC_OBJ_SUFFIX", ""))
     os.makedirs(objdir, exist_ok=True)
     units = [("f64", ["-DALMPC_BUILD_F64=1", "-DALMPC_BUILD_F32=0"]), ("f32", ["-DALMPC_BUILD_F64=0", "-DALMPC_BUILD_F32=1"]),
              ("f64_se", ["-DALMPC_BUILD_F64=1", "-DALMPC_BUILD_F32=0", "-DALMPC_BUILD_SE=1"]),
@@ -60,13 +62,13 @@ def build(force=False, verbose=False):
     if verbose:
         for _, err in results:
             print(err)
-    link = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + [o for o, _ in results]
+    link = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + [o for o, _ in results]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + res.stdout + res.stderr)
     for o, _ in results:  # objects are not needed once linked (keeps the gpurun snapshot small)
         os.remove(o)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

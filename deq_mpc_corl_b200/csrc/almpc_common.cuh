@@ -66,13 +66,12 @@ struct KParams {
 // ------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------
-// 1/sqrt(x): fp32 MUFU seed (2^-22) + one cubically convergent correction in fp64 (~1 ulp):
-//   r = 1 - x y^2 ;  x^-1/2 = y (1 + r/2 + 3 r^2/8 + O(r^3)).  Pivots outside the fp32 range are flagged by
-// the caller (d < 1e30) and never occur for rho <= 1e12.
+// 1/sqrt(x): the FP64 MUFU seed (rsqrt.approx.ftz.f64: ~20 correct bits, one instruction, no conversions) + one
+// cubically convergent correction in fp64 (~1 ulp):   r = 1 - x y^2 ;  x^-1/2 = y (1 + r/2 + 3 r^2/8 + O(r^3)).
+// A non-positive pivot yields NaN / Inf, which the callers detect on the finished solution.
 __device__ __forceinline__ double rsqrt_(double x) {
-  float y32;  // raw MUFU.RSQ: rsqrtf() wraps it in denormal / range handling that the pivots never need
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y32) : "f"((float)x));
-  const double y = (double)y32;
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   const double r = fma(-x * y, y, 1.0);
   const double p = fma(0.375, r, 0.5);
   return fma(y * r, p, y);

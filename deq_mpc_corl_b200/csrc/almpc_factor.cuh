@@ -15,13 +15,13 @@ namespace almpc {
 // of one shuffle pair per entry: the first version was bound by the SM's shuffle throughput.
 //   colbuf : FUSED: 2 x 32 scalars (double-buffered pivot column).  !FUSED: the L rows, [NN][LDL].
 template <int NN, bool FUSED, typename S>
-__device__ __forceinline__ bool eliminate(S (&a)[NN], int lane, S* colbuf, int LDL = 0) {
-  bool ok = true;
+__device__ __forceinline__ void eliminate(S (&a)[NN], int lane, S* colbuf, int LDL = 0) {
   if (FUSED) {
     // software-pipelined pivots: as soon as column k+1 has its update, the next pivot is broadcast and its
     // reciprocal square root (the longest dependent chain of the step) runs under the remaining updates
+    // a non-positive pivot turns into NaN / Inf here and poisons the whole solution of the problem, which is
+    // what the caller tests (cheaper than a comparison per pivot)
     S d = __shfl_sync(FULL, a[0], 0);
-    ok = (d > S(0));
     S inv = rsqrt_(d);
 #pragma unroll
     for (int k = 0; k < NN; ++k) {
@@ -33,7 +33,6 @@ __device__ __forceinline__ bool eliminate(S (&a)[NN], int lane, S* colbuf, int L
         __syncwarp();
         a[k + 1] -= lk * col[k + 1];
         d = __shfl_sync(FULL, a[k + 1], k + 1);
-        ok = ok && (d > S(0));
         inv = rsqrt_(d);
         // rest of the pivot column: one scalar head (odd start), 16-byte pairs, one scalar tail (odd NN)
         constexpr bool kVec = !ALMPC_NO_VEC2;
@@ -68,7 +67,6 @@ __device__ __forceinline__ bool eliminate(S (&a)[NN], int lane, S* colbuf, int L
       }
     }
   }
-  return ok;
 }
 
 // factor storage per problem: T blocks [NN][NN] then (T-1) blocks [NX][NN]
@@ -363,7 +361,6 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
   // ---- forward sweep over the stages: gradient, Hessian block, fused elimination.
   // Two block buffers ping-pong: X holds G_t (prefetched) and is overwritten by E_t; Y holds E_{t-1} and,
   // once its last reader is done, receives the prefetch of G_{t+1}.
-  bool ok = true;
   S* X = Gt;
   S* Y = Ep;
   for (int t = 0; t < T; ++t) {
@@ -455,7 +452,7 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
     __syncwarp();  // Y (E_{t-1}) has no reader left: prefetch G_{t+1} into it behind the pivot chain
     if (t + 1 < T - 1) warp_copy_block_async<NX, NN, LB>(Y, Gp + (size_t)(t + 1) * NX * NN, lane);
     cp_async_commit();
-    ok = eliminate<NN, true>(a, lane, scr) && ok;
+    eliminate<NN, true>(a, lane, scr);
     __syncwarp();
     {
       // write-outs with per-lane destinations: L rows -> global factor; rhs -> dv (y_t); E rows -> X + global factor
@@ -523,7 +520,6 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
     __syncwarp();
     S* tmp = X; X = Y; Y = tmp;  // Y := E_t, X := G_{t+1}
   }
-  ok = __all_sync(FULL, ok);
   // ---- backward sweep, d = -H^{-1} g.  L_tt / E_t come back from the streamed factor (L2) through
   // cp.async: the blocks of stage t-1 are in flight while the substitution of stage t runs.
   cp_async_wait_all();
@@ -570,6 +566,9 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
   // A non-positive pivot (never seen in fp64; routine in fp32 once rho/R exceeds ~1e10) leaves no
   // usable direction: the step is skipped (d = 0 keeps the iterate) and the problem is flagged, instead of the
   // backend-specific garbage direction the reference would push through its line search.
+  bool ok = true;
+  for (int i = lane; i < L.N; i += 32) ok = ok && finite_(dv[i]);
+  ok = __all_sync(FULL, ok);
   for (int i = lane; i < L.N; i += 32) {
     const S d = ok ? -dv[i] : S(0);
     d_g[pN + i] = d;
