@@ -28,12 +28,14 @@ __device__ __forceinline__ void eliminate(S (&a)[NN], int lane, S* colbuf, int L
       const S lk = a[k] * inv;
       a[k] = (lane == k) ? inv : lk;
       if (k + 1 < NN) {
+        // the next pivot lives in lane k+1 and needs only that lane's own multiplier (col[k+1] == its lk): it is
+        // broadcast from registers, so the shared-memory round trip of the column is off the critical pivot chain
+        d = __shfl_sync(FULL, a[k + 1] - lk * lk, k + 1);
+        inv = rsqrt_(d);
         S* col = colbuf + (k & 1) * 32;
         if (lane < NN) col[lane] = lk;  // only rows k+1..NN-1 of the pivot column are read
         __syncwarp();
         a[k + 1] -= lk * col[k + 1];
-        d = __shfl_sync(FULL, a[k + 1], k + 1);
-        inv = rsqrt_(d);
         // rest of the pivot column: one scalar head (odd start), 16-byte pairs, one scalar tail (odd NN)
         constexpr bool kVec = !ALMPC_NO_VEC2;
         const int j0 = k + 2;
@@ -578,6 +580,410 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
     int status = (mode == MODE_FIRST) ? (ALMPC_STATUS_FINITE | ALMPC_STATUS_CHOL_OK) : status_g[prob];
     if (!ok) status &= ~ALMPC_STATUS_CHOL_OK;
     status_g[prob] = status;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 2/3, "pair" mapping for n <= 16 and nx + 1 <= 16 (pendulum, cartpoles, quadrotor):
+//   1 HALF-warp = 1 problem, 2 problems per warp, TWO matrix rows per lane:
+//     a[] = row hl of the SPD block (-> row of L)            b[] = rhs (hl = 0) / row hl-1 of -rho G_t (-> E_t)
+// Everything that is per-pivot overhead in the row-per-lane kernel above (pivot broadcast through shared memory,
+// the rsqrt chain, the diagonal shuffle, synchronisation) is issued once for two problems; the trailing updates
+// keep the same DFMA count per problem.  Measured on the elimination alone (tools/exp/elim_pair.cu): 1.5x.
+// Same inputs, outputs, factor layout and arithmetic per problem as k_factor_solve.
+// ------------------------------------------------------------------------------------------------
+template <int NN, typename S>
+__device__ __forceinline__ void eliminate_pair(S (&a)[NN], S (&b)[NN], int hl, int half, S* colbuf) {
+  // colbuf: this problem's 2 x 16 scalars (double-buffered pivot column)
+  S d = __shfl_sync(FULL, a[0], half * 16);
+  S inv = rsqrt_(d);
+#pragma unroll
+  for (int k = 0; k < NN; ++k) {
+    const S lk = a[k] * inv, mk = b[k] * inv;
+    a[k] = (hl == k) ? inv : lk;
+    b[k] = mk;
+    if (k + 1 < NN) {
+      // next pivot straight from lane k+1's registers (col[k+1] is that lane's own lk): the shared-memory
+      // round trip of the column stays off the critical pivot chain
+      d = __shfl_sync(FULL, a[k + 1] - lk * lk, half * 16 + k + 1);
+      inv = rsqrt_(d);
+      S* col = colbuf + (k & 1) * 16;
+      col[hl] = lk;
+      __syncwarp();
+      const S c1 = col[k + 1];
+      a[k + 1] -= lk * c1;
+      b[k + 1] -= mk * c1;
+      const int j0 = k + 2;
+      const int js = (j0 + 1) & ~1;
+      if ((j0 & 1) && j0 < NN) {
+        const S c = col[j0];
+        a[j0] -= lk * c;
+        b[j0] -= mk * c;
+      }
+#pragma unroll
+      for (int j = 0; j < NN; j += 2) {
+        if (j >= js && j + 1 < NN) {
+          const Vec2<S> v = *reinterpret_cast<const Vec2<S>*>(col + j);
+          a[j] -= lk * v.x;
+          a[j + 1] -= lk * v.y;
+          b[j] -= mk * v.x;
+          b[j + 1] -= mk * v.y;
+        }
+      }
+      if ((NN & 1) && (NN - 1) >= js) {
+        const S c = col[NN - 1];
+        a[NN - 1] -= lk * c;
+        b[NN - 1] -= mk * c;
+      }
+    }
+  }
+}
+
+template <typename S>
+__device__ __forceinline__ S half_sum(S v) {  // sum over the 16 lanes of a half-warp
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+template <int ROWS, int NN, int LB, typename S>
+__device__ __forceinline__ void half_copy_block_async(S* dst, const S* src, int hl) {
+  for (int e = hl; e < ROWS * NN; e += 16) {
+    const int r = e / NN, c = e - r * NN;
+    if constexpr (sizeof(S) == 8) cp_async8(dst + r * LB + c, src + e);
+    else cp_async4(dst + r * LB + c, src + e);
+  }
+}
+
+template <int NX, int NU, typename S, int WPB, int V>
+__global__ void __launch_bounds__(WPB * 32)
+k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restrict__ q_g,
+                    const S* __restrict__ xu_g, S* __restrict__ lam_g, S* __restrict__ rho_g, S* fac_g,
+                    const S* __restrict__ G_g, const S* __restrict__ c_g, S* __restrict__ d_g,
+                    S* __restrict__ merit_g, double* __restrict__ rentry_g, int* __restrict__ status_g,
+                    S* __restrict__ debug_g, const Ctl* __restrict__ ctl) {
+  constexpr int NN = NX + NU;
+  static_assert(NN <= 16 && NX + 1 <= 16, "pair mapping: both row sets must fit a half-warp");
+  constexpr int LD = ScrLd<NN>::LD;
+  constexpr int LB = NN | 1;
+  constexpr bool SE = (V == 2);
+  static_assert(V != 1, "obstacle rows are compiled for the row-per-lane kernel only");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  grid_dep_wait();
+  const int mode = ctl->mode;
+  if (mode == MODE_DONE) return;
+  const int T = P.T;
+  const Layout<NX, NU> L(T, 0, SE);
+  constexpr int SI = 2 * NU;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+  const int pw = (blockIdx.x * WPB + warp) * 2;  // first problem of this warp
+  if (pw >= P.B) return;
+  // an odd batch leaves the last half-warp without a problem: it recomputes its neighbour's and stores nothing
+  const bool live = pw + half < P.B;
+  const int prob = live ? pw + half : pw;
+  const int prob_of[2] = {pw, (pw + 1 < P.B) ? pw + 1 : pw};
+  S* smw = reinterpret_cast<S*>(smem_raw) + (size_t)warp * 2 * L.total;
+  S* sm = smw + (size_t)half * L.total;
+  S* xu = sm + L.xu;
+  S* dv = sm + L.dv;
+  S* wv = sm + L.w;
+  S* Gt = sm + L.Gt;
+  S* Ep = sm + L.Ep;
+  S* scr = sm + L.scr;
+  const size_t pN = (size_t)prob * L.N;
+  const S* Qd = Qd_g + pN;
+  const S* qv = q_g + pN;
+  S* lam = lam_g + (size_t)prob * L.m;
+  const S* cres = c_g + (size_t)prob * L.neq;
+  const S* Gp = G_g + (size_t)prob * (T - 1) * NX * NN;
+  S* fac = fac_g + (size_t)prob * factor_elems<NX, NU>(T);
+  S* dbg = (debug_g && live) ? debug_g + (size_t)prob * (2 * L.N + 24) : nullptr;
+
+  if (T > 1) half_copy_block_async<NX, NN, LB>(Gt, Gp, hl);
+  cp_async_commit();
+  S rho = rho_g[prob];
+  for (int base = 0; base < L.N; base += 64) {
+    S xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + hl + 16 * u;
+      xv[u] = (i < L.N) ? xu_g[pN + i] : S(0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + hl + 16 * u;
+      if (i < L.N) xu[i] = xv[u];
+    }
+  }
+  __syncwarp();
+
+  // ---- dual / penalty update of the previous AL iteration, entry residual, merit, w = lam_eq + rho c, cost gradient
+  const bool dual = (mode == MODE_DUAL_NEWTON);
+  const S rho_old = rho;
+  if (dual) rho = next_rho(rho, P.rho_mult, P.rho_f32);
+  {
+    S s2 = S(0), sl = S(0), cost = S(0);
+    for (int base = 0; base < L.neq; base += 64) {
+      S cv[4], lv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + hl + 16 * u;
+        cv[u] = (i < L.neq) ? cres[i] : S(0);
+        lv[u] = (i < L.neq) ? lam[i] : S(0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + hl + 16 * u;
+        if (i < L.neq) {
+          S li = lv[u];
+          if (dual) { li += rho_old * cv[u]; if (live) lam[i] = li; }
+          s2 += cv[u] * cv[u];
+          sl += li * cv[u];
+          wv[i] = li + rho * cv[u];
+        }
+      }
+    }
+    for (int base = 0; base < L.nin; base += 64) {
+      S lv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + hl + 16 * u;
+        lv[u] = (i < L.nin) ? lam[L.neq + i] : S(0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + hl + 16 * u;
+        if (i < L.nin) {
+          const int t = i / SI, sidx = i - t * SI;
+          const S ci = ineq_res<NX, NU, S>(xu + t * NN, sidx, P.ulo, P.uhi, nullptr, S(0));
+          S li = lv[u];
+          if (dual) { li = fmax0(li + rho_old * ci); if (live) lam[L.neq + i] = li; }
+          const S cp = fmax0(ci);
+          s2 += cp * cp;
+          sl += li * ci;
+        }
+      }
+    }
+    for (int base = 0; base < L.N; base += 64) {
+      S Qv[4], qq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + hl + 16 * u;
+        Qv[u] = (i < L.N) ? Qd[i] : S(0);
+        qq[u] = (i < L.N) ? qv[i] : S(0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + hl + 16 * u;
+        if (i < L.N) {
+          const S z = xu[i];
+          const bool in_cost = !SE || (i % NN) < NX;
+          if (in_cost) cost += S(0.5) * (z * Qv[u] * z) + qq[u] * z;
+          dv[i] = in_cost ? Qv[u] * z + qq[u] : S(0);
+        }
+      }
+    }
+    s2 = half_sum(s2);
+    sl = half_sum(sl);
+    cost = half_sum(cost);
+    if (hl == 0 && live) {
+      if (dual) rho_g[prob] = rho;
+      rentry_g[prob] = (double)s2;
+      if (mode != MODE_CONT) merit_g[prob] = cost + S(0.5) * rho * s2 + sl;
+    }
+  }
+  __syncwarp();
+
+  // ---- forward sweep
+  S* X = Gt;
+  S* Y = Ep;
+  const S rho_p[2] = {__shfl_sync(FULL, rho, 0), __shfl_sync(FULL, rho, 16)};
+  for (int t = 0; t < T; ++t) {
+    S* Lg = fac + (size_t)t * NN * NN;
+    S* Eg = fac + (size_t)T * NN * NN + (size_t)t * NX * NN;
+    const bool has_G = t < T - 1, has_E = t > 0;
+    cp_async_wait_all();
+    __syncwarp();
+    if (hl < NN) {
+      const int j = hl, idx = t * NN + j;
+      S g = dv[idx];
+      if (has_G) {
+        S s0 = S(0), s1 = S(0);
+#pragma unroll
+        for (int i = 0; i + 1 < NX; i += 2) {
+          s0 += X[i * LB + j] * wv[t * NX + i];
+          s1 += X[(i + 1) * LB + j] * wv[t * NX + i + 1];
+        }
+        if (NX & 1) s0 += X[(NX - 1) * LB + j] * wv[t * NX + NX - 1];
+        g -= s0 + s1;
+      }
+      if (j < NX) {
+        if (has_E) g += wv[(t - 1) * NX + j];
+        else if (!SE) g += wv[(T - 1) * NX + j];
+      } else if (!SE) {
+        const int sidx = j - NX;
+        const S u = xu[idx];
+        const S cu = u - P.uhi[sidx], cl = P.ulo[sidx] - u;
+        const S lu = lam[L.neq + t * SI + sidx], ll = lam[L.neq + t * SI + NU + sidx];
+        g += (lu - ll) + rho * (fmax0(cu) - fmax0(cl));
+      }
+      if (dbg) dbg[idx] = g;
+      if (has_E && j < NX) {
+        S s0 = S(0), s1 = S(0);
+#pragma unroll
+        for (int k = 0; k + 1 < NN; k += 2) {
+          s0 += Y[j * LB + k] * dv[(t - 1) * NN + k];
+          s1 += Y[j * LB + k + 1] * dv[(t - 1) * NN + k + 1];
+        }
+        if (NN & 1) s0 += Y[j * LB + NN - 1] * dv[(t - 1) * NN + NN - 1];
+        g -= s0 + s1;
+      }
+      dv[idx] = g;
+    }
+    // Hessian blocks of both problems: the DMMA assembly is warp-wide, one problem after the other
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      S* smp = smw + (size_t)p * L.total;
+      S* Xp = (X == Gt) ? smp + L.Gt : smp + L.Ep;
+      S* Yp = (X == Gt) ? smp + L.Ep : smp + L.Gt;
+      build_block<NX, NU, S>(smp + L.scr + 64, smp + L.xu + t * NN, Xp, Yp, has_G, has_E, lane, rho_p[p],
+                             Qd_g + (size_t)prob_of[p] * L.N + t * NN, P.ulo, P.uhi, !SE || has_E, !SE);
+    }
+    __syncwarp();
+    S a[NN], b[NN];
+    {
+      const int ei = hl - 1;
+      const bool e_act = (ei >= 0) && (ei < NX) && has_G;
+      const S* arow = scr + 64 + (hl < NN ? hl : 0) * LD;
+      const S* brow = (hl == 0) ? (dv + t * NN) : (X + (e_act ? ei : 0) * LB);
+      const S bscale = (hl == 0) ? S(1) : (e_act ? -rho : S(0));
+#pragma unroll
+      for (int c = 0; c < NN; ++c) {
+        a[c] = arow[c];
+        b[c] = brow[c] * bscale;
+      }
+      if (NN < 16 && hl >= NN) {  // lanes beyond the block: a harmless identity row
+#pragma unroll
+        for (int c = 0; c < NN; ++c) a[c] = S(0);
+      }
+    }
+    __syncwarp();
+    if (t + 1 < T - 1) half_copy_block_async<NX, NN, LB>(Y, Gp + (size_t)(t + 1) * NX * NN, hl);
+    cp_async_commit();
+    eliminate_pair<NN, S>(a, b, hl, half, scr);
+    __syncwarp();
+    {
+      const int ei = hl - 1;
+      const bool e_wr = (ei >= 0) && (ei < NX) && has_G;
+      if (hl < NN && live) {
+        S* gdst = Lg + hl * NN;
+        if constexpr (NN % 2 == 0) {
+#pragma unroll
+          for (int c = 0; c < NN; c += 2) {
+            Vec2<S> v;
+            v.x = (c <= hl) ? a[c] : S(0);
+            v.y = (c + 1 <= hl) ? a[c + 1] : S(0);
+            *reinterpret_cast<Vec2<S>*>(gdst + c) = v;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < NN; ++c) gdst[c] = (c <= hl) ? a[c] : S(0);
+        }
+      }
+      S* sdst = (hl == 0) ? (dv + t * NN) : (e_wr ? (X + ei * LB) : nullptr);
+      if (sdst) {
+#pragma unroll
+        for (int c = 0; c < NN; ++c) sdst[c] = b[c];
+      }
+      if (e_wr && live) {
+        S* gdst = Eg + ei * NN;
+        if constexpr (NN % 2 == 0) {
+#pragma unroll
+          for (int c = 0; c < NN; c += 2) {
+            Vec2<S> v;
+            v.x = b[c];
+            v.y = b[c + 1];
+            *reinterpret_cast<Vec2<S>*>(gdst + c) = v;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < NN; ++c) gdst[c] = b[c];
+        }
+      }
+    }
+    __syncwarp();
+    S* tmp = X; X = Y; Y = tmp;
+  }
+  // ---- backward sweep, d = -H^{-1} g: L_tt / E_t come back from the streamed factor through cp.async.
+  // A dead half-warp (odd batch) stored no factor: it reads its neighbour's, which is the same problem.
+  cp_async_wait_all();
+  __syncwarp();
+  S* Lsm = scr + 64;
+  S* Ecur = X;
+  S* Enext = Y;
+  constexpr int CW = CopyWidth<NX, NU, S>::W;
+  auto copy_L = [&](const S* src) {
+    constexpr int CHUNKS = NN * NN * (int)sizeof(S) / CW;
+    for (int ch = hl; ch < CHUNKS; ch += 16) {
+      if constexpr (CW == 16) cp_async16((char*)Lsm + ch * 16, (const char*)src + ch * 16);
+      else if constexpr (CW == 8) cp_async8((char*)Lsm + ch * 8, (const char*)src + ch * 8);
+      else cp_async4((char*)Lsm + ch * 4, (const char*)src + ch * 4);
+    }
+  };
+  copy_L(fac + (size_t)(T - 1) * NN * NN);
+  cp_async_commit();
+  for (int t = T - 1; t >= 0; --t) {
+    cp_async_wait_all();
+    __syncwarp();
+    S l[NN];
+    if (hl < NN) {
+#pragma unroll
+      for (int r = 0; r < NN; ++r) l[r] = Lsm[r * NN + hl];
+    } else {
+#pragma unroll
+      for (int r = 0; r < NN; ++r) l[r] = S(0);
+    }
+    S bb = (hl < NN) ? dv[t * NN + hl] : S(0);
+    if (t < T - 1 && hl < NN) {
+      S s0 = S(0), s1 = S(0);
+#pragma unroll
+      for (int i = 0; i + 1 < NX; i += 2) {
+        s0 += Ecur[i * LB + hl] * dv[(t + 1) * NN + i];
+        s1 += Ecur[(i + 1) * LB + hl] * dv[(t + 1) * NN + i + 1];
+      }
+      if (NX & 1) s0 += Ecur[(NX - 1) * LB + hl] * dv[(t + 1) * NN + NX - 1];
+      bb -= s0 + s1;
+    }
+    __syncwarp();
+    if (t > 0) {
+      copy_L(fac + (size_t)(t - 1) * NN * NN);
+      half_copy_block_async<NX, NN, LB>(Enext, fac + (size_t)T * NN * NN + (size_t)(t - 1) * NX * NN, hl);
+    }
+    cp_async_commit();
+#pragma unroll
+    for (int r = NN - 1; r >= 0; --r) {
+      const S dr = __shfl_sync(FULL, bb * l[r], half * 16 + r);
+      bb = (hl == r) ? dr : (bb - l[r] * dr);
+    }
+    if (hl < NN) dv[t * NN + hl] = bb;
+    S* tmp = Ecur; Ecur = Enext; Enext = tmp;
+  }
+  __syncwarp();
+  bool okl = true;
+  for (int i = hl; i < L.N; i += 16) okl = okl && finite_(dv[i]);
+  const unsigned okm = __ballot_sync(FULL, okl);
+  const bool ok = ((okm >> (half * 16)) & 0xffffu) == 0xffffu;
+  if (live) {
+    for (int i = hl; i < L.N; i += 16) {
+      const S d = ok ? -dv[i] : S(0);
+      d_g[pN + i] = d;
+      if (dbg) dbg[L.N + i] = d;
+    }
+    if (hl == 0) {
+      int status = (mode == MODE_FIRST) ? (ALMPC_STATUS_FINITE | ALMPC_STATUS_CHOL_OK) : status_g[prob];
+      if (!ok) status &= ~ALMPC_STATUS_CHOL_OK;
+      status_g[prob] = status;
+    }
   }
 }
 

@@ -168,6 +168,15 @@ static cudaError_t ls_warp_cfg(LsWarpCfg& c, int n_sm, int n_obs) {
   return cudaSuccess;
 }
 
+// the half-warp-per-problem factor kernel exists for blocks that fit a half-warp (n <= 16, nx + 1 <= 16) and
+// for the variants without obstacle rows
+constexpr int kWPP = 2;  // warps per CTA of the pair kernel (4 problems per CTA)
+template <int NX, int NU, typename S, int V>
+static auto pair_kernel() -> decltype(&k_factor_solve<NX, NU, S, kWPB, V>) {
+  if constexpr (NX + NU <= 16 && NX + 1 <= 16 && V != 1) return &k_factor_solve_pair<NX, NU, S, kWPP, V>;
+  else return nullptr;
+}
+
 template <class M, typename S, int V>
 static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* q, S* xu, S* lam, S* rho, S* factor,
                         float* x_out, float* u_out, S* dyn_res_out, int32_t* status_out, int32_t* info_out,
@@ -190,7 +199,15 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   if (smem_fac + 1024 > 227 * 1024 || smem_ls + 1024 > 227 * 1024)
     return set_err(-11, "horizon too long for the shared-memory layout");
   auto kjac = k_jacobian<M, S, V>;
-  auto kfac = k_factor_solve<NX, NU, S, kWPB, V>;
+  auto kfac = &k_factor_solve<NX, NU, S, kWPB, V>;
+  int fac_threads = kWPB * 32, fac_per_cta = kWPB;
+  if (auto kp = pair_kernel<NX, NU, S, V>(); kp && !getenv("ALMPC_FAC_SINGLE")) {  // env: A/B against the row-per-lane kernel
+    kfac = kp;
+    fac_threads = kWPP * 32;
+    fac_per_cta = 2 * kWPP;
+    smem_fac = (size_t)fac_per_cta * L.total * sizeof(S);
+    if (const char* pad = getenv("ALMPC_FAC_SMEM_PAD")) smem_fac += (size_t)atoi(pad);
+  }
   auto kls = k_line_search<M, S, V>;
   auto kfin = k_final_dual<M, S, kWPB, V>;
   cudaError_t e;
@@ -286,7 +303,7 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
       const int groups = (pt.n + lg.pls - 1) / lg.pls;
       pt.ls_grid = ls_grid < groups ? ls_grid : groups;
     }
-    pt.nb = n_blocks(pt.n);
+    pt.nb = (pt.n + fac_per_cta - 1) / fac_per_cta;
     pt.jac_blocks = (unsigned)(((long)pt.n * (T - 1) * (NN - M::NTRIV) + 127) / 128);
     pt.s = (np == 0) ? st : aux[np];
     pt.P = P;
@@ -331,7 +348,7 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
                c_g + lo * L.neq, ctl);
       toc();
       tic(1);
-      launch_k(kfac, pt.nb, kWPB * 32, smem_fac, pt.s, pdl, pt.P, Qd + lo * L.N, q + lo * L.N, xu + lo * L.N,
+      launch_k(kfac, pt.nb, fac_threads, smem_fac, pt.s, pdl, pt.P, Qd + lo * L.N, q + lo * L.N, xu + lo * L.N,
                lam + lo * L.m, rho + lo, factor + lo * FE, G_g + lo * GE, c_g + lo * L.neq, d_g + lo * L.N,
                merit + lo, rentry + lo, status + lo, dbg, ctl);
       toc();
