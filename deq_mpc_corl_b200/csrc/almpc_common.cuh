@@ -171,7 +171,7 @@ template <int NX, int NU>
 struct Layout {
   static constexpr int NN = NX + NU;
   int N, neq, nin, m, SI;
-  int xu, dv, w, Gt, Ep, scr, total;
+  int xu, dv, w, lin, qd, Gt, Ep, scr, total;
   __host__ __device__ Layout(int T, int nobs = 0, bool se = false) {
     // inequality rows per stage: control bounds, then obstacle rows.  State-estimator variant
     // (al_utils_se.py): the T-1 dynamics blocks only
@@ -182,6 +182,8 @@ struct Layout {
     xu = take(N);
     dv = take(N);
     w = take(neq);
+    lin = take(nin);  // inequality multipliers and the cost diagonal: read once from HBM in the prologue, then
+    qd = take(N);     // per stage from shared memory (a global load inside the stage loop stalls the whole chain)
     // n = 16 (row stride 17): the nx staged rows of G / E sit on nx consecutive 8-byte bank pairs; place both
     // buffers so that the right-hand-side row (dv + t*n), moved by the same instructions, lands on the next one
     constexpr bool kAlign = (NN % 16 == 0) && (NX % 4 == 0) && (NX < 16);

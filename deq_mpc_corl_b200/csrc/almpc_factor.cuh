@@ -655,8 +655,9 @@ __device__ __forceinline__ void half_copy_block_async(S* dst, const S* src, int 
   }
 }
 
+// small blocks keep little in shared memory, so their occupancy is set by registers: cap them for 12 CTAs / SM
 template <int NX, int NU, typename S, int WPB, int V>
-__global__ void __launch_bounds__(WPB * 32)
+__global__ void __launch_bounds__(WPB * 32, (NX + NU <= 8) ? 12 : 6)
 k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restrict__ q_g,
                     const S* __restrict__ xu_g, S* __restrict__ lam_g, S* __restrict__ rho_g, S* fac_g,
                     const S* __restrict__ G_g, const S* __restrict__ c_g, S* __restrict__ d_g,
@@ -681,12 +682,13 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
   // an odd batch leaves the last half-warp without a problem: it recomputes its neighbour's and stores nothing
   const bool live = pw + half < P.B;
   const int prob = live ? pw + half : pw;
-  const int prob_of[2] = {pw, (pw + 1 < P.B) ? pw + 1 : pw};
   S* smw = reinterpret_cast<S*>(smem_raw) + (size_t)warp * 2 * L.total;
   S* sm = smw + (size_t)half * L.total;
   S* xu = sm + L.xu;
   S* dv = sm + L.dv;
   S* wv = sm + L.w;
+  S* lin = sm + L.lin;
+  S* qds = sm + L.qd;
   S* Gt = sm + L.Gt;
   S* Ep = sm + L.Ep;
   S* scr = sm + L.scr;
@@ -702,6 +704,18 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
   if (T > 1) half_copy_block_async<NX, NN, LB>(Gt, Gp, hl);
   cp_async_commit();
   S rho = rho_g[prob];
+  // first round (64 entries per half-warp) of every input array is issued before anything is consumed: one HBM
+  // round trip instead of one per array
+  S p_c[4], p_l[4], p_li[4], p_Q[4], p_q[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = hl + 16 * u;
+    p_c[u] = (i < L.neq) ? cres[i] : S(0);
+    p_l[u] = (i < L.neq) ? lam[i] : S(0);
+    p_li[u] = (i < L.nin) ? lam[L.neq + i] : S(0);
+    p_Q[u] = (i < L.N) ? Qd[i] : S(0);
+    p_q[u] = (i < L.N) ? qv[i] : S(0);
+  }
   for (int base = 0; base < L.N; base += 64) {
     S xv[4];
 #pragma unroll
@@ -728,8 +742,8 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int i = base + hl + 16 * u;
-        cv[u] = (i < L.neq) ? cres[i] : S(0);
-        lv[u] = (i < L.neq) ? lam[i] : S(0);
+        cv[u] = (base == 0) ? p_c[u] : ((i < L.neq) ? cres[i] : S(0));
+        lv[u] = (base == 0) ? p_l[u] : ((i < L.neq) ? lam[i] : S(0));
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -748,7 +762,7 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int i = base + hl + 16 * u;
-        lv[u] = (i < L.nin) ? lam[L.neq + i] : S(0);
+        lv[u] = (base == 0) ? p_li[u] : ((i < L.nin) ? lam[L.neq + i] : S(0));
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -758,6 +772,7 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
           const S ci = ineq_res<NX, NU, S>(xu + t * NN, sidx, P.ulo, P.uhi, nullptr, S(0));
           S li = lv[u];
           if (dual) { li = fmax0(li + rho_old * ci); if (live) lam[L.neq + i] = li; }
+          lin[i] = li;
           const S cp = fmax0(ci);
           s2 += cp * cp;
           sl += li * ci;
@@ -769,8 +784,8 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int i = base + hl + 16 * u;
-        Qv[u] = (i < L.N) ? Qd[i] : S(0);
-        qq[u] = (i < L.N) ? qv[i] : S(0);
+        Qv[u] = (base == 0) ? p_Q[u] : ((i < L.N) ? Qd[i] : S(0));
+        qq[u] = (base == 0) ? p_q[u] : ((i < L.N) ? qv[i] : S(0));
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -780,6 +795,7 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
           const bool in_cost = !SE || (i % NN) < NX;
           if (in_cost) cost += S(0.5) * (z * Qv[u] * z) + qq[u] * z;
           dv[i] = in_cost ? Qv[u] * z + qq[u] : S(0);
+          qds[i] = Qv[u];
         }
       }
     }
@@ -824,7 +840,7 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
         const int sidx = j - NX;
         const S u = xu[idx];
         const S cu = u - P.uhi[sidx], cl = P.ulo[sidx] - u;
-        const S lu = lam[L.neq + t * SI + sidx], ll = lam[L.neq + t * SI + NU + sidx];
+        const S lu = lin[t * SI + sidx], ll = lin[t * SI + NU + sidx];
         g += (lu - ll) + rho * (fmax0(cu) - fmax0(cl));
       }
       if (dbg) dbg[idx] = g;
@@ -847,7 +863,7 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
       S* Xp = (X == Gt) ? smp + L.Gt : smp + L.Ep;
       S* Yp = (X == Gt) ? smp + L.Ep : smp + L.Gt;
       build_block<NX, NU, S>(smp + L.scr + 64, smp + L.xu + t * NN, Xp, Yp, has_G, has_E, lane, rho_p[p],
-                             Qd_g + (size_t)prob_of[p] * L.N + t * NN, P.ulo, P.uhi, !SE || has_E, !SE);
+                             smp + L.qd + t * NN, P.ulo, P.uhi, !SE || has_E, !SE);
     }
     __syncwarp();
     S a[NN], b[NN];
