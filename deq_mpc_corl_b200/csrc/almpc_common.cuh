@@ -172,7 +172,7 @@ struct Layout {
   static constexpr int NN = NX + NU;
   int N, neq, nin, m, SI;
   int xu, dv, w, lin, qd, Gt, Ep, scr, total;
-  __host__ __device__ Layout(int T, int nobs = 0, bool se = false) {
+  __host__ __device__ Layout(int T, int nobs = 0, bool se = false, bool staged = false) {
     // inequality rows per stage: control bounds, then obstacle rows.  State-estimator variant
     // (al_utils_se.py): the T-1 dynamics blocks only
     SI = se ? 0 : 2 * NU + nobs;
@@ -182,8 +182,10 @@ struct Layout {
     xu = take(N);
     dv = take(N);
     w = take(neq);
-    lin = take(nin);  // inequality multipliers and the cost diagonal: read once from HBM in the prologue, then
-    qd = take(N);     // per stage from shared memory (a global load inside the stage loop stalls the whole chain)
+    // pair kernel only: inequality multipliers and the cost diagonal are read once from HBM in the prologue and
+    // then per stage from shared memory (a global load inside the stage loop stalls the whole chain)
+    lin = staged ? take(nin) : 0;
+    qd = staged ? take(N) : 0;
     // n = 16 (row stride 17): the nx staged rows of G / E sit on nx consecutive 8-byte bank pairs; place both
     // buffers so that the right-hand-side row (dv + t*n), moved by the same instructions, lands on the next one
     constexpr bool kAlign = (NN % 16 == 0) && (NX % 4 == 0) && (NX < 16);

@@ -674,7 +674,7 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
   const int mode = ctl->mode;
   if (mode == MODE_DONE) return;
   const int T = P.T;
-  const Layout<NX, NU> L(T, 0, SE);
+  const Layout<NX, NU> L(T, 0, SE, true);
   constexpr int SI = 2 * NU;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
   const int pw = (blockIdx.x * WPB + warp) * 2;  // first problem of this warp

@@ -205,8 +205,9 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
     kfac = kp;
     fac_threads = kWPP * 32;
     fac_per_cta = 2 * kWPP;
-    smem_fac = (size_t)fac_per_cta * L.total * sizeof(S);
+    smem_fac = (size_t)fac_per_cta * Layout<NX, NU>(T, 0, SE, true).total * sizeof(S);
     if (const char* pad = getenv("ALMPC_FAC_SMEM_PAD")) smem_fac += (size_t)atoi(pad);
+    if (smem_fac + 1024 > 227 * 1024) return set_err(-11, "horizon too long for the shared-memory layout");
   }
   auto kls = k_line_search<M, S, V>;
   auto kfin = k_final_dual<M, S, kWPB, V>;
