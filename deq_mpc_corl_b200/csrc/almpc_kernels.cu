@@ -195,7 +195,9 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   if (const char* pad = getenv("ALMPC_FAC_SMEM_PAD")) smem_fac += (size_t)atoi(pad);  // occupancy experiments
   size_t smem_ls = 2 * (size_t)lg.pls * LL.total * sizeof(S);  // double-buffered staging
   if (smem_ls < (size_t)lg.threads * 3 * sizeof(double)) smem_ls = (size_t)lg.threads * 3 * sizeof(double);
-  const size_t smem_fin = (size_t)kWPB * (L.N + L.neq) * sizeof(S);
+  int fin_ppw = 32 / (T - 1);  // problems per warp of the final kernel: its threads share the (problem, stage) items
+  fin_ppw = fin_ppw < 1 ? 1 : (fin_ppw > 8 ? 8 : fin_ppw);
+  const size_t smem_fin = (size_t)kWPB * fin_ppw * (L.N + L.neq) * sizeof(S);
   if (smem_fac + 1024 > 227 * 1024 || smem_ls + 1024 > 227 * 1024)
     return set_err(-11, "horizon too long for the shared-memory layout");
   auto kjac = k_jacobian<M, S, V>;
@@ -321,7 +323,6 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
     if (e != cudaSuccess) return cuda_err(e, "cudaEventRecord");
     for (int p = 1; p < np; ++p) cudaStreamWaitEvent(parts[p].s, ev_fork, 0);
   }
-  const int nb = n_blocks(B);
   const int launches = d->al_iter * d->max_newton;
   const bool pdl = !prof_requested && np == 1 && getenv("ALMPC_PDL");  // measured: no gain on B200, off by default
   ProfEv pe[3 * ALMPC_MAX_AL_ITER * 8 + 1];
@@ -389,7 +390,8 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
     }
   }
   tic(3);
-  launch_k(kfin, nb, kWPB * 32, smem_fin, st, pdl, P, x0, xu, lam, rho, x_out, u_out, dyn_res_out, info_out, ctl);
+  launch_k(kfin, (B + kWPB * fin_ppw - 1) / (kWPB * fin_ppw), kWPB * 32, smem_fin, st, pdl, P, x0, xu, lam, rho, x_out,
+           u_out, dyn_res_out, info_out, ctl, fin_ppw);
   toc();
   if (prof) {  // profiling mode synchronises (never used on the timed path)
     cudaStreamSynchronize(st);

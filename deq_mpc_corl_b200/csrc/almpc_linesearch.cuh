@@ -512,7 +512,9 @@ template <class M, typename S, int WPB, int V>
 __global__ void __launch_bounds__(WPB * 32)
 k_final_dual(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__ xu_g, S* __restrict__ lam_g,
              S* __restrict__ rho_g, float* __restrict__ x_out, float* __restrict__ u_out, S* __restrict__ dyn_res_g,
-             int* __restrict__ info_g, Ctl* ctl) {
+             int* __restrict__ info_g, Ctl* ctl, const int ppw) {
+  // a CTA owns WPB * ppw consecutive problems: the (problem, stage) dynamics evaluations are spread over all its
+  // threads (one warp per problem left 28 of 32 lanes idle at T = 5), then each warp finishes ppw problems
   constexpr int NX = M::NX, NU = M::NU, NN = NX + NU;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = P.T;
@@ -520,20 +522,27 @@ k_final_dual(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict
   const int n_obs = OBS ? P.n_obs : 0;
   const Layout<NX, NU> L(T, n_obs, SE);
   const int SI = OBS ? L.SI : 2 * NU;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int prob = blockIdx.x * WPB + warp;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int per_cta = WPB * ppw;
+  const int prob0 = blockIdx.x * per_cta;
+  const int np = (P.B - prob0 < per_cta) ? P.B - prob0 : per_cta;
   grid_dep_wait();
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && tid == 0) {
     info_g[ALMPC_INFO_RHO_EXCEEDED] = (ctl->rho_final_max > P.rho_max) ? 1 : 0;
   }
-  if (prob >= P.B) return;
-  S* sm = reinterpret_cast<S*>(smem_raw) + (size_t)warp * (L.N + L.neq);
-  S* xu = sm;
-  S* cres = sm + L.N;
-  const size_t pN = (size_t)prob * L.N;
-  for (int i = lane; i < L.N; i += 32) xu[i] = xu_g[pN + i];
-  __syncwarp();
-  for (int t = lane; t < T - 1; t += 32) {
+  if (np <= 0) return;
+  const int stride = L.N + L.neq;
+  S* sm = reinterpret_cast<S*>(smem_raw);
+  for (int e = tid; e < np * L.N; e += nthr) {
+    const int p = e / L.N;
+    sm[p * stride + (e - p * L.N)] = xu_g[(size_t)prob0 * L.N + e];
+  }
+  __syncthreads();
+  for (int it = tid; it < np * (T - 1); it += nthr) {
+    const int p = it / (T - 1), t = it - p * (T - 1);
+    const S* xu = sm + p * stride;
+    S* cres = sm + p * stride + L.N;
     S xs[NX], us[NU], xn[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) xs[i] = xu[t * NN + i];
@@ -543,41 +552,50 @@ k_final_dual(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict
 #pragma unroll
     for (int i = 0; i < NX; ++i) cres[t * NX + i] = xu[(t + 1) * NN + i] - xn[i];
   }
-  if (!SE)
-    for (int i = lane; i < NX; i += 32) cres[(T - 1) * NX + i] = xu[i] - x0_g[(size_t)prob * NX + i];
-  __syncwarp();
-  const S rho = rho_g[prob];
-  S* lamp = lam_g + (size_t)prob * L.m;
-  const bool upd = !(P.flags & ALMPC_FLAG_SKIP_FINAL_DUAL);
-  S s2 = S(0);
-  for (int i = lane; i < L.neq; i += 32) {
-    S ci = cres[i];
-    if (upd) lamp[i] += rho * ci;
-    s2 += ci * ci;
-  }
-  const S* obs = OBS ? P.obs + (size_t)prob * T * n_obs * 3 : nullptr;
-  for (int i = lane; i < L.nin; i += 32) {
-    const int t = i / SI, s = i - t * SI;
-    const S ci = ineq_res<NX, NU, S>(xu + t * NN, s, P.ulo, P.uhi, OBS ? obs + (size_t)t * n_obs * 3 : nullptr, P.obs_r2);
-    if (upd) lamp[L.neq + i] = fmax0(lamp[L.neq + i] + rho * ci);
-    S cp = fmax0(ci);
-    s2 += cp * cp;
-  }
-  s2 = warp_sum(s2);
-  if (lane == 0) {
-    if (upd) rho_g[prob] = next_rho(rho, P.rho_mult, P.rho_f32);
-    if (dyn_res_g) dyn_res_g[prob] = sqrt(s2);
-  }
-  if (x_out) {
-    for (int i = lane; i < T * NX; i += 32) {
-      int t = i / NX, j = i - t * NX;
-      x_out[(size_t)prob * T * NX + i] = (float)xu[t * NN + j];
+  if (!SE) {
+    for (int e = tid; e < np * NX; e += nthr) {
+      const int p = e / NX, i = e - p * NX;
+      sm[p * stride + L.N + (T - 1) * NX + i] = sm[p * stride + i] - x0_g[(size_t)(prob0 + p) * NX + i];
     }
   }
-  if (u_out) {
-    for (int i = lane; i < T * NU; i += 32) {
-      int t = i / NU, j = i - t * NU;
-      u_out[(size_t)prob * T * NU + i] = (float)xu[t * NN + NX + j];
+  __syncthreads();
+  const bool upd = !(P.flags & ALMPC_FLAG_SKIP_FINAL_DUAL);
+  for (int p = warp; p < np; p += WPB) {
+    const int prob = prob0 + p;
+    const S* xu = sm + p * stride;
+    const S* cres = xu + L.N;
+    const S rho = rho_g[prob];
+    S* lamp = lam_g + (size_t)prob * L.m;
+    S s2 = S(0);
+    for (int i = lane; i < L.neq; i += 32) {
+      const S ci = cres[i];
+      if (upd) lamp[i] += rho * ci;
+      s2 += ci * ci;
+    }
+    const S* obs = OBS ? P.obs + (size_t)prob * T * n_obs * 3 : nullptr;
+    for (int i = lane; i < L.nin; i += 32) {
+      const int t = i / SI, sx = i - t * SI;
+      const S ci = ineq_res<NX, NU, S>(xu + t * NN, sx, P.ulo, P.uhi, OBS ? obs + (size_t)t * n_obs * 3 : nullptr, P.obs_r2);
+      if (upd) lamp[L.neq + i] = fmax0(lamp[L.neq + i] + rho * ci);
+      const S cp = fmax0(ci);
+      s2 += cp * cp;
+    }
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      if (upd) rho_g[prob] = next_rho(rho, P.rho_mult, P.rho_f32);
+      if (dyn_res_g) dyn_res_g[prob] = sqrt(s2);
+    }
+    if (x_out) {
+      for (int i = lane; i < T * NX; i += 32) {
+        const int t = i / NX, j = i - t * NX;
+        x_out[(size_t)prob * T * NX + i] = (float)xu[t * NN + j];
+      }
+    }
+    if (u_out) {
+      for (int i = lane; i < T * NU; i += 32) {
+        const int t = i / NU, j = i - t * NU;
+        u_out[(size_t)prob * T * NU + i] = (float)xu[t * NN + NX + j];
+      }
     }
   }
 }
