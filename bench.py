@@ -87,7 +87,7 @@ def algorithmic_bytes(model, T, esize):
 
 # DRAM traffic per launch measured once with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum),
 # profiles/r01_v6_three_kernels_ncu_full_summary.csv — only valid for the exact workload it was captured on.
-NCU_TRAFFIC = {("rex_quadrotor", 5, 65536, "f64"): {"k_jacobian": 48.37e6 + 375.15e6, "k_factor_solve": 665.39e6 + 1075.69e6,
+NCU_TRAFFIC = {("rex_quadrotor", 5, 65536, "f64"): {"k_jacobian": 48.37e6 + 375.15e6, "k_factor_solve": 629.38e6 + 1063.53e6,  # k_factor_solve_pair, profiles/r01_v11_*
                                                     "k_line_search": 228.87e6 + 31.84e6}}
 
 
