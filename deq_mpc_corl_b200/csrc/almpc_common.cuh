@@ -78,6 +78,9 @@ __device__ __forceinline__ double rsqrt_(double x) {
 }
 __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
 template <typename S> __device__ __forceinline__ S fmax0(S x) { return x > S(0) ? x : S(0); }
+// one entry of the quadratic cost (al_utils.py:425-435), 1/2 Q z^2 + q z as z (1/2 (Q z) + q): one multiply and two
+// fused multiply-adds.  Every kernel that evaluates a merit uses THIS form, so entry merit and candidates agree.
+template <typename S> __device__ __forceinline__ S cost_term(S z, S Q, S q) { return z * (S(0.5) * (Q * z) + q); }
 template <typename S> __device__ __forceinline__ bool finite_(S x) { return (x - x) == S(0); }
 
 // Programmatic dependent launch: the step kernels are launched with stream serialization relaxed, so a kernel's

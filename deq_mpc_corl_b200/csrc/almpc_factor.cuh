@@ -344,7 +344,7 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
           const S z = xu[i];
           // state estimator: cost and cost gradient see the states only (al_utils_se.py:272-305)
           const bool in_cost = !SE || (i % NN) < NX;
-          if (in_cost) cost += S(0.5) * (z * Qv[u] * z) + qq[u] * z;
+          if (in_cost) cost += cost_term(z, Qv[u], qq[u]);
           dv[i] = in_cost ? Qv[u] * z + qq[u] : S(0);  // cost gradient (al_utils.py:438-446), completed per stage below
         }
       }
@@ -793,7 +793,7 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
         if (i < L.N) {
           const S z = xu[i];
           const bool in_cost = !SE || (i % NN) < NX;
-          if (in_cost) cost += S(0.5) * (z * Qv[u] * z) + qq[u] * z;
+          if (in_cost) cost += cost_term(z, Qv[u], qq[u]);
           dv[i] = in_cost ? Qv[u] * z + qq[u] : S(0);
           qds[i] = Qv[u];
         }

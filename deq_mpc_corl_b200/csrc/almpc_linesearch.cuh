@@ -83,14 +83,14 @@ __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU
     for (int i = 0; i < NX; ++i) {
       const S z = xu[t * LS + i] + alpha * dv[t * LS + i];
       xs[i] = z;
-      cost += S(0.5) * (z * Qd[t * LS + i] * z) + qv[t * LS + i] * z;
+      cost += cost_term(z, Qd[t * LS + i], qv[t * LS + i]);
     }
 #pragma unroll
     for (int i = 0; i < NU; ++i) {
       const S z = xu[t * LS + NX + i] + alpha * dv[t * LS + NX + i];
       us[i] = z;
       if (!SE) {
-        cost += S(0.5) * (z * Qd[t * LS + NX + i] * z) + qv[t * LS + NX + i] * z;
+        cost += cost_term(z, Qd[t * LS + NX + i], qv[t * LS + NX + i]);
         const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
         sl += lam[L.neq + t * SI + i] * cu + lam[L.neq + t * SI + NU + i] * cl;
         const S pu = fmax0(cu), pl = fmax0(cl);
@@ -123,14 +123,14 @@ __device__ __forceinline__ void ls_item(const S* sp, const LsLayout<M::NX, M::NU
       s2 += ci * ci;
       sl += lam[t * NX + i] * ci;
       if (OBS && i < 3) zlast[i] = z1;
-      if (t == T - 2) cost += S(0.5) * (z1 * Qd[(t + 1) * LS + i] * z1) + qv[(t + 1) * LS + i] * z1;
+      if (t == T - 2) cost += cost_term(z1, Qd[(t + 1) * LS + i], qv[(t + 1) * LS + i]);
     }
     if (!SE && t == T - 2) {
 #pragma unroll
       for (int i = 0; i < NU; ++i) {
         const int e = (T - 1) * LS + NX + i;
         const S z = xu[e] + alpha * dv[e];
-        cost += S(0.5) * (z * Qd[e] * z) + qv[e] * z;
+        cost += cost_term(z, Qd[e], qv[e]);
         const S cu = z - P.uhi[i], cl = P.ulo[i] - z;
         sl += lam[L.neq + (T - 1) * SI + i] * cu + lam[L.neq + (T - 1) * SI + NU + i] * cl;
         const S pu = fmax0(cu), pl = fmax0(cl);

@@ -51,6 +51,16 @@ template <typename S> __device__ __forceinline__ void sincos_(Dual<S> a, Dual<S>
   s = {sv, cv * a.d};
   c = {cv, -sv * a.d};
 }
+// v + 2 t with one fused multiply-add (2 t is exact, so this is bit-identical to v + (t + t))
+template <typename T, typename W> __device__ __forceinline__ T twice_plus(T t, W v) { return v + (t + t); }
+#ifndef ALMPC_MODELS_NO_CUDA
+__device__ __forceinline__ double twice_plus(double t, double v) { return fma(2.0, t, v); }
+__device__ __forceinline__ float twice_plus(float t, float v) { return fmaf(2.0f, t, v); }
+template <typename S> __device__ __forceinline__ Dual<S> twice_plus(Dual<S> t, Dual<S> v) {
+  return {twice_plus(t.v, v.v), twice_plus(t.d, v.d)};
+}
+template <typename S> __device__ __forceinline__ Dual<S> twice_plus(Dual<S> t, S v) { return {twice_plus(t.v, v), t.d + t.d}; }
+#endif
 template <typename S> __device__ __forceinline__ S value_of(S a) { return a; }
 template <typename S> __device__ __forceinline__ S value_of(Dual<S> a) { return a.v; }
 
@@ -84,7 +94,7 @@ __device__ __forceinline__ void quatrot(V w, const V* r, const W* v, V* o) {
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     V t = w * rv[i] + rrv[i];
-    o[i] = v[i] + (t + t);
+    o[i] = twice_plus(t, v[i]);
   }
 }
 
@@ -127,9 +137,10 @@ __device__ __forceinline__ void quad_body(const V* m, const V* v, const V* w, co
     V mw = m[0] * w[0] + m[1] * w[1] + m[2] * w[2];
     V mxw[3];
     cross3(m, w, mxw);
-    V a = S(1) - n2;
+    // 1/4 (a w + 2 (m x w + (m.w) m)) with the exact power-of-two scalings folded in: a/4 w + (m x w + (m.w) m)/2
+    V a4 = (S(1) - n2) * S(0.25);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) mdot[i] = (a * w[i] + (mxw[i] + mw * m[i]) * S(2)) * S(0.25);
+    for (int i = 0; i < 3; ++i) mdot[i] = a4 * w[i] + (mxw[i] + mw * m[i]) * S(0.5);
   }
   quatrot(q0, qv, v, pdot);
   {
