@@ -33,7 +33,7 @@ from deq_mpc_corl_b200.problems import MODEL_SPECS, make_inputs, tracking_cost  
 
 # F_dyn: flops of one RK4 step of each model's ODE as written in csrc/almpc_models.cuh, counted by
 # tools/count_flops.cpp (add/sub/mul = 1, fma = 2, reciprocal = 1, sincos = 2).  Frozen here.
-F_DYN = {"pendulum": 50, "cartpole1l": 120, "cartpole2l": 322, "rex_quadrotor": 988, "flying_cartpole": 1158}
+F_DYN = {"pendulum": 50, "cartpole1l": 120, "cartpole2l": 322, "rex_quadrotor": 980, "flying_cartpole": 1150}
 
 
 def algorithmic_flops(model, T):

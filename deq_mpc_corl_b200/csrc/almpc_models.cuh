@@ -106,8 +106,9 @@ __device__ __forceinline__ void quad_body(const V* m, const V* v, const V* w, co
   V n2 = m[0] * m[0] + m[1] * m[1] + m[2] * m[2];
   V den = recip(n2 + S(1));
   q0 = (S(1) - n2) * den;
+  V den2 = den + den;  // exact doubling: (2 m) den == m (2 den)
 #pragma unroll
-  for (int i = 0; i < 3; ++i) qv[i] = (m[i] * S(2)) * den;
+  for (int i = 0; i < 3; ++i) qv[i] = m[i] * den2;
   // controls: u <- act_scale * (u + u_hover)
   V us[4];
 #pragma unroll

@@ -12,5 +12,5 @@ for R,jac in [(65536*4, True), (65536*80, False)]:
         else: dyn(x,u)
         e1.record(); torch.cuda.synchronize()
     ms=e0.elapsed_time(e1)
-    flops = R*(16*3*988 if jac else 988)
+    flops = R*(16*3*980 if jac else 980)
     print(f"R={R} jac={jac}: {ms:.3f} ms  -> {flops/ms/1e9:.2f} TFLOP/s (dual counted as 3x primal)")
