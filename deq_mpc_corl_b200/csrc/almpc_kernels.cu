@@ -204,12 +204,29 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   auto kfac = &k_factor_solve<NX, NU, S, kWPB, V>;
   int fac_threads = kWPB * 32, fac_per_cta = kWPB;
   if (auto kp = pair_kernel<NX, NU, S, V>(); kp && !getenv("ALMPC_FAC_SINGLE")) {  // env: A/B against the row-per-lane kernel
-    kfac = kp;
-    fac_threads = kWPP * 32;
-    fac_per_cta = 2 * kWPP;
-    smem_fac = (size_t)fac_per_cta * Layout<NX, NU>(T, 0, SE, true).total * sizeof(S);
-    if (const char* pad = getenv("ALMPC_FAC_SMEM_PAD")) smem_fac += (size_t)atoi(pad);
-    if (smem_fac + 1024 > 227 * 1024) return set_err(-11, "horizon too long for the shared-memory layout");
+    // Both kernels are bound by (latency of one problem) / (problems resident per SM): take the pair kernel
+    // unless its larger shared-memory footprint (long horizons) leaves it with clearly fewer resident problems.
+    const size_t smem_pair = (size_t)2 * kWPP * Layout<NX, NU>(T, 0, SE, true).total * sizeof(S);
+    int occ_single = 0, occ_pair = 0;
+    bool use_pair = smem_pair + 1024 <= 227 * 1024;
+    if (use_pair) {
+      cudaError_t e1 = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair);
+      cudaError_t e2 = cudaFuncSetAttribute(kfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fac);
+      if (e1 == cudaSuccess && e2 == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pair, kp, kWPP * 32, smem_pair) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_single, kfac, kWPB * 32, smem_fac) == cudaSuccess)
+        use_pair = occ_pair * 2 * kWPP * 5 >= occ_single * kWPB * 4;  // pair wins down to 0.8x the resident problems
+      else
+        (void)cudaGetLastError();
+    }
+    if (getenv("ALMPC_FAC_PAIR")) use_pair = smem_pair + 1024 <= 227 * 1024;
+    if (use_pair) {
+      kfac = kp;
+      fac_threads = kWPP * 32;
+      fac_per_cta = 2 * kWPP;
+      smem_fac = smem_pair;
+      if (const char* pad = getenv("ALMPC_FAC_SMEM_PAD")) smem_fac += (size_t)atoi(pad);
+    }
   }
   auto kls = k_line_search<M, S, V>;
   auto kfin = k_final_dual<M, S, kWPB, V>;
