@@ -8,7 +8,9 @@
 //
 //   k_jacobian      1 thread = 1 (problem, stage t, tangent column j): dynamics + Jacobians G_t=[A_t B_t]
 //                   by forward-mode duals, residuals c_t                                       al_utils.py:233-265
-//   k_factor_solve  1 warp = 1 problem (~28 warps/SM): residual statistics, (optional) dual/penalty update of
+//   k_factor_solve(_pair)  1 warp = 1 problem (row per lane), or for blocks up to 16 wide 1 half-warp = 1 problem
+//                   (two rows per lane, the default for pendulum / cartpoles / quadrotor): residual statistics,
+//                   (optional) dual/penalty update of
 //                   the previous AL iteration (AL_mpc.py:315-325), merit (al_utils.py:52-77), gradient
 //                   (:113-117), block-tridiagonal Cholesky of H = diag(Qd) + rho Jc^T Jc and both triangular
 //                   sweeps (:119-120, 510-515; the reference factors the dense matrix, H is exactly block
