@@ -169,7 +169,14 @@ class MPC(Module):
 
     # ------------------------------------------------------------------------------------------
     def rollout(self, x, actions, dynamics):
-        """AL_mpc.py:521-534 with the native functor (or the user's callable in generic mode)."""
+        """AL_mpc.py:521-534 with the native functor (or the user's callable in generic mode); a ``LinDx(F, f)``
+        rolls out the time-varying linear model ``x+ = F_t [x; u] + f_t`` like the reference (:527-529)."""
+        if isinstance(dynamics, LinDx):
+            xs = [x]
+            for t in range(self.T - 1):
+                z = torch.cat([xs[t], actions[:, t]], dim=-1)
+                xs.append(torch.bmm(dynamics.F[:, t], z.unsqueeze(-1)).squeeze(-1) + dynamics.f[:, t])
+            return torch.stack(xs, 1)
         try:
             dyn = resolve(dynamics)
         except _lib.AlmpcError:

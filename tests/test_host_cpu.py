@@ -114,6 +114,21 @@ def test_mpc_state_semantics_and_cpu_refusal():
     assert se.lamda_prev.shape == (6, 16)
 
 
+def test_rollout_with_lindx_matches_reference_formula():
+    from deq_mpc_corl_b200.al_utils import LinDx
+
+    g = torch.Generator().manual_seed(4)
+    B, T, nx, nu = 3, 4, 2, 1
+    F, f = torch.randn(B, T - 1, nx, nx + nu, generator=g), torch.randn(B, T - 1, nx, generator=g)
+    x0, u = torch.randn(B, nx, generator=g), torch.randn(B, T, nu, generator=g)
+    ctrl = MPC(nx, nu, T, u_lower=torch.tensor([-1.0]), u_upper=torch.tensor([1.0]), n_batch=B)
+    xs = ctrl.rollout(x0, u, LinDx(F, f))
+    assert xs.shape == (B, T, nx) and torch.equal(xs[:, 0], x0)
+    for t in range(T - 1):  # AL_mpc.py:527-529: new_x = bmv(F[:, t], cat[x_t, u_t]) + f[:, t]
+        ref = torch.einsum("bij,bj->bi", F[:, t], torch.cat([xs[:, t], u[:, t]], -1)) + f[:, t]
+        assert torch.allclose(xs[:, t + 1], ref, atol=1e-6)
+
+
 def test_resolve_recognises_reference_style_objects():
     class RexQuadrotor_dynamics:  # attribute-compatible stand-in for the reference class
         m, motor_dist, kf, bf, km, dt, act_scale = 2.0, 0.28, 0.0244101, -30.48576, 0.00029958, 0.05, 100.0
