@@ -191,6 +191,14 @@ class MPC(Module):
     def get_xu(self):
         return torch.cat((self.x_init, self.u_init), dim=2)
 
+    def get_cost(self, cost):
+        """AL_mpc.py:558-563: cost of the current warm start under ``cost`` (C may be diag-embedded or its diagonal)."""
+        from .al_utils import compute_cost
+
+        C = cost.C.diagonal(dim1=-2, dim2=-1) if cost.C.ndimension() == 4 else cost.C
+        xu = self.get_xu()
+        return compute_cost(xu, C.to(xu.dtype), cost.c.to(xu.dtype), None if cost.f is None else cost.f.to(xu.dtype))
+
     def reinitialize(self, x, mask=None):
         """AL_mpc.py:569-579: cold start — lam = 0, rho = 1 (in the dtype of ``x``), drop the warm start."""
         n_batch = x.size(0)

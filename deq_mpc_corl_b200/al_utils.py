@@ -21,6 +21,23 @@ QuadCost.__new__.__defaults__ = (None,) * len(QuadCost._fields)
 LinDx.__new__.__defaults__ = (None,) * len(LinDx._fields)
 
 
+def compute_cost(xu, Q, q, f=None, diag_cost=True):
+    """Quadratic cost of a trajectory batch, same conventions as qpth/al_utils.py:425-435 (diagonal ``Q[B,T,n]``,
+    linear term ``q``, optional per-stage constant ``f[B,T]``).  A plain torch expression for callers that want
+    the cost of an iterate (``MPC.get_cost``); the solver's own merit evaluation lives in the CUDA kernels."""
+    if not diag_cost:
+        raise ValueError("only the diagonal cost is supported (diag_cost=True is the only mode the reference's callers use)")
+    c = (0.5 * (xu * Q * xu).sum(-1) + (q * xu).sum(-1)).sum(dim=-1)
+    return c if f is None else c + f.sum(dim=-1)
+
+
+def compute_cost_gradient(xu, Q, q, diag_cost=True):
+    """qpth/al_utils.py:438-446 for the diagonal cost."""
+    if not diag_cost:
+        raise ValueError("only the diagonal cost is supported")
+    return Q * xu + q
+
+
 @dataclass
 class NewtonContext:
     dynamics: object

@@ -114,6 +114,23 @@ def test_mpc_state_semantics_and_cpu_refusal():
     assert se.lamda_prev.shape == (6, 16)
 
 
+def test_get_cost_matches_reference_formula():
+    from deq_mpc_corl_b200.al_utils import compute_cost, compute_cost_gradient
+
+    g = torch.Generator().manual_seed(9)
+    B, T, n = 4, 5, 3
+    xu, Q, q, f = (torch.randn(B, T, n, generator=g), torch.rand(B, T, n, generator=g), torch.randn(B, T, n, generator=g),
+                   torch.randn(B, T, generator=g))
+    ref = torch.stack([sum(0.5 * xu[b, t] @ torch.diag(Q[b, t]) @ xu[b, t] + q[b, t] @ xu[b, t] + f[b, t] for t in range(T))
+                       for b in range(B)])
+    assert torch.allclose(compute_cost(xu, Q, q, f), ref, atol=1e-5)
+    assert torch.allclose(compute_cost_gradient(xu, Q, q), Q * xu + q)
+    ctrl = MPC(2, 1, T, u_lower=torch.tensor([-1.0]), u_upper=torch.tensor([1.0]), n_batch=B)
+    ctrl.x_init, ctrl.u_init = xu[..., :2], xu[..., 2:]
+    got = ctrl.get_cost(QuadCost(torch.diag_embed(Q), q, f))
+    assert torch.allclose(got, ref, atol=1e-5)
+
+
 def test_rollout_with_lindx_matches_reference_formula():
     from deq_mpc_corl_b200.al_utils import LinDx
 
