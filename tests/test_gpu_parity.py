@@ -588,6 +588,80 @@ def test_tracking_mpc_obstacle_and_state_estimator_routes():
     assert se.ctrl.lamda_prev.shape == (B, (T - 1) * nx)
 
 
+def test_c_abi_used_directly_like_integration_md():
+    """The ctypes stub of INTEGRATION.md section 3, written out independently of deq_mpc_corl_b200/_lib.py: plain
+    pointers, sizes and a stream are all the library needs; the result equals the Python drop-in's."""
+    import ctypes
+
+    from deq_mpc_corl_b200 import _lib as product_lib
+
+    class Desc(ctypes.Structure):  # struct almpc_desc (include/almpc.h)
+        _fields_ = [("B", ctypes.c_int32), ("T", ctypes.c_int32), ("dyn_id", ctypes.c_int32),
+                    ("al_iter", ctypes.c_int32), ("max_newton", ctypes.c_int32), ("stream_mode", ctypes.c_int32),
+                    ("rho_f32", ctypes.c_int32), ("flags", ctypes.c_int32),
+                    ("rho_mult", ctypes.c_double), ("rho_max", ctypes.c_double),
+                    ("dyn_params", ctypes.c_double * 48), ("u_lower", ctypes.c_double * 8), ("u_upper", ctypes.c_double * 8),
+                    ("n_obs", ctypes.c_int32), ("reserved", ctypes.c_int32), ("obs_radius", ctypes.c_double),
+                    ("obstacles", ctypes.c_void_p)]
+
+    lib = ctypes.CDLL(product_lib.LIB_PATH)
+    vp = ctypes.c_void_p
+    for fn, nargs in (("almpc_forward_f64", 15), ("almpc_backward_f64", 6)):
+        getattr(lib, fn).argtypes = [ctypes.POINTER(Desc)] + [vp] * nargs
+        getattr(lib, fn).restype = ctypes.c_int
+    for fn in ("almpc_factor_elems", "almpc_workspace_bytes"):
+        getattr(lib, fn).argtypes = [ctypes.POINTER(Desc)]
+        getattr(lib, fn).restype = ctypes.c_size_t
+    lib.almpc_last_error.restype = ctypes.c_char_p
+
+    model, T, B = "rex_quadrotor", 5, 100
+    spec = MODEL_SPECS[model]
+    nx, nu = spec["nx"], spec["nu"]
+    n, m = nx + nu, T * nx + 2 * T * nu
+    inp = make_inputs(model, T, B, 202)
+    dyn = make_dyn(model)
+    Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"])
+    d = Desc(B=B, T=T, dyn_id=dyn.dyn_id, al_iter=2, max_newton=4, stream_mode=0, rho_f32=1, flags=0, rho_mult=10.0,
+             rho_max=1e8)
+    for i, v in enumerate(dyn.param_block()):
+        d.dyn_params[i] = v
+    for i in range(nu):
+        d.u_lower[i], d.u_upper[i] = float(inp["u_lower"][i]), float(inp["u_upper"][i])
+    f64 = dict(dtype=torch.float64, device=DEV)
+    x0 = inp["x0"].double().to(DEV).contiguous()
+    Qd_d, q_d = Qd.to(DEV).contiguous(), q.to(DEV).contiguous()
+    xu = torch.cat([inp["x_ref"], inp["u_ref"]], -1).double().to(DEV).contiguous()
+    lam, rho = torch.zeros(B, m, **f64), torch.ones(B, **f64)
+    factor = torch.empty(B, lib.almpc_factor_elems(ctypes.byref(d)), **f64)
+    ws = torch.empty(lib.almpc_workspace_bytes(ctypes.byref(d)), dtype=torch.uint8, device=DEV)
+    xf, uf = torch.empty(B, T, nx, device=DEV), torch.empty(B, T, nu, device=DEV)
+    dyn_res, status = torch.empty(B, **f64), torch.empty(B, dtype=torch.int32, device=DEV)
+    info = torch.empty(36, dtype=torch.int32, device=DEV)
+    p = lambda t: vp(0 if t is None else t.data_ptr())
+    stream = vp(torch.cuda.current_stream().cuda_stream)
+    rc = lib.almpc_forward_f64(ctypes.byref(d), p(x0), p(Qd_d), p(q_d), p(xu), p(lam), p(rho), p(factor), p(xf), p(uf),
+                               p(dyn_res), p(status), p(info), None, p(ws), stream)
+    assert rc == 0, lib.almpc_last_error()
+    g = torch.Generator().manual_seed(5)
+    grad = torch.randn(B, T, n, generator=g, dtype=torch.float64).to(DEV)
+    gQ, gq = torch.empty_like(xu), torch.empty_like(xu)
+    rc = lib.almpc_backward_f64(ctypes.byref(d), p(factor), p(xu), p(grad), p(gQ), p(gq), stream)
+    assert rc == 0, lib.almpc_last_error()
+    torch.cuda.synchronize()
+    # the Python drop-in on the same inputs
+    ctrl = MPC(nx, nu, T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B)
+    ctrl.reinitialize(inp["x_ref"].to(DEV))
+    ctrl.x_init, ctrl.u_init = inp["x_ref"].to(DEV), inp["u_ref"].to(DEV)
+    ql = q_d.clone().requires_grad_(True)
+    x, u, _ = ctrl(x0, QuadCost(Qd_d, ql, None), dyn, dyn)
+    qg, = torch.autograd.grad((x, u), ql, (grad[..., :nx].float(), grad[..., nx:].float()))
+    assert torch.equal(xu, ctrl.last_xu) and torch.equal(xf, x) and torch.equal(uf, u)
+    assert torch.equal(lam, ctrl.lamda_prev) and (status == 3).all()
+    assert info[0].item() == 2 and info[4:6].tolist() == ctrl.newton_steps()
+    # the drop-in feeds fp32 output gradients (AL_mpc.py:337-338 casts x, u to float)
+    assert rel_err(gq.cpu(), qg.cpu()) < 1e-6
+
+
 def test_forward_backward_are_cuda_graph_capturable():
     """include/almpc.h promises no host synchronisation and no allocation inside the library: capture a whole
     forward + backward in a CUDA graph, replay it on fresh inputs, compare with the eager result."""
