@@ -71,6 +71,23 @@ def build(force=False, verbose=False):
     return out
 
 
+def build_example(force=False):
+    """examples/c_host: a plain C++ / CUDA-runtime host linked against libalmpc.so (no Python, no torch)."""
+    src = os.path.join(ROOT, "examples", "c_host.cpp")
+    out = os.path.join(ROOT, "examples", "c_host")
+    if not os.path.exists(src):
+        return None
+    if not force and os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src), os.path.getmtime(OUT)):
+        return out
+    cmd = [nvcc_path(), "-std=c++17", "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "include"), src, "-o", out,
+           "-L", HERE, "-lalmpc", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../deq_mpc_corl_b200"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("example build failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return out
+
+
 if __name__ == "__main__":
     build(force=True, verbose="--verbose" in sys.argv)
     print("built", OUT)
+    print("built", build_example(force=True))

@@ -7,6 +7,7 @@ conditioned for two correct implementations to agree that closely*; cond(H) ~ rh
 budget is widened with the largest penalty used in the call exactly as for the oracle-vs-reference
 check (tests/test_oracle_golden.py::tolerances), and fp32 is only asserted in the rho <= 1e2 regime
 (SURVEY.md A.5)."""
+import os
 import types
 
 import pytest
@@ -660,6 +661,22 @@ def test_c_abi_used_directly_like_integration_md():
     assert info[0].item() == 2 and info[4:6].tolist() == ctrl.newton_steps()
     # the drop-in feeds fp32 output gradients (AL_mpc.py:337-338 casts x, u to float)
     assert rel_err(gq.cpu(), qg.cpu()) < 1e-6
+
+
+def test_cpp_host_example_runs():
+    """examples/c_host: a C++ / CUDA-runtime host (no Python, no torch) on the same C ABI; built by build()."""
+    import re
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "c_host")
+    if not os.path.exists(exe):
+        pytest.skip("examples/c_host not built (python -m deq_mpc_corl_b200.build)")
+    out = subprocess.run([exe, "777"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    m = re.search(r"AL iterations (\d+), newton steps \[(\d+), (\d+)\].*status ok (\d+)/(\d+)", out.stdout)
+    assert m, out.stdout
+    assert int(m.group(1)) == 2 and 1 <= int(m.group(2)) <= 4 and 1 <= int(m.group(3)) <= 4
+    assert m.group(4) == m.group(5) == "777"
 
 
 def test_forward_backward_are_cuda_graph_capturable():
