@@ -8,15 +8,14 @@ namespace almpc {
 // right-looking elimination on "one row per lane".
 //   lanes 0..NN-1 : rows of the SPD block (lower part in a[0..lane])         -> rows of L (diag = 1/L_ii)
 //   lanes >= NN   : extra rows b (rhs, sub-diagonal block rows)               -> b L^{-T}
-// FUSED=true  : factor + solve in one pass.
-// FUSED=false : lanes 0..NN-1 already hold L (read-only); only lanes >= NN are transformed.
+// Factor and solve in one pass.
 // ------------------------------------------------------------------------------------------------
 // The pivot column travels through shared memory (one STS per lane, then 16-byte broadcast loads) instead
 // of one shuffle pair per entry: the first version was bound by the SM's shuffle throughput.
-//   colbuf : FUSED: 2 x 32 scalars (double-buffered pivot column).  !FUSED: the L rows, [NN][LDL].
-template <int NN, bool FUSED, typename S>
-__device__ __forceinline__ void eliminate(S (&a)[NN], int lane, S* colbuf, int LDL = 0) {
-  if (FUSED) {
+//   colbuf : 2 x 32 scalars (double-buffered pivot column)
+template <int NN, typename S>
+__device__ __forceinline__ void eliminate(S (&a)[NN], int lane, S* colbuf) {
+  {
     // software-pipelined pivots: as soon as column k+1 has its update, the next pivot is broadcast and its
     // reciprocal square root (the longest dependent chain of the step) runs under the remaining updates
     // a non-positive pivot turns into NaN / Inf here and poisons the whole solution of the problem, which is
@@ -55,17 +54,6 @@ __device__ __forceinline__ void eliminate(S (&a)[NN], int lane, S* colbuf, int L
           for (int j = 0; j < NN; ++j)
             if (j >= j0) a[j] -= lk * col[j];
         }
-      }
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < NN; ++k) {
-      const S inv = colbuf[k * LDL + k];
-      const S lk = a[k] * inv;
-      if (lane >= NN) a[k] = lk;
-#pragma unroll
-      for (int j = k + 1; j < NN; ++j) {
-        if (lane >= NN) a[j] -= lk * colbuf[j * LDL + k];
       }
     }
   }
@@ -454,12 +442,12 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
     __syncwarp();  // Y (E_{t-1}) has no reader left: prefetch G_{t+1} into it behind the pivot chain
     if (t + 1 < T - 1) warp_copy_block_async<NX, NN, LB>(Y, Gp + (size_t)(t + 1) * NX * NN, lane);
     cp_async_commit();
-    eliminate<NN, true>(a, lane, scr);
+    eliminate<NN, S>(a, lane, scr);
     __syncwarp();
     {
       // write-outs with per-lane destinations: L rows -> global factor; rhs -> dv (y_t); E rows -> X + global factor
       const int ei = lane - NN - 1;
-      const bool e_wr = (ei >= 0) && (ei < NX) && has_G && (NX <= EX0);
+      const bool e_wr = (ei >= 0) && (ei < NX) && has_G;  // ei < EX0 by construction
       const int last = (lane < NN) ? lane : NN - 1;
       S* gdst = (lane < NN) ? (Lg + lane * NN) : (e_wr ? (Eg + ei * NN) : nullptr);
       S* sdst = (lane == NN) ? (dv + t * NN) : (e_wr ? (X + ei * LB) : nullptr);
@@ -481,41 +469,26 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
 #pragma unroll
         for (int c = 0; c < NN; ++c) sdst[c] = a[c];
       }
-      if (lane < NN && NX > EX0 && has_G) {  // publish L for the second elimination pass
-#pragma unroll
-        for (int c = 0; c < NN; ++c) scr[64 + lane * LD + c] = a[c];
-      }
     }
-    if (NX > EX0 && has_G) {  // sub-diagonal rows that did not fit (flying cartpole: nx=14, n=18)
-      // rows of the first pass are parked in registers until every row of -rho G_t has been read from X
-      S keep[NN];
+    if (NX > EX0 && has_G) {
+      // Sub-diagonal rows that did not fit next to the L rows (flying cartpole: nx = 14, n = 18 -> one row):
+      // x = (-rho G_t[i,:]) L^{-T} by a forward substitution ACROSS the lanes that still hold the rows of L in
+      // registers: lane j owns element j; after x_k is known (lane k: b_k / L_kk) every lane j > k subtracts
+      // L[j][k] x_k with its own a[k].  Registers and shuffles only — the first version ran a second full
+      // elimination pass over shared memory for this one row.  Rows EX0.. of X still hold G_t (the rows written
+      // above are 0..EX0-1).
+      for (int i = EX0; i < NX; ++i) {
+        S bj = (lane < NN) ? -rho * X[i * LB + lane] : S(0);
+        S xres = S(0);
 #pragma unroll
-      for (int c = 0; c < NN; ++c) keep[c] = a[c];
-      const int i0 = lane - NN - 1;
-      constexpr int PER = 32 - NN;
-      for (int base = EX0; base < NX; base += PER) {
-        const int i = base + (lane - NN);
-        const bool act = (lane >= NN) && (i < NX);
-        if (lane >= NN) {
-#pragma unroll
-          for (int c = 0; c < NN; ++c) a[c] = act ? -rho * X[i * LB + c] : S(0);
+        for (int k = 0; k < NN; ++k) {
+          const S xk = __shfl_sync(FULL, bj * a[k], k);  // lane k: a[k] = 1 / L_kk
+          if (lane == k) xres = xk;
+          else if (lane > k && lane < NN) bj -= xk * a[k];  // a[k] = L[lane][k]
         }
-        __syncwarp();
-        eliminate<NN, false>(a, lane, scr + 64, LD);
-        __syncwarp();
-        if (act) {
-#pragma unroll
-          for (int c = 0; c < NN; ++c) {
-            X[i * LB + c] = a[c];
-            Eg[i * NN + c] = a[c];
-          }
-        }
-      }
-      if (lane > NN && i0 < NX) {
-#pragma unroll
-        for (int c = 0; c < NN; ++c) {
-          X[i0 * LB + c] = keep[c];
-          Eg[i0 * NN + c] = keep[c];
+        if (lane < NN) {
+          X[i * LB + lane] = xres;
+          Eg[i * NN + lane] = xres;
         }
       }
     }
