@@ -32,6 +32,9 @@
 #ifndef ALMPC_LS_MINB
 #define ALMPC_LS_MINB 4  // CTAs/SM the warp line search is compiled for
 #endif
+#ifndef ALMPC_JAC_MINB
+#define ALMPC_JAC_MINB 2  // CTAs/SM the Jacobian kernel is compiled for (3 forces spills: measured slower)
+#endif
 #ifndef ALMPC_FAC_MINB
 #define ALMPC_FAC_MINB 6  // CTAs/SM the factor kernel is compiled for (register cap 80; 5..7 measured within 2%)
 #endif

@@ -9,7 +9,7 @@ namespace almpc {
 //   G_g[prob][t][i][j] = d f_i / d z_j at (x_t,u_t) ; c_g[prob][t*nx+i] = x_{t+1,i} - f_i ; last block: x_0 - x0
 // ------------------------------------------------------------------------------------------------
 template <class M, typename S, int V>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, ALMPC_JAC_MINB)
 k_jacobian(const KParams<S> P, const S* __restrict__ x0_g, const S* __restrict__ xu_g, S* __restrict__ G_g,
            S* __restrict__ c_g, const Ctl* __restrict__ ctl) {
   constexpr int NX = M::NX, NU = M::NU, NN = NX + NU;
