@@ -73,6 +73,10 @@ class MPC(Module):
         self.just_initialized = True
         self.cost_hist_stream = [[], []]
         self.mask = None
+        # opt-in: replay the forward launch sequence as one CUDA graph (saves ~0.25 ms per call; pays for batches of
+        # a few hundred problems, e.g. the reference's bsz = 200 training runs).  Fused native path only.
+        self.cuda_graph = False
+        self._graph_cache = None
         self.last_info = None      # device int32[INFO_INTS] of the latest solve (no sync to keep it)
         self.last_status = None    # device int32[B] per-problem status bits
         self._bounds_host = (self.u_lower.double().cpu().tolist(), self.u_upper.double().cpu().tolist())
@@ -131,6 +135,12 @@ class MPC(Module):
         if dyn is not None:
             solve = ALSolve
             cfg = SolveConfig(dyn=dyn, u_lower=self._bounds_host[0], u_upper=self._bounds_host[1], **common, **extra)
+            if self.cuda_graph:
+                if self._graph_cache is None:
+                    from .solver import GraphCache
+
+                    self.__dict__["_graph_cache"] = GraphCache()
+                cfg.graph_cache = self._graph_cache
         else:
             if extra:
                 raise _lib.AlmpcError("obstacle constraints need a native dynamics functor")

@@ -32,6 +32,7 @@ class SolveConfig:
     obstacles: object = None      # device tensor [B,T,n_obs,3] in the solver dtype (Obstacle_MPC)
     obs_radius: float = 0.0
     state_estimator: bool = False  # MPC(state_estimator=True): dynamics rows only, controls are data (al_utils_se.py)
+    graph_cache: object = None     # a GraphCache: replay the forward launch sequence as one CUDA graph
 
     def desc(self, B):
         d = _lib.Desc()
@@ -105,6 +106,59 @@ def raw_forward(cfg: SolveConfig, x0, Qd, q, xu, lam, rho):
     return out
 
 
+class GraphCache:
+    """Opt-in CUDA-graph replay of ``raw_forward`` for small batches, where a solve is bound by its ~27 kernel
+    launches (``MPC.cuda_graph = True``).  One entry per (shape, dtype, configuration): static input / output
+    buffers and the captured launch sequence; a call copies its inputs in, replays, and hands back fresh clones
+    (the factor is saved for backward by autograd, so the static buffers must not leak out).  The library
+    itself neither allocates nor synchronises, which is what makes the capture legal
+    (tests/test_gpu_parity.py::test_forward_backward_are_cuda_graph_capturable)."""
+
+    def __init__(self):
+        self.entries = {}
+
+    @staticmethod
+    def _key(cfg, xu):
+        ob = cfg.obstacles
+        return (tuple(xu.shape), xu.dtype, xu.device, cfg.dyn.dyn_id, tuple(cfg.dyn.param_block()), cfg.T,
+                tuple(cfg.u_lower), tuple(cfg.u_upper), cfg.al_iter, cfg.max_newton, cfg.stream_mode, cfg.rho_f32,
+                cfg.rho_mult, cfg.rho_max, cfg.skip_final_dual, cfg.state_estimator,
+                None if ob is None else tuple(ob.shape), cfg.obs_radius)
+
+    def forward(self, cfg, x0, Qd, q, xu, lam, rho):
+        import copy
+
+        key = self._key(cfg, xu)
+        ent = self.entries.get(key)
+        names = ("x0", "Qd", "q", "xu", "lam", "rho")
+        live = dict(zip(names, (x0, Qd, q, xu, lam, rho)))
+        if ent is None:
+            static = {k: v.clone() for k, v in live.items()}
+            scfg = copy.copy(cfg)
+            scfg.debug = False
+            if cfg.obstacles is not None:
+                scfg.obstacles = cfg.obstacles.clone()
+            side = torch.cuda.Stream(device=xu.device)
+            side.wait_stream(torch.cuda.current_stream(xu.device))
+            with torch.cuda.stream(side):  # warm-up outside capture (lazy loading, function attributes)
+                raw_forward(scfg, *(static[k].clone() for k in names))
+            torch.cuda.current_stream(xu.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = raw_forward(scfg, *(static[k] for k in names))
+            ent = self.entries[key] = dict(static=static, cfg=scfg, graph=graph, out=out)
+        for k in names:
+            ent["static"][k].copy_(live[k])
+        if cfg.obstacles is not None:
+            ent["cfg"].obstacles.copy_(cfg.obstacles)
+        ent["graph"].replay()
+        # results leave as fresh tensors; the caller-owned in/out buffers are updated like raw_forward does
+        xu.copy_(ent["static"]["xu"])
+        lam.copy_(ent["static"]["lam"])
+        rho.copy_(ent["static"]["rho"])
+        return {k: (None if v is None else v.clone()) for k, v in ent["out"].items()}
+
+
 def raw_backward(cfg: SolveConfig, factor, xu, grad_xu, need_Q=True):
     lib = _lib.load()
     _lib.require_cuda(grad_xu, "grad_xu")
@@ -131,7 +185,8 @@ class ALSolve(torch.autograd.Function):
         xu = xu_init.detach().clone().contiguous()
         lam = lam.detach().clone().contiguous()
         rho = rho.detach().clone().contiguous()
-        out = raw_forward(cfg, x0.detach().contiguous(), Qd.detach().contiguous(), q.detach().contiguous(), xu, lam, rho)
+        fwd = raw_forward if cfg.graph_cache is None or cfg.debug else cfg.graph_cache.forward
+        out = fwd(cfg, x0.detach().contiguous(), Qd.detach().contiguous(), q.detach().contiguous(), xu, lam, rho)
         ctx.cfg = cfg
         ctx.save_for_backward(out["factor"], xu)
         dbg = out["debug"] if out["debug"] is not None else torch.empty(0, device=xu.device)

@@ -723,6 +723,40 @@ def test_forward_backward_are_cuda_graph_capturable():
         assert torch.equal(out["info"], info_e)
 
 
+def test_mpc_cuda_graph_mode_equals_eager():
+    """MPC.cuda_graph = True replays the forward launch sequence as one CUDA graph: bit-identical to the eager path
+    over a chain of calls (duals and penalties carried, fresh inputs each call), gradients included."""
+    model, T, B = "cartpole1l", 5, 200
+    spec = MODEL_SPECS[model]
+    dyn = make_dyn(model, dt=spec["dt"])
+    inp = make_inputs(model, T, B, 77)
+
+    def chain(graph):
+        ctrl = MPC(spec["nx"], spec["nu"], T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B)
+        ctrl.cuda_graph = graph
+        ctrl.reinitialize(inp["x_ref"].to(DEV))
+        ctrl.x_init, ctrl.u_init = inp["x_ref"].to(DEV), inp["u_ref"].to(DEV)
+        outs = []
+        x_ref = inp["x_ref"].clone()
+        for it in range(3):
+            Qd, q, _ = tracking_cost(inp["Qd"], x_ref, inp["u_ref"])
+            ql = q.to(DEV).requires_grad_(True)
+            x, u, _ = ctrl(inp["x0"].to(DEV), QuadCost(Qd.to(DEV), ql, None), dyn, dyn)
+            qg, = torch.autograd.grad((x, u), ql, (torch.ones_like(x), torch.ones_like(u)))
+            outs.append((x.clone(), u.clone(), qg.clone(), ctrl.lamda_prev.clone(), ctrl.rho_prev.clone(), ctrl.newton_steps()))
+            x_ref = 0.7 * x_ref + 0.3 * x.detach().cpu()
+            x_ref[:, 0] = inp["x0"]
+        return outs, ctrl
+
+    eager, _ = chain(False)
+    graphed, ctrl = chain(True)
+    assert len(ctrl._graph_cache.entries) == 1
+    for a, b in zip(eager, graphed):
+        for ta, tb in zip(a[:5], b[:5]):
+            assert torch.equal(ta, tb)
+        assert a[5] == b[5]
+
+
 def test_deq_chain_without_resync_matches_oracle():
     """BASELINE config 1 shape (pendulum, T=5, B=200, fp64, 6 DEQ iterations of al_iter=2 with lam / rho and the
     warm start carried across calls, rho 1 -> 1e12): the CUDA module and the oracle run the whole chain from the

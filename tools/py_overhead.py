@@ -13,6 +13,7 @@ inp = make_inputs(model, T, B, 3)
 inp = {k: (v.to(dev) if torch.is_tensor(v) and v.dim() > 1 else v) for k, v in inp.items()}
 dyn = make_dyn(model, dt=spec["dt"])
 ctrl = MPC(spec["nx"], spec["nu"], T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B)
+ctrl.cuda_graph = "--graph" in sys.argv
 Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"])
 Qd, q = Qd.to(dev), q.to(dev)
 gx, gu = torch.randn(B, T, spec["nx"], device=dev), torch.randn(B, T, spec["nu"], device=dev)
