@@ -628,9 +628,10 @@ __device__ __forceinline__ void half_copy_block_async(S* dst, const S* src, int 
   }
 }
 
-// small blocks keep little in shared memory, so their occupancy is set by registers: cap them for 12 CTAs / SM
+// small blocks (and fp32) keep little in shared memory, so their occupancy is set by registers: cap them for
+// 12 (10) CTAs / SM; the fp64 quadrotor is limited to 6 by shared memory anyway and may use up to 170 registers
 template <int NX, int NU, typename S, int WPB, int V>
-__global__ void __launch_bounds__(WPB * 32, (NX + NU <= 8) ? 12 : 6)
+__global__ void __launch_bounds__(WPB * 32, (NX + NU <= 8) ? 12 : (sizeof(S) == 4 ? 10 : 6))
 k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restrict__ q_g,
                     const S* __restrict__ xu_g, S* __restrict__ lam_g, S* __restrict__ rho_g, S* fac_g,
                     const S* __restrict__ G_g, const S* __restrict__ c_g, S* __restrict__ d_g,

@@ -1,4 +1,4 @@
-"""Per-kernel CUDA-event times of one 64K quadrotor forward (almpc_set_profiling): tools/kernel_times.py [model T B]."""
+"""Per-kernel CUDA-event times of one 64K quadrotor forward (almpc_set_profiling): tools/kernel_times.py [model T B [f32]]."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
@@ -10,19 +10,20 @@ from deq_mpc_corl_b200.solver import SolveConfig, raw_forward
 model = sys.argv[1] if len(sys.argv) > 1 else "rex_quadrotor"
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
+DT = torch.float32 if (len(sys.argv) > 4 and sys.argv[4] == "f32") else torch.float64
 dev = "cuda:0"
 spec = MODEL_SPECS[model]
 inp = make_inputs(model, T, B, 1003)
-Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"], torch.float64)
+Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"], DT)
 dyn = make_dyn(model, dt=spec["dt"])
 cfg = SolveConfig(dyn=dyn, T=T, u_lower=list(map(float, inp["u_lower"])), u_upper=list(map(float, inp["u_upper"])))
-x0 = inp["x0"].double().to(dev); Qd = Qd.to(dev).contiguous(); q = q.to(dev).contiguous()
-xu0 = torch.cat([inp["x_ref"], inp["u_ref"]], -1).double().to(dev).contiguous()
+x0 = inp["x0"].to(DT).to(dev); Qd = Qd.to(dev).contiguous(); q = q.to(dev).contiguous()
+xu0 = torch.cat([inp["x_ref"], inp["u_ref"]], -1).to(DT).to(dev).contiguous()
 m = T * spec["nx"] + T * 2 * spec["nu"]
 lib = _lib.load()
 res = []
 for it in range(4):
-    xu = xu0.clone(); lam = torch.zeros(B, m, dtype=torch.float64, device=dev); rho = torch.ones(B, dtype=torch.float64, device=dev)
+    xu = xu0.clone(); lam = torch.zeros(B, m, dtype=DT, device=dev); rho = torch.ones(B, dtype=DT, device=dev)
     lib.almpc_set_profiling(1 if it else 0)
     out = raw_forward(cfg, x0, Qd, q, xu, lam, rho)
     torch.cuda.synchronize()
