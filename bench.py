@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""Headline benchmark: AL-MPC solves/sec (forward + implicit backward), rex-quadrotor T=5, 64K problems
-per GPU, fp64 (BASELINE.json).  One *step* = one cold-start `MPC.forward` (al_iter=2) plus its
-`NewtonAL.backward` for every problem of the batch.
+"""Headline benchmark: AL-MPC solves/sec (forward + implicit backward), rex-quadrotor T=5, batch 64K, fp64, at
+1/2/4/8 GPUs (BASELINE.json).  One *step* = one cold-start `MPC.forward` (al_iter=2) plus its `NewtonAL.backward`
+for every problem of the batch.
 
     python bench.py [--gpus N --steps K --warmup W] [--dtype f64|f32] [--model ...] [--T ..] [--batch ..]
-    torchrun --nproc-per-node N bench.py --gpus N ...          (one rank per GPU, batch sharded, no collective
-                                                                 on the data path -> "scaling": "weak")
-    python bench.py --impl reference ...                        (the CPU oracle port on the host cores)
+    torchrun --nproc-per-node N bench.py --gpus N ...   one rank per GPU; the GLOBAL batch (--batch, default the
+                                                        65 536 problems BASELINE names) is split over the ranks
+                                                        (sharding.shard_bounds), no data-path collective
+                                                        -> "scaling": "strong"; the weak curve (64K per GPU) is an
+                                                        extra key
+    python bench.py --impl reference ...                the UNMODIFIED reference (qpth.AL_mpc.MPC on torch CPU, staged
+                                                        under oracle/_ref/py) on the host cores, a bounded sample per step
 
-Prints ONE JSON line (contract in the task statement): value = device-timed whole-job solves/s with
-inputs resident in HBM; e2e = the same through the reference-facing `MPC` module with pinned HOST
-buffers and the H2D/D2H copies inside the timed region; roofline = FP64 (FP32) FMA-pipe fraction of
-the dominant kernel of the Newton step (k_jacobian / k_factor_solve / k_line_search, timed per launch with
-CUDA events inside the library) from algorithmic flops and bytes, against the FMA peak
-measured in this run by almpc_fma_peak (MEASURED_PEAKS.json has no FP64 figure), plus the HBM view;
-cpu_baseline = the oracle port timed on this box's host cores on a bounded sample.
+Prints ONE JSON line (contract in the task statement):
+  value      device-timed whole-job solves/s, inputs resident in HBM
+  e2e        the same through the reference-facing `MPC` module with pinned HOST buffers, H2D/D2H inside the timed region
+  roofline   the dominant kernel of the Newton step against the roofline that binds the path (FP64 / FP32 FMA pipe,
+             SURVEY.md 8d; peak measured in this run by almpc_fma_peak because MEASURED_PEAKS.json has no such figure),
+             HBM view beside it, `traffic` from the committed ncu capture of the same workload (profiles/r02_ncu_traffic.json)
+  cpu_baseline   the unmodified reference timed on this box's host cores on a bounded sample of the same workload
+  suite      the other BASELINE.json configurations (N=1 only): fp32 64K, the 6-deep DEQ chain, pendulum B=200,
+             cartpole 4K with streaming warm starts, flying cartpole T=10 16K — each with its own CPU sample
 """
 import argparse
 import json
@@ -34,6 +40,8 @@ from deq_mpc_corl_b200.problems import MODEL_SPECS, make_inputs, tracking_cost  
 # F_dyn: flops of one RK4 step of each model's ODE as written in csrc/almpc_models.cuh, counted by
 # tools/count_flops.cpp (add/sub/mul = 1, fma = 2, reciprocal = 1, sincos = 2).  Frozen here.
 F_DYN = {"pendulum": 50, "cartpole1l": 120, "cartpole2l": 322, "rex_quadrotor": 980, "flying_cartpole": 1150}
+METRIC = "AL-MPC solves/sec (fwd+implicit bwd)"
+HEADLINE_BATCH = 65536
 
 
 def algorithmic_flops(model, T):
@@ -52,9 +60,10 @@ def algorithmic_flops(model, T):
     return dict(newton=f_newton, dual=f_dual, bwd=f_bwd)
 
 
-def kernel_work(model, T, esize):
-    """Algorithmic flops / HBM bytes per problem of the three kernels of one Newton step (same SURVEY §8d
-    terms as algorithmic_flops, split by kernel; G and c cross HBM between the kernels)."""
+def kernel_work(model, T, esize, fused):
+    """Algorithmic flops / HBM bytes per problem of the kernels of one Newton step (same SURVEY §8d terms as
+    algorithmic_flops, split by kernel; G and c cross HBM between k_jacobian and the factor phase; with the fused
+    Newton tail the direction, merit and entry residual no longer do)."""
     spec = MODEL_SPECS[model]
     nx, nu = spec["nx"], spec["nu"]
     n, N, m = nx + nu, T * (nx + nu), T * nx + 2 * T * nu
@@ -62,15 +71,16 @@ def kernel_work(model, T, esize):
     G = (T - 1) * nx * n
     factor = T * n * n + (T - 1) * nx * n
     subst = 2 * (T * n * n + 2 * (T - 1) * nx * n)
-    return {
-        "k_jacobian": dict(flops=(T - 1) * 2 * n * f_dyn, bytes=(N + nx + G + T * nx) * esize),
-        "k_factor_solve": dict(
-            flops=(T - 1) * nx * n * (n + 1) + 4 * (T - 1) * nx * n + 4 * T * nu + T * n ** 3 / 3
-            + (T - 1) * (nx * n * n + nx * nx * n) + subst + 6 * N + 3 * m,
-            bytes=(G + T * nx + 3 * N + m + 1 + factor + N + 2) * esize),
-        "k_line_search": dict(flops=20 * ((T - 1) * f_dyn + 6 * T * n + 2 * m) + 2 * N,
-                              bytes=(5 * N + m + nx + 3 + N) * esize),
-    }
+    f_fac = ((T - 1) * nx * n * (n + 1) + 4 * (T - 1) * nx * n + 4 * T * nu + T * n ** 3 / 3
+             + (T - 1) * (nx * n * n + nx * nx * n) + subst + 6 * N + 3 * m)
+    f_ls = 20 * ((T - 1) * f_dyn + 6 * T * n + 2 * m) + 2 * N
+    jac = dict(flops=(T - 1) * 2 * n * f_dyn, bytes=(N + nx + G + T * nx) * esize)
+    if fused:
+        return {"k_jacobian": jac,
+                "k_newton_pair": dict(flops=f_fac + f_ls, bytes=(G + T * nx + 3 * N + m + 1 + nx + factor + N + m + 3) * esize)}
+    return {"k_jacobian": jac,
+            "k_factor_solve": dict(flops=f_fac, bytes=(G + T * nx + 3 * N + m + 1 + factor + N + 2) * esize),
+            "k_line_search": dict(flops=f_ls, bytes=(5 * N + m + nx + 3 + N) * esize)}
 
 
 def algorithmic_bytes(model, T, esize):
@@ -82,13 +92,18 @@ def algorithmic_bytes(model, T, esize):
     factor = T * n * n + (T - 1) * nx * n
     fwd = (nx + 3 * N + m + 1) + (N + m + 1 + factor)
     bwd = factor + 2 * N + 2 * N
-    return dict(fwd=fwd * esize, bwd=bwd * esize, newton_launch=(nx + 3 * N + m + 2 + N + factor + 2) * esize)
+    return dict(fwd=fwd * esize, bwd=bwd * esize, solve=(fwd + bwd) * esize,
+                newton_launch=(nx + 3 * N + m + 2 + N + factor + 2) * esize)
 
 
-# DRAM traffic per launch measured once with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum),
-# profiles/r01_v6_three_kernels_ncu_full_summary.csv — only valid for the exact workload it was captured on.
-NCU_TRAFFIC = {("rex_quadrotor", 5, 65536, "f64"): {"k_jacobian": 48.37e6 + 375.15e6, "k_factor_solve": 629.38e6 + 1063.53e6,  # k_factor_solve_pair, profiles/r01_v11_*
-                                                    "k_line_search": 228.87e6 + 31.84e6}}
+def ncu_traffic(model, T, B, dtype_name):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each step kernel from the committed
+    `ncu --set full` capture of THIS workload, or None (never a constant pasted for another workload)."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+    except Exception:
+        return None
+    return tab.get(f"{model}/T{T}/B{B}/{dtype_name}")
 
 
 class ClockSampler:
@@ -138,66 +153,363 @@ class ClockSampler:
         return out
 
 
-def cpu_oracle_run(model, T, B, dtype, seed, repeats=1):
-    """Times the oracle port (oracle/almpc_oracle.py) forward+backward on the host: returns
-    (solves/s, newton step counts)."""
+# --------------------------------------------------------------------------------------------------------------
+# CPU arm: the unmodified reference (oracle/ref_runner.py) when it is staged, else the oracle port
+# --------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(model, T, B, dtype, seed, stream_calls=0):
+    """-> (solves/s, newton steps, seconds, kind, description).  kind = "reference": qpth.AL_mpc.MPC.forward +
+    autograd backward of the UNMODIFIED reference (BASELINE.md §3 recipe, chunks <= 4096); "port": the torch
+    restatement oracle/almpc_oracle.py (only when the reference copy is not staged)."""
+    from oracle import ref_import
+
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    if ref_import.available():
+        from oracle import ref_runner
+
+        r = ref_runner.run(model, T, B, dtype, seed, stream_calls=stream_calls)
+        return (r["solves_per_s"], r["newton_steps"], r["seconds"], "reference",
+                f"unmodified reference qpth.AL_mpc.MPC.forward + backward (torch {torch.__version__} CPU, {cores} threads, chunks <= 4096)")
     from oracle import almpc_oracle as orc
     from oracle.problem_gen import make_oracle_model
 
-    torch.set_num_threads(os.cpu_count())
     inp = make_inputs(model, T, B, seed)
     Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"], dtype)
-    om = make_oracle_model(model)
-    best, steps = None, None
-    for _ in range(repeats):
-        mpc = orc.OracleMPC(om, T, inp["u_lower"], inp["u_upper"], B, dtype=dtype, al_iter=2)
-        mpc.reinitialize(inp["x_ref"])
-        mpc.x_init, mpc.u_init = inp["x_ref"].clone(), inp["u_ref"].clone()
-        tr = orc.SolveTrace()
-        t0 = time.perf_counter()
-        x, u, _, _ = mpc.solve(inp["x0"], Qd, q, trace=tr)
-        mpc.backward(torch.ones_like(x), torch.ones_like(u))
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-        steps = tr.newton_steps
-    return B / best, steps, best
+    mpc = orc.OracleMPC(make_oracle_model(model), T, inp["u_lower"], inp["u_upper"], B, dtype=dtype, al_iter=2)
+    mpc.reinitialize(inp["x_ref"])
+    mpc.x_init, mpc.u_init = inp["x_ref"].clone(), inp["u_ref"].clone()
+    tr = orc.SolveTrace()
+    t0 = time.perf_counter()
+    x, u, _, _ = mpc.solve(inp["x0"], Qd, q, trace=tr)
+    mpc.backward(torch.ones_like(x), torch.ones_like(u))
+    dt = time.perf_counter() - t0
+    return (B / dt, tr.newton_steps, dt, "port",
+            f"oracle port of qpth AL_mpc (torch {torch.__version__} CPU, {cores} threads): reference copy not staged")
+
+
+def cpu_baseline_entry(model, T, sample, dtype, workload_B):
+    # one small warm-up call first: the reference's TorchScript dynamics modules specialise on their first calls
+    cpu_reference_run(model, T, min(64, sample), dtype, 999)
+    v, steps, secs, kind, desc = cpu_reference_run(model, T, sample, dtype, 1003)
+    return {"value": v, "unit": "solves/s", "cores": os.cpu_count(), "kind": kind,
+            "sample": f"{sample} of the {workload_B} problems, 1 fwd+bwd, {secs:.1f} s; {desc}; newton steps {steps}"}
+
+
+def workload_config(args):
+    """Names the workload (identical for both arms and every N: the driver compares it)."""
+    B = args.batch
+    return {
+        "workload": f"{args.model} T={args.T} al_iter=2 cold start (lam=0, rho=1), max 4 Newton steps/AL iter, "
+                    f"20-pt line search; global batch {B} problems split over the GPUs",
+        "global_batch": B, "T": args.T,
+        "parallelism": "batch-sharded (independent problems, contiguous split, no data-path collective)",
+        "l2": "inputs + factor of a 64K-problem step (1.3 GB) exceed the 126 MB L2; no explicit flush",
+    }
 
 
 def run_reference_arm(args, rank):
-    """`--impl reference`: the reference's CPU path (oracle port) on the host cores, rank 0 only."""
+    """`--impl reference`: the reference's own CPU implementation on the host cores, rank 0 only; each step a
+    bounded sample of the workload."""
     if rank != 0:
         return
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     B = args.cpu_sample
-    for _ in range(args.warmup):
-        cpu_oracle_run(args.model, args.T, min(B, 64), dtype, 1003)
+    kind = desc = steps = None
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_run(args.model, args.T, min(B, 256), dtype, 1003)
     t0 = time.perf_counter()
-    steps = None
     for _ in range(args.steps):
-        _, steps, _ = cpu_oracle_run(args.model, args.T, B, dtype, 1003)
+        _, steps, _, kind, desc = cpu_reference_run(args.model, args.T, B, dtype, 1003)
     el = time.perf_counter() - t0
     val = args.steps * B / el
     cores = os.cpu_count()
     line = {
-        "impl": "reference", "metric": "AL-MPC solves/sec (fwd+implicit bwd)", "value": val, "unit": "solves/s",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "solves/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": workload_config(args, B, 1),
-        "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
-                         "sample": f"{B} problems per step x {args.steps} steps, oracle port of qpth AL_mpc (torch {torch.__version__} CPU, {cores} threads); newton steps {steps}"},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": kind,
+                         "sample": f"{B} of the {args.batch} problems per step x {args.steps} steps; {desc}; newton steps {steps}"},
         "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def workload_config(args, batch_per_gpu, n_gpus):
+# --------------------------------------------------------------------------------------------------------------
+# GPU arm helpers
+# --------------------------------------------------------------------------------------------------------------
+class Problem:
+    """Device-resident synthetic batch of one model (SURVEY §8d recipe) + the solver configuration."""
+
+    def __init__(self, model, T, B, dtype, seed, dev, lo=0, hi=None):
+        from deq_mpc_corl_b200.dynamics import make as make_dyn
+        from deq_mpc_corl_b200.solver import SolveConfig
+
+        spec = MODEL_SPECS[model]
+        self.model, self.T, self.dtype, self.dev, self.spec = model, T, dtype, dev, spec
+        self.nx, self.nu = spec["nx"], spec["nu"]
+        self.n, self.m = self.nx + self.nu, T * self.nx + 2 * T * self.nu
+        inp = make_inputs(model, T, B, seed)
+        hi = B if hi is None else hi
+        inp = {k: (v[lo:hi] if v.dim() > 1 else v) for k, v in inp.items()}  # this rank's shard of the global batch
+        self.B = hi - lo
+        self.inp = inp
+        self.Qd_h, self.q_h, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"], dtype)
+        self.dyn = make_dyn(model, dt=spec["dt"])
+        self.cfg = SolveConfig(dyn=self.dyn, T=T, u_lower=inp["u_lower"].tolist(), u_upper=inp["u_upper"].tolist(),
+                               al_iter=2, rho_f32=(dtype == torch.float64))
+        self.x0 = inp["x0"].to(dtype).to(dev)
+        self.Qd, self.q = self.Qd_h.to(dev), self.q_h.to(dev)
+        self.xu_init = torch.cat([inp["x_ref"], inp["u_ref"]], -1).to(dtype).to(dev).contiguous()
+        self.lam0 = torch.zeros(self.B, self.m, dtype=dtype, device=dev)
+        self.rho0 = torch.ones(self.B, dtype=dtype, device=dev)
+        g = torch.Generator().manual_seed(7 + seed)
+        self.gen = g
+        self.grad_xu = torch.randn(self.B, T, self.n, generator=g).to(dtype).to(dev)
+        self.xu, self.lam, self.rho = torch.empty_like(self.xu_init), torch.empty_like(self.lam0), torch.empty_like(self.rho0)
+
+    def device_step(self):
+        from deq_mpc_corl_b200.solver import raw_backward, raw_forward
+
+        self.xu.copy_(self.xu_init)
+        self.lam.copy_(self.lam0)
+        self.rho.copy_(self.rho0)
+        out = raw_forward(self.cfg, self.x0, self.Qd, self.q, self.xu, self.lam, self.rho)
+        raw_backward(self.cfg, out["factor"], self.xu, self.grad_xu, need_Q=True, status=out["status"])
+        return out
+
+    def newton_counts(self, out):
+        from deq_mpc_corl_b200 import _lib
+
+        info = out["info"].cpu().tolist()
+        return info[_lib.INFO_NEWTON0:_lib.INFO_NEWTON0 + info[_lib.INFO_AL_DONE]]
+
+    def kernel_profile(self):
+        """Per-kernel CUDA-event times of one forward (events around every launch inside the library, on the
+        launching stream): median of 3.  -> {kernel: avg launch ms}, fused?"""
+        from deq_mpc_corl_b200.solver import raw_forward
+
+        runs = []
+        self.cfg.profile = True
+        for _ in range(3):
+            self.xu.copy_(self.xu_init)
+            self.lam.copy_(self.lam0)
+            self.rho.copy_(self.rho0)
+            runs.append(raw_forward(self.cfg, self.x0, self.Qd, self.q, self.xu, self.lam, self.rho)["profile_ms"])
+            torch.cuda.synchronize()
+        self.cfg.profile = False
+        runs.sort(key=lambda r: r[0] + r[1] + r[2])
+        pr = runs[len(runs) // 2]
+        fused = pr[6] == 0
+        if fused:
+            return {"k_jacobian": pr[0] / max(pr[4], 1), "k_newton_pair": pr[1] / max(pr[5], 1)}, True
+        return {"k_jacobian": pr[0] / max(pr[4], 1), "k_factor_solve": pr[1] / max(pr[5], 1),
+                "k_line_search": pr[2] / max(pr[6], 1)}, False
+
+
+def timed(fn, steps, warmup, barrier):
+    """W warm-up + K timed calls of fn, bracketed by barrier + synchronize; device ms of the K calls."""
+    out = None
+    for _ in range(warmup):
+        out = fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1), out
+
+
+def fma_peak(dtype, dev):
+    """FMA-pipe peak (roofline denominator), measured here because MEASURED_PEAKS.json has none: TFLOP/s."""
+    import ctypes
+
+    from deq_mpc_corl_b200 import _lib
+
+    lib = _lib.load()
+    sink = torch.zeros(256 * 148 * 16, dtype=dtype, device=dev)
+    fl = ctypes.c_double()
+    fn = getattr(lib, "almpc_fma_peak_" + _lib.suffix(dtype))
+    best = 0.0
+    for i in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(fn(148 * 16, 8192, _lib.ptr(sink), ctypes.byref(fl), _lib.stream_ptr()), "fma_peak")
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            best = max(best, fl.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def roofline_block(pb, kernel_ms, fused, peak_tflops, hbm_peak, peaks_known, dtype_name):
+    model, T, B = pb.model, pb.T, pb.B
+    esize = 8 if pb.dtype == torch.float64 else 4
+    fl = algorithmic_flops(model, T)
+    by = algorithmic_bytes(model, T, esize)
+    kw = kernel_work(model, T, esize, fused)
+    fma_name = "fp64_fma" if pb.dtype == torch.float64 else "fp32_fma"
+    traffic = ncu_traffic(model, T, B, dtype_name) or {}
+    kernels = {}
+    for kn, ms in kernel_ms.items():
+        tf = kw[kn]["flops"] * B / (ms * 1e-3) / 1e12
+        gb = kw[kn]["bytes"] * B / (ms * 1e-3) / 1e9
+        kernels[kn] = {"avg_launch_ms": ms, "flops_per_problem": kw[kn]["flops"], "bytes_per_problem": kw[kn]["bytes"],
+                       "fma_tflops": tf, "fma_frac": tf / peak_tflops, "hbm_gbs": gb, "hbm_frac": gb / hbm_peak,
+                       "algorithmic_bytes_per_launch": kw[kn]["bytes"] * B, "traffic": traffic.get(kn)}
+    step_ms = sum(kernel_ms.values())
+    ach = fl["newton"] * B / (step_ms * 1e-3) / 1e12
+    hbm_ach = by["newton_launch"] * B / (step_ms * 1e-3) / 1e9
+    dom = max(kernel_ms, key=kernel_ms.get)
+    dk = kernels[dom]
+    solve_dram = traffic.get("solve_dram_bytes_per_problem")
     return {
-        "workload": f"{args.model} T={args.T} al_iter=2 cold start (lam=0, rho=1), max 4 Newton steps/AL iter, "
-                    f"20-pt line search; {batch_per_gpu} problems per GPU",
-        "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * n_gpus, "T": args.T,
-        "parallelism": f"batch-sharded x{n_gpus} (independent problems, no data-path collective)",
-        "l2": "inputs+factor per step exceed the 126 MB L2 (no explicit flush)" if batch_per_gpu >= 32768 else "small batch: L2-resident",
+        # dominant kernel by time, on the roofline that BINDS this path (FMA pipe: ~55 flop/B against a machine
+        # balance of ~6, SURVEY.md 8d); the HBM view is the secondary one
+        "kernel": dom, "bound": fma_name, "achieved": dk["fma_tflops"], "peak": peak_tflops, "unit": "TFLOP/s",
+        "frac": dk["fma_frac"], "avg_launch_ms": dk["avg_launch_ms"], "traffic": dk["traffic"],
+        "hbm": {"bound": "hbm", "achieved": dk["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dk["hbm_frac"]},
+        "peak_source": {"fma": "measured in this run by almpc_fma_peak (8 independent FMA chains/thread); MEASURED_PEAKS.json has no FP64/FP32 FMA figure",
+                        "hbm": "MEASURED_PEAKS.json" if peaks_known else "fallback 6650 GB/s"},
+        "kernels": kernels,
+        # the whole Newton step (all its launches) against the FMA roofline that binds the path
+        "newton_step": {"bound": fma_name, "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s",
+                        "frac": ach / peak_tflops, "flops_per_problem": fl["newton"], "ms": step_ms,
+                        "launches": len(kernel_ms),
+                        "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                                "bytes_per_problem": by["newton_launch"]}},
+        # measured DRAM bytes of a whole solve (ncu: per-launch sums x realised launches) / algorithmic bytes of a solve
+        "traffic_ratio": (solve_dram / by["solve"]) if solve_dram else None,
     }
+
+
+def suite_entry(model, T, B, dtype, dev, steps, cpu_sample, peak, hbm_peak, peaks_known, no_cpu):
+    """One BASELINE configuration besides the headline one: device-timed solves/s, FMA-roofline fraction of the
+    Newton step, CPU reference sample."""
+    pb = Problem(model, T, B, dtype, 1003, dev)
+    ms, out = timed(pb.device_step, steps, 3, torch.cuda.synchronize)
+    kms, fused = pb.kernel_profile()
+    dn = "f64" if dtype == torch.float64 else "f32"
+    rf = roofline_block(pb, kms, fused, peak, hbm_peak, peaks_known, dn)
+    e = {"workload": f"{model} T={T} B={B} {dn} cold start al_iter=2", "value": steps * B / (ms * 1e-3), "unit": "solves/s",
+         "ms_per_step": ms / steps, "newton_steps_per_al_iter": pb.newton_counts(out),
+         "newton_step_ms": rf["newton_step"]["ms"], "fma_frac_newton_step": rf["newton_step"]["frac"],
+         "hbm_frac_newton_step": rf["newton_step"]["hbm"]["frac"], "kernels_ms": kms, "fma_peak_tflops": peak}
+    if not no_cpu:
+        e["cpu_baseline"] = cpu_baseline_entry(model, T, cpu_sample, dtype, B)
+    return e
+
+
+def deq_chain_entry(model, T, B, dtype, dev, iters):
+    """SURVEY §8(d) secondary number: a `iters`-deep DEQ chain — MPC.forward(al_iter=2) + backward per iteration
+    with duals / penalty / warm start carried (rho: 1 -> 1e12), synthetic network x_ref <- 0.7 x_ref + 0.3 x."""
+    from deq_mpc_corl_b200 import _lib
+    from deq_mpc_corl_b200.al_mpc import MPC
+    from deq_mpc_corl_b200.al_utils import QuadCost
+
+    pb = Problem(model, T, B, dtype, 1003, dev)
+    ctrl = MPC(pb.nx, pb.nu, T, u_lower=pb.inp["u_lower"], u_upper=pb.inp["u_upper"], n_batch=B, dtype=dtype)
+    x_ref0, u_ref = pb.inp["x_ref"].to(dev), pb.inp["u_ref"].to(dev)
+    x0 = pb.inp["x0"].to(dev)
+    Q1 = pb.inp["Qd"].to(dtype).to(dev)
+    gx = torch.randn(B, T, pb.nx, generator=pb.gen).to(dev)
+    gu = torch.randn(B, T, pb.nu, generator=pb.gen).to(dev)
+    counts = []
+
+    def chain(record):
+        ctrl.reinitialize(x_ref0, None)
+        ctrl.x_init, ctrl.u_init = x_ref0.clone(), u_ref.clone()
+        x_ref = x_ref0
+        for it in range(iters):
+            Qd, q, _ = tracking_cost(Q1, x_ref, u_ref, dtype)
+            ql = q.requires_grad_(True)
+            x, u, _ = ctrl(x0, QuadCost(Qd, ql, None), pb.dyn, pb.dyn)
+            torch.autograd.grad((x, u), ql, (gx, gu))
+            if record:
+                counts.append(ctrl.last_info)
+            x_ref = 0.7 * x_ref + 0.3 * x.detach()
+            x_ref[:, 0] = x0
+
+    chain(False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    chain(True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    steps = []
+    for info in counts:
+        info = info.cpu().tolist()
+        steps.append(info[_lib.INFO_NEWTON0:_lib.INFO_NEWTON0 + info[_lib.INFO_AL_DONE]])
+    fl = algorithmic_flops(model, T)
+    flops = sum(sum(s) for s in steps) * fl["newton"] + iters * (2 * fl["dual"] + fl["bwd"])
+    return {"workload": f"{model} T={T} B={B} {'f64' if dtype == torch.float64 else 'f32'}: {iters}-deep DEQ chain through MPC.forward "
+                        f"(al_iter=2 per call, lam/rho/warm start carried, rho 1 -> 1e{2 * iters}) + backward per call",
+            "value": iters * B / (ms * 1e-3), "unit": "solves/s", "ms_per_chain": ms, "newton_steps_per_call": steps,
+            "achieved_tflops": flops * B / (ms * 1e-3) / 1e12,
+            "rho_final": float(ctrl.rho_prev.max())}
+
+
+def streaming_entry(model, T, B, dtype, dev):
+    """BASELINE config 2: cartpole, 6-iteration cold chain, then 2 streaming steps of warm-started calls
+    (`warm_start_initialize`: lam <- 0, rho <- min(rho, 1e4); al_solve_stream semantics: each streaming step runs
+    calls until the rho_max exit reports status=True — the 2+2+1 AL-iteration pattern of SURVEY §8d)."""
+    import types
+
+    from deq_mpc_corl_b200.al_mpc import MPC
+    from deq_mpc_corl_b200.al_utils import QuadCost
+
+    pb = Problem(model, T, B, dtype, 1003, dev)
+    ctrl = MPC(pb.nx, pb.nu, T, u_lower=pb.inp["u_lower"], u_upper=pb.inp["u_upper"], n_batch=B, dtype=dtype)
+    x_ref0, u_ref = pb.inp["x_ref"].to(dev), pb.inp["u_ref"].to(dev)
+    x0 = pb.inp["x0"].to(dev)
+    Q1 = pb.inp["Qd"].to(dtype).to(dev)
+    wargs = types.SimpleNamespace(rho_init_max=1e4)
+    pattern = []
+
+    def run(record):
+        ctrl.reinitialize(x_ref0, None)
+        ctrl.x_init, ctrl.u_init = x_ref0.clone(), u_ref.clone()
+        x_ref = x_ref0
+        calls = 0
+        for it in range(6):
+            Qd, q, _ = tracking_cost(Q1, x_ref, u_ref, dtype)
+            x, u, _ = ctrl(x0, QuadCost(Qd, q, None), pb.dyn, pb.dyn)
+            calls += 1
+            x_ref = 0.7 * x_ref + 0.3 * x.detach()
+            x_ref[:, 0] = x0
+        for s in range(2):
+            xi, ui = ctrl.x_init, ctrl.u_init
+            ui[:, -1:] = u_ref[:, -1:]
+            xi[:, -1:] = x_ref[:, -1:]
+            ctrl.warm_start_initialize(xi, ui, wargs)
+            n_al = []
+            for it in range(6):
+                Qd, q, _ = tracking_cost(Q1, x_ref, u_ref, dtype)
+                x, u, status = ctrl(x0, QuadCost(Qd, q, None), pb.dyn, pb.dyn)
+                calls += 1
+                n_al.append(len(ctrl.newton_steps()))
+                if status:
+                    break
+            if record:
+                pattern.append(n_al)
+        return calls
+
+    run(False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    calls = run(True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"workload": f"{model} T={T} B={B}: 6-call cold DEQ chain + 2 streaming steps (warm start, rho <- min(rho,1e4), "
+                        "calls until the rho_max exit), forward only like the reference's streaming evaluation",
+            "value": calls * B / (ms * 1e-3), "unit": "solves/s (MPC.forward calls x problems / s)", "ms_total": ms,
+            "forward_calls": calls, "al_iterations_per_streaming_call": pattern}
 
 
 def main():
@@ -208,14 +520,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="rex_quadrotor", choices=list(MODEL_SPECS))
     ap.add_argument("--T", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=65536, help="problems per GPU")
+    ap.add_argument("--batch", type=int, default=HEADLINE_BATCH, help="GLOBAL batch, split over the GPUs")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--cpu-sample", type=int, default=None, help="problems in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-suite", action="store_true", help="skip the other BASELINE configurations")
+    ap.add_argument("--no-weak", action="store_true", help="N>1: skip the extra weak-scaling measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.cpu_sample is None:
-        args.cpu_sample = 6144 if args.impl == "b200" else 1024
+        args.cpu_sample = 4096 if args.impl == "b200" else 2048
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -228,11 +542,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the solver has no CPU fallback; use --impl reference for the CPU arm)")
     import torch.distributed as dist
-    from deq_mpc_corl_b200 import _lib
+
     from deq_mpc_corl_b200.al_mpc import MPC
     from deq_mpc_corl_b200.al_utils import QuadCost
-    from deq_mpc_corl_b200.dynamics import make as make_dyn
-    from deq_mpc_corl_b200.solver import SolveConfig, raw_backward, raw_forward
+    from deq_mpc_corl_b200.sharding import shard_bounds
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -245,102 +558,38 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
-    esize = 8 if dtype == torch.float64 else 4
-    model, T, B = args.model, args.T, args.batch
-    spec = MODEL_SPECS[model]
-    nx, nu = spec["nx"], spec["nu"]
-    n, m = nx + nu, T * nx + 2 * T * nu
+    model, T, GB = args.model, args.T, args.batch
+    lo, hi = shard_bounds(GB, world, rank)
 
-    # ---- synthetic inputs (seed differs per rank: every GPU solves different problems)
-    inp = make_inputs(model, T, B, 1003 + rank)
-    Qd_h, q_h, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"], dtype)
-    dyn = make_dyn(model, dt=spec["dt"])
-    cfg = SolveConfig(dyn=dyn, T=T, u_lower=inp["u_lower"].tolist(), u_upper=inp["u_upper"].tolist(), al_iter=2,
-                      rho_f32=(dtype == torch.float64))
-    x0 = inp["x0"].to(dtype).to(dev)
-    Qd, q = Qd_h.to(dev), q_h.to(dev)
-    xu_init = torch.cat([inp["x_ref"], inp["u_ref"]], -1).to(dtype).to(dev).contiguous()
-    lam0 = torch.zeros(B, m, dtype=dtype, device=dev)
-    rho0 = torch.ones(B, dtype=dtype, device=dev)
-    g = torch.Generator().manual_seed(7 + rank)
-    grad_xu = torch.randn(B, T, n, generator=g).to(dtype).to(dev)
+    # ---- this rank's shard of the global batch (strong scaling: total work fixed)
+    pb = Problem(model, T, GB, dtype, 1003, dev, lo, hi)
+    B = pb.B
+    nx, nu, n = pb.nx, pb.nu, pb.n
+    peak_tflops = fma_peak(dtype, dev)
 
-    xu, lam, rho = torch.empty_like(xu_init), torch.empty_like(lam0), torch.empty_like(rho0)
-
-    def device_step():
-        xu.copy_(xu_init)
-        lam.copy_(lam0)
-        rho.copy_(rho0)
-        out = raw_forward(cfg, x0, Qd, q, xu, lam, rho)
-        raw_backward(cfg, out["factor"], xu, grad_xu, need_Q=True)
-        return out
-
-    # ---- FMA-pipe peak (roofline denominator), measured here because MEASURED_PEAKS.json has none
-    lib = _lib.load()
-    import ctypes
-
-    def fma_peak():
-        sink = torch.zeros(256 * 148 * 16, dtype=dtype, device=dev)
-        fl = ctypes.c_double()
-        fn = getattr(lib, "almpc_fma_peak_" + _lib.suffix(dtype))
-        best = 0.0
-        for i in range(6):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _lib.check(fn(148 * 16, 8192, _lib.ptr(sink), ctypes.byref(fl), _lib.stream_ptr()), "fma_peak")
-            e1.record()
-            torch.cuda.synchronize()
-            if i >= 2:
-                best = max(best, fl.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
-        return best
-
-    peak_tflops = fma_peak()
-
-    # ---- warm-up
+    # ---- value: K steps, device resident
+    out = None
     for _ in range(args.warmup):
-        out = device_step()
+        out = pb.device_step()
     torch.cuda.synchronize()
-    info = out["info"].cpu().tolist()
-    newton = info[_lib.INFO_NEWTON0:_lib.INFO_NEWTON0 + info[_lib.INFO_AL_DONE]]
-    n_newton = sum(newton)
-
-    # ---- kernel-level timing for the roofline: CUDA events around every launch inside the library
-    # (almpc_set_profiling), on the stream the kernels are launched on; median of 3 forward solves
-    prof_runs = []
-    lib.almpc_set_profiling(1)
-    for _ in range(3):
-        xu.copy_(xu_init); lam.copy_(lam0); rho.copy_(rho0)
-        raw_forward(cfg, x0, Qd, q, xu, lam, rho)
-        torch.cuda.synchronize()
-        buf = (ctypes.c_double * 8)()
-        lib.almpc_get_profile(buf)
-        prof_runs.append(list(buf))
-    lib.almpc_set_profiling(0)
-    prof_runs.sort(key=lambda r: r[0] + r[1] + r[2])
-    pr = prof_runs[len(prof_runs) // 2]
-    kernel_ms = {"k_jacobian": pr[0] / max(pr[4], 1), "k_factor_solve": pr[1] / max(pr[5], 1),
-                 "k_line_search": pr[2] / max(pr[6], 1)}
-    newton_launch_ms = sum(kernel_ms.values())
-
-    # ---- timed region: K steps, device resident
+    newton = pb.newton_counts(out)
+    kernel_ms, fused = pb.kernel_profile()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        device_step()
-    e1.record()
-    barrier()
-    el_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(el_ms, op=dist.ReduceOp.MAX)
-    el_ms = el_ms.item()
+    el_ms, _ = timed(pb.device_step, args.steps, 0, barrier)
+    el_ms = max_over_ranks(el_ms)
 
     # ---- e2e: reference-facing MPC module, pinned host buffers, H2D + D2H inside the timed region
-    ctrl = MPC(nx, nu, T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B, dtype=dtype)
+    ctrl = MPC(nx, nu, T, u_lower=pb.inp["u_lower"], u_upper=pb.inp["u_upper"], n_batch=B, dtype=dtype)
+    g = pb.gen
     pin = lambda t: t.contiguous().pin_memory()
-    h = dict(x0=pin(inp["x0"]), Qd=pin(Qd_h), q=pin(q_h), x_ref=pin(inp["x_ref"]), u_ref=pin(inp["u_ref"]),
+    h = dict(x0=pin(pb.inp["x0"]), Qd=pin(pb.Qd_h), q=pin(pb.q_h), x_ref=pin(pb.inp["x_ref"]), u_ref=pin(pb.inp["u_ref"]),
              gx=pin(torch.randn(B, T, nx, generator=g)), gu=pin(torch.randn(B, T, nu, generator=g)))
     out_h = dict(x=torch.empty(B, T, nx).pin_memory(), u=torch.empty(B, T, nu).pin_memory(),
                  qg=torch.empty(B, T, n, dtype=dtype).pin_memory())
@@ -358,7 +607,7 @@ def main():
         ev_free = [torch.cuda.Event() for _ in range(2)]
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-        def h2d(i):
+        def h2d_copy(i):
             with torch.cuda.stream(s_in):
                 s_in.wait_event(ev_free[i])
                 for k, v in hin.items():
@@ -370,11 +619,11 @@ def main():
         t0.record(cur)
         s_in.wait_event(t0)
         s_out.wait_event(t0)
-        h2d(0)
+        h2d_copy(0)
         for j in range(k_steps):
             i = j & 1
             if j + 1 < k_steps:
-                h2d(i ^ 1)
+                h2d_copy(i ^ 1)
             cur.wait_event(ev_in[i])
             res = solve(bufs[i])
             ev_free[i].record(cur)
@@ -396,7 +645,7 @@ def main():
         ctrl.reinitialize(d["x_ref"], None)
         ctrl.x_init, ctrl.u_init = d["x_ref"], d["u_ref"]
         ql = d["q"].detach().requires_grad_(True)
-        x, u, _ = ctrl(d["x0"], QuadCost(d["Qd"], ql, None), dyn, dyn)
+        x, u, _ = ctrl(d["x0"], QuadCost(d["Qd"], ql, None), pb.dyn, pb.dyn)
         qg, = torch.autograd.grad((x, u), ql, (d["gx"], d["gu"]))
         return dict(x=x.detach(), u=u.detach(), qg=qg)
 
@@ -405,17 +654,8 @@ def main():
         for k, t in res.items():
             out_h[k].copy_(t, non_blocking=True)
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
     k_e2e = max(3, args.steps // 2)
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for _ in range(k_e2e):
-        e2e_step()
-    e3.record()
-    barrier()
-    e2e_serial_ms = torch.tensor([e2.elapsed_time(e3)], device=dev, dtype=torch.float64)
+    e2e_serial_ms, _ = timed(e2e_step, k_e2e, 2, barrier)
     torch.cuda.synchronize()
     serial_out = {k: v.clone() for k, v in out_h.items()}
     for v in out_h.values():
@@ -423,27 +663,26 @@ def main():
     pipelined_ms(e2e_solve, h, out_h, 6)  # warm-up: the caching allocator needs a few steps to reach steady state
     barrier()
     k_pipe = max(4, args.steps)
-    e2e_ms = torch.tensor([pipelined_ms(e2e_solve, h, out_h, k_pipe)], device=dev, dtype=torch.float64)
+    e2e_ms = pipelined_ms(e2e_solve, h, out_h, k_pipe)
     # the overlapped copies must deliver exactly what the serial path delivers (same inputs every step)
     e2e_verified = all(torch.equal(out_h[k], serial_out[k]) for k in out_h)
     if not e2e_verified:
         raise RuntimeError("pipelined e2e results differ from the serial e2e results")
     barrier()
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_serial_ms, op=dist.ReduceOp.MAX)
-    e2e_ms = e2e_ms.item()
-    e2e_serial_ms = e2e_serial_ms.item()
+    e2e_ms, e2e_serial_ms = max_over_ranks(e2e_ms), max_over_ranks(e2e_serial_ms)
+
     # ---- e2e one level up: Tracking_MPC (the reference's actual caller, policies.py:1117-1315): host inputs are
     # the fp32 network outputs (x0, x_ref, u_ref) + output grads; the cost build and its chain rule run fused
     import types as _types
+
     from deq_mpc_corl_b200.tracking import Tracking_MPC
 
+    spec = pb.spec
     targs = _types.SimpleNamespace(T=T, bsz=B, Q=torch.tensor(spec["Q"]), R=torch.tensor(spec["R"]),
                                    dtype="double" if dtype == torch.float64 else "float", device=dev,
                                    solver_type="al", env=model, rho_init_max=1e4)
-    tenv = _types.SimpleNamespace(nx=nx, nu=nu, nq=None, dt=spec["dt"], dynamics=dyn, dynamics_derivatives=dyn,
-                                  action_space=_types.SimpleNamespace(low=inp["u_lower"].numpy(), high=inp["u_upper"].numpy()))
+    tenv = _types.SimpleNamespace(nx=nx, nu=nu, nq=None, dt=spec["dt"], dynamics=pb.dyn, dynamics_derivatives=pb.dyn,
+                                  action_space=_types.SimpleNamespace(low=pb.inp["u_lower"].numpy(), high=pb.inp["u_upper"].numpy()))
     tm = Tracking_MPC(targs, tenv)
     th = dict(x0=h["x0"], x_ref=h["x_ref"], u_ref=h["u_ref"], gx=h["gx"], gu=h["gu"])
     tout = dict(x=out_h["x"], u=out_h["u"], gxr=torch.empty(B, T, nx).pin_memory(), gur=torch.empty(B, T, nu).pin_memory())
@@ -459,81 +698,73 @@ def main():
 
     pipelined_ms(e2e_tracking_solve, th, tout, 6)
     barrier()
-    e2e_t_ms = torch.tensor([pipelined_ms(e2e_tracking_solve, th, tout, k_pipe)], device=dev, dtype=torch.float64)
-    barrier()
-    if world > 1:
-        dist.all_reduce(e2e_t_ms, op=dist.ReduceOp.MAX)
-    e2e_t_ms = e2e_t_ms.item()
+    e2e_t_ms = max_over_ranks(pipelined_ms(e2e_tracking_solve, th, tout, k_pipe))
     clocks = sampler.stop() if sampler else None
 
+    # ---- N>1: the weak-scaling point (every GPU solves a whole headline batch) as an extra key
+    weak = None
+    if world > 1 and not args.no_weak:
+        wpb = Problem(model, T, GB, dtype, 1003 + rank, dev)
+        w_ms, _ = timed(wpb.device_step, args.steps, 3, barrier)
+        w_ms = max_over_ranks(w_ms)
+        weak = {"scaling": "weak", "batch_per_gpu": GB, "global_batch": GB * world,
+                "value": args.steps * GB * world / (w_ms * 1e-3), "unit": "solves/s", "ms_per_step": w_ms / args.steps}
+        del wpb
+
     if rank == 0:
-        fl = algorithmic_flops(model, T)
-        by = algorithmic_bytes(model, T, esize)
-        fma_name = "fp64_fma" if dtype == torch.float64 else "fp32_fma"
-        ach_tflops = fl["newton"] * B / (newton_launch_ms * 1e-3) / 1e12
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        hbm_ach = by["newton_launch"] * B / (newton_launch_ms * 1e-3) / 1e9
-        kw = kernel_work(model, T, esize)
-        kernels = {}
-        for kn, ms in kernel_ms.items():
-            tf = kw[kn]["flops"] * B / (ms * 1e-3) / 1e12
-            gb = kw[kn]["bytes"] * B / (ms * 1e-3) / 1e9
-            kernels[kn] = {"avg_launch_ms": ms, "flops_per_problem": kw[kn]["flops"], "bytes_per_problem": kw[kn]["bytes"],
-                           "fma_tflops": tf, "fma_frac": tf / peak_tflops, "hbm_gbs": gb, "hbm_frac": gb / hbm_peak,
-                           "algorithmic_bytes_per_launch": kw[kn]["bytes"] * B,
-                           "traffic": NCU_TRAFFIC.get((model, T, B, args.dtype), {}).get(kn)}
-        dom = max(kernel_ms, key=kernel_ms.get)
-        dk = kernels[dom]
-        dom_fma = dk["fma_frac"] >= dk["hbm_frac"]
-        value = args.steps * B * world / (el_ms * 1e-3)
+        known = "hbm_gbs" in peaks
+        rf = roofline_block(pb, kernel_ms, fused, peak_tflops, hbm_peak, known, args.dtype)
+        fl = algorithmic_flops(model, T)
+        value = args.steps * GB / (el_ms * 1e-3)
+        launches_per_step = pb.cfg.al_iter * pb.cfg.max_newton * len(kernel_ms) + 2  # step kernels per Newton slot + final dual + backward
+        flops_solve = fl["newton"] * sum(newton) + 2 * fl["dual"] + fl["bwd"]
         line = {
-            "metric": "AL-MPC solves/sec (fwd+implicit bwd)", "value": value, "unit": "solves/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": el_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": workload_config(args, B, world),
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": workload_config(args),
+            "batch_per_gpu": B,
             "newton_steps_per_al_iter": newton,
+            "fused_newton_tail": fused,
             "clocks": clocks,
-            "e2e": {"value": k_pipe * B * world / (e2e_ms * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / k_pipe, "steps": k_pipe, "matches_serial": e2e_verified,
+            "e2e": {"value": k_pipe * GB / (e2e_ms * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms / k_pipe, "steps": k_pipe, "matches_serial": e2e_verified,
                     "api": "deq_mpc_corl_b200.al_mpc.MPC.forward + autograd backward; every step copies its inputs "
                            "from pinned host buffers and its results back, double-buffered: the H2D of step j+1 and the "
                            "D2H of step j-1 run on copy streams under the solve of step j",
-                    "serial": {"value": k_e2e * B * world / (e2e_serial_ms * 1e-3), "ms_per_step": e2e_serial_ms / k_e2e,
-                               "note": "same step with copy-in, solve, copy-out serialised on one stream"}},
-            "e2e_tracking": {"value": k_pipe * B * world / (e2e_t_ms * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": t_h2d,
-                             "d2h_bytes_per_step": t_d2h, "ms_per_step": e2e_t_ms / k_pipe,
+                    "serial": {"value": k_e2e * GB / (e2e_serial_ms * 1e-3), "ms_per_step": e2e_serial_ms / k_e2e,
+                               "note": "same step with copy-in, solve, copy-out serialised on one stream"},
+                    "note": "N>1: all ranks share the host's DRAM / PCIe root for their pinned copies — the only non-linear term of the multi-GPU run besides wave quantisation (no collective is involved)"},
+            "e2e_tracking": {"value": k_pipe * GB / (e2e_t_ms * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": t_h2d * world,
+                             "d2h_bytes_per_step": t_d2h * world, "ms_per_step": e2e_t_ms / k_pipe,
                              "api": "deq_mpc_corl_b200.tracking.Tracking_MPC.forward (fused cost build) + autograd backward to x_ref/u_ref; same double-buffered copies"},
-            "gpu_launches": args.steps * (cfg.al_iter * cfg.max_newton * 3 + 2),  # 3 kernels per Newton-step slot + final dual + backward
-            "roofline": {
-                # dominant kernel by time, against whichever of its two rooflines it sits closer to
-                "kernel": dom, "bound": (fma_name if dom_fma else "hbm"),
-                "achieved": dk["fma_tflops"] if dom_fma else dk["hbm_gbs"],
-                "peak": peak_tflops if dom_fma else hbm_peak, "unit": "TFLOP/s" if dom_fma else "GB/s",
-                "frac": dk["fma_frac"] if dom_fma else dk["hbm_frac"], "avg_launch_ms": dk["avg_launch_ms"],
-                "traffic": dk["traffic"],
-                "peak_source": {"fma": "measured in this run by almpc_fma_peak (8 independent FMA chains/thread); MEASURED_PEAKS.json has no FP64/FP32 FMA figure",
-                                "hbm": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
-                "kernels": kernels,
-                # the whole Newton step (3 launches) against the FMA roofline that binds the path
-                "newton_step": {"bound": fma_name, "achieved": ach_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-                                "frac": ach_tflops / peak_tflops, "flops_per_problem": fl["newton"],
-                                "ms": newton_launch_ms,
-                                "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                                        "bytes_per_problem": by["newton_launch"]}},
-            },
-            "flops_per_solve": fl["newton"] * n_newton + 2 * fl["dual"] + fl["bwd"],
+            "gpu_launches": args.steps * launches_per_step,
+            "roofline": rf,
+            "flops_per_solve": flops_solve,
+            "achieved_tflops_whole_solve_per_gpu": flops_solve * GB / (el_ms / args.steps * 1e-3) / 1e12 / world,
         }
-        if not args.no_cpu_baseline and world == 1:
-            v, steps, secs = cpu_oracle_run(model, T, args.cpu_sample, dtype, 1003)
-            line["cpu_baseline"] = {
-                "value": v, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
-                "sample": f"{args.cpu_sample} of the {B} problems, 1 fwd+bwd, {secs:.1f} s, oracle port of qpth AL_mpc "
-                          f"(torch {torch.__version__} CPU, {os.cpu_count()} threads), newton steps {steps}"}
+        if weak:
+            line["weak"] = weak
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_entry(model, T, args.cpu_sample, dtype, GB)
+        if world == 1 and not args.no_suite:
+            del pb
+            torch.cuda.empty_cache()
+            nc = args.no_cpu_baseline
+            f32_peak = fma_peak(torch.float32, dev)
+            line["suite"] = {
+                "quadrotor_64k_f32": suite_entry("rex_quadrotor", 5, 65536, torch.float32, dev, 5, 1024, f32_peak, hbm_peak, known, nc),
+                "quadrotor_64k_deq_chain6": deq_chain_entry("rex_quadrotor", 5, 65536, torch.float64, dev, 6),
+                "pendulum_b200": suite_entry("pendulum", 5, 200, torch.float64, dev, 50, 200, peak_tflops, hbm_peak, known, nc),
+                "cartpole_4k_streaming": streaming_entry("cartpole1l", 5, 4096, torch.float64, dev),
+                "flying_cartpole_T10_16k": suite_entry("flying_cartpole", 10, 16384, torch.float64, dev, 5, 512, peak_tflops, hbm_peak, known, nc),
+            }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

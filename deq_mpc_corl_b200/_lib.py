@@ -40,10 +40,39 @@ class Desc(ctypes.Structure):
         ("u_lower", ctypes.c_double * MAX_NU),
         ("u_upper", ctypes.c_double * MAX_NU),
         ("n_obs", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("select", ctypes.c_int32),
         ("obs_radius", ctypes.c_double),
         ("obstacles", ctypes.c_void_p),
+        ("profile_ms", ctypes.POINTER(ctypes.c_double)),
+        ("stop_stats", ctypes.c_void_p),
+        ("stop_reduce", ctypes.c_void_p),
+        ("stop_reduce_user", ctypes.c_void_p),
+        ("tune", ctypes.c_int32 * 4),
     ]
+
+
+# int (*almpc_stop_reduce_fn)(double* stats_dev, void* stream, void* user)
+STOP_REDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
+
+SELECT_FAC_SINGLE, SELECT_NO_FUSE, SELECT_LS_CTA, SELECT_PDL = 1, 2, 4, 8
+
+
+def env_tune():
+    """desc.tune from ALMPC_TUNE="a,b,c,d" (measurement knobs; empty = library defaults)."""
+    v = os.environ.get("ALMPC_TUNE", "")
+    out = [0, 0, 0, 0]
+    for i, t in enumerate(v.split(",")[:4]):
+        if t.strip():
+            out[i] = int(t)
+    return out
+
+
+def env_select():
+    """desc.select from the environment (A/B measurements, differential tests): ALMPC_FAC_SINGLE, ALMPC_NO_FUSE,
+    ALMPC_LS_CTA, ALMPC_PDL.  Read per call on the host side; the library itself has no global state."""
+    e = os.environ
+    return ((SELECT_FAC_SINGLE if e.get("ALMPC_FAC_SINGLE") else 0) | (SELECT_NO_FUSE if e.get("ALMPC_NO_FUSE") else 0)
+            | (SELECT_LS_CTA if e.get("ALMPC_LS_CTA") else 0) | (SELECT_PDL if e.get("ALMPC_PDL") else 0))
 
 
 FLAG_SKIP_FINAL_DUAL = 1
@@ -80,7 +109,7 @@ def load():
         f.argtypes = [dp] + [vp] * 15
         f.restype = ctypes.c_int
         b = getattr(lib, "almpc_backward_" + sfx)
-        b.argtypes = [dp] + [vp] * 6
+        b.argtypes = [dp] + [vp] * 7
         b.restype = ctypes.c_int
         d = getattr(lib, "almpc_dynamics_" + sfx)
         d.argtypes = [dp, i64] + [vp] * 6
@@ -99,10 +128,6 @@ def load():
         f = getattr(lib, "almpc_blocktri_" + sfx)
         f.argtypes = [i32] * 5 + [vp] * 8
         f.restype = ctypes.c_int
-    lib.almpc_set_profiling.argtypes = [i32]
-    lib.almpc_set_profiling.restype = None
-    lib.almpc_get_profile.argtypes = [ctypes.POINTER(dbl)]
-    lib.almpc_get_profile.restype = None
     _lib = lib
     return lib
 
@@ -113,7 +138,7 @@ EXPORTS = [
     "almpc_dynamics_f64", "almpc_dynamics_f32", "almpc_fma_peak_f64", "almpc_fma_peak_f32",
     "almpc_tracking_cost_f64", "almpc_tracking_cost_f32", "almpc_tracking_cost_bwd_f64", "almpc_tracking_cost_bwd_f32",
     "almpc_blocktri_f64", "almpc_blocktri_f32",
-    "almpc_set_profiling", "almpc_get_profile", "almpc_last_error", "almpc_version",
+    "almpc_last_error", "almpc_version",
 ]
 
 

@@ -77,6 +77,9 @@ class MPC(Module):
         # a few hundred problems, e.g. the reference's bsz = 200 training runs).  Fused native path only.
         self.cuda_graph = False
         self._graph_cache = None
+        # opt-in: a sharding.GlobalStop -> the reference's batch-GLOBAL stop rule / rho_max exit across the ranks of a
+        # sharded batch (default None: every shard applies the rule to its own problems)
+        self.global_stop = None
         self.last_info = None      # device int32[INFO_INTS] of the latest solve (no sync to keep it)
         self.last_status = None    # device int32[B] per-problem status bits
         self._bounds_host = (self.u_lower.double().cpu().tolist(), self.u_upper.double().cpu().tolist())
@@ -135,7 +138,8 @@ class MPC(Module):
         if dyn is not None:
             solve = ALSolve
             cfg = SolveConfig(dyn=dyn, u_lower=self._bounds_host[0], u_upper=self._bounds_host[1], **common, **extra)
-            if self.cuda_graph:
+            cfg.global_stop = self.global_stop
+            if self.cuda_graph and self.global_stop is None:
                 if self._graph_cache is None:
                     from .solver import GraphCache
 

@@ -60,7 +60,10 @@ struct KParams {
   S ulo[ALMPC_MAX_NU], uhi[ALMPC_MAX_NU];
   double rho_mult, rho_max;
   int B, T, al_iter, max_newton, stream_mode, rho_f32, flags;
-  int part_off, ticket_total;  // k_line_search: slot offset of this part's CTA partials / CTAs of all parts
+  int part_off, ticket_total;  // line search: slot offset of the CTA partials / CTAs that take a ticket
+  int stagger, n_sm;           // k_newton_pair: start-up delay (cycles) per warp slot of an SM / SMs of the device
+  int global_stop;             // 1: the last CTA publishes this shard's statistics instead of steering (k_steer does)
+  double* stop_stats;          // device [4]: sum ||c+||^2 at entry, at exit, max rho — reduced over the shards by the caller
   int n_obs;                   // obstacle rows per stage (Obstacle_MPC), 0 = none
   S obs_r2;                    // obstacle radius squared
   const S* obs;                // [B][T][n_obs][3] obstacle centres (device)
@@ -80,7 +83,8 @@ __device__ __forceinline__ double rsqrt_(double x) {
   return fma(y * r, p, y);
 }
 __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
-template <typename S> __device__ __forceinline__ S fmax0(S x) { return x > S(0) ? x : S(0); }
+// max(x, 0) that propagates NaN like torch.clamp(min=0) (AL_mpc.py:317, al_utils.py:419)
+template <typename S> __device__ __forceinline__ S fmax0(S x) { return x < S(0) ? S(0) : x; }
 // one entry of the quadratic cost (al_utils.py:425-435), 1/2 Q z^2 + q z as z (1/2 (Q z) + q): one multiply and two
 // fused multiply-adds.  Every kernel that evaluates a merit uses THIS form, so entry merit and candidates agree.
 template <typename S> __device__ __forceinline__ S cost_term(S z, S Q, S q) { return z * (S(0.5) * (Q * z) + q); }

@@ -628,36 +628,49 @@ __device__ __forceinline__ void half_copy_block_async(S* dst, const S* src, int 
   }
 }
 
-// small blocks (and fp32) keep little in shared memory, so their occupancy is set by registers: cap them for
-// 12 (10) CTAs / SM; the fp64 quadrotor is limited to 6 by shared memory anyway and may use up to 170 registers
-template <int NX, int NU, typename S, int WPB, int V>
-__global__ void __launch_bounds__(WPB * 32, (NX + NU <= 8) ? 12 : (sizeof(S) == 4 ? 10 : 6))
-k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restrict__ q_g,
-                    const S* __restrict__ xu_g, S* __restrict__ lam_g, S* __restrict__ rho_g, S* fac_g,
-                    const S* __restrict__ G_g, const S* __restrict__ c_g, S* __restrict__ d_g,
-                    S* __restrict__ merit_g, double* __restrict__ rentry_g, int* __restrict__ status_g,
-                    S* __restrict__ debug_g, const Ctl* __restrict__ ctl) {
+// What the factor phase of one half-warp hands to the caller (the fused Newton-tail kernel continues with the line
+// search on the same problems without a trip through global memory).
+template <typename S>
+struct PairCarry {
+  S rho;        // penalty used by this Newton step (after the dual update of MODE_DUAL_NEWTON)
+  S s2_entry;   // ||c+||^2 at the entry point
+  S merit;      // merit at the entry point (valid when mode != MODE_CONT)
+  int status;   // per-problem status bits after this factorisation
+  int prob;     // problem of this half-warp (the neighbour's when !live)
+  bool ok;      // every pivot positive / direction finite
+  bool live;    // false: odd batch, this half-warp duplicates its neighbour and must store nothing
+};
+
+// The factor phase proper: one HALF-warp = one problem.  Returns false for a warp without problems.
+//   FUSED = false: stand-alone kernel k_factor_solve_pair (direction, merit, entry residual and status go to global
+//                  memory for k_line_search)
+//   FUSED = true : called by k_newton_pair (almpc_fused.cuh); the direction stays in shared memory (dv, sign
+//                  flipped by the caller), merit / entry residual / status stay in registers (PairCarry)
+template <int NX, int NU, typename S, int WPB, int V, bool FUSED>
+__device__ __forceinline__ bool factor_pair(const KParams<S>& P, const S* __restrict__ Qd_g, const S* __restrict__ q_g,
+                                            const S* xu_g, S* lam_g, S* __restrict__ rho_g,
+                                            S* fac_g, const S* __restrict__ G_g, const S* __restrict__ c_g,
+                                            S* __restrict__ d_g, S* __restrict__ merit_g,
+                                            double* __restrict__ rentry_g, int* __restrict__ status_g,
+                                            S* __restrict__ debug_g, const int mode, unsigned char* smem_raw,
+                                            const int smem_per_problem, const int pw, PairCarry<S>& out) {
   constexpr int NN = NX + NU;
   static_assert(NN <= 16 && NX + 1 <= 16, "pair mapping: both row sets must fit a half-warp");
   constexpr int LD = ScrLd<NN>::LD;
   constexpr int LB = NN | 1;
   constexpr bool SE = (V == 2);
   static_assert(V != 1, "obstacle rows are compiled for the row-per-lane kernel only");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  grid_dep_wait();
-  const int mode = ctl->mode;
-  if (mode == MODE_DONE) return;
   const int T = P.T;
   const Layout<NX, NU> L(T, 0, SE, true);
   constexpr int SI = 2 * NU;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
-  const int pw = (blockIdx.x * WPB + warp) * 2;  // first problem of this warp
-  if (pw >= P.B) return;
+  if (pw >= P.B) return false;  // pw = first problem of this warp
   // an odd batch leaves the last half-warp without a problem: it recomputes its neighbour's and stores nothing
   const bool live = pw + half < P.B;
   const int prob = live ? pw + half : pw;
-  S* smw = reinterpret_cast<S*>(smem_raw) + (size_t)warp * 2 * L.total;
-  S* sm = smw + (size_t)half * L.total;
+  // smem_per_problem >= L.total (the fused kernel may need more room for its line-search staging area)
+  S* smw = reinterpret_cast<S*>(smem_raw) + (size_t)warp * 2 * smem_per_problem;
+  S* sm = smw + (size_t)half * smem_per_problem;
   S* xu = sm + L.xu;
   S* dv = sm + L.dv;
   S* wv = sm + L.w;
@@ -776,10 +789,14 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
     s2 = half_sum(s2);
     sl = half_sum(sl);
     cost = half_sum(cost);
+    out.s2_entry = s2;
+    out.merit = cost + S(0.5) * rho * s2 + sl;
     if (hl == 0 && live) {
       if (dual) rho_g[prob] = rho;
-      rentry_g[prob] = (double)s2;
-      if (mode != MODE_CONT) merit_g[prob] = cost + S(0.5) * rho * s2 + sl;
+      if constexpr (!FUSED) {
+        rentry_g[prob] = (double)s2;
+        if (mode != MODE_CONT) merit_g[prob] = out.merit;
+      }
     }
   }
   __syncwarp();
@@ -833,7 +850,7 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
     // Hessian blocks of both problems: the DMMA assembly is warp-wide, one problem after the other
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-      S* smp = smw + (size_t)p * L.total;
+      S* smp = smw + (size_t)p * smem_per_problem;
       S* Xp = (X == Gt) ? smp + L.Gt : smp + L.Ep;
       S* Yp = (X == Gt) ? smp + L.Ep : smp + L.Gt;
       build_block<NX, NU, S>(smp + L.scr + 64, smp + L.xu + t * NN, Xp, Yp, has_G, has_E, lane, rho_p[p],
@@ -963,18 +980,44 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
   for (int i = hl; i < L.N; i += 16) okl = okl && finite_(dv[i]);
   const unsigned okm = __ballot_sync(FULL, okl);
   const bool ok = ((okm >> (half * 16)) & 0xffffu) == 0xffffu;
+  int status = ALMPC_STATUS_FINITE | ALMPC_STATUS_CHOL_OK;
+  if (mode != MODE_FIRST && hl == 0) status = status_g[prob];
+  if (!ok) status &= ~ALMPC_STATUS_CHOL_OK;
   if (live) {
-    for (int i = hl; i < L.N; i += 16) {
-      const S d = ok ? -dv[i] : S(0);
-      d_g[pN + i] = d;
-      if (dbg) dbg[L.N + i] = d;
+    if (!FUSED || dbg) {
+      for (int i = hl; i < L.N; i += 16) {
+        const S d = ok ? -dv[i] : S(0);
+        if constexpr (!FUSED) d_g[pN + i] = d;
+        if (dbg) dbg[L.N + i] = d;
+      }
     }
-    if (hl == 0) {
-      int status = (mode == MODE_FIRST) ? (ALMPC_STATUS_FINITE | ALMPC_STATUS_CHOL_OK) : status_g[prob];
-      if (!ok) status &= ~ALMPC_STATUS_CHOL_OK;
-      status_g[prob] = status;
-    }
+    if (!FUSED && hl == 0) status_g[prob] = status;
   }
+  out.rho = rho;
+  out.status = status;  // meaningful on lane hl == 0 of each half-warp
+  out.prob = prob;
+  out.ok = ok;
+  out.live = live;
+  return true;
+}
+
+// small blocks (and fp32) keep little in shared memory, so their occupancy is set by registers: cap them for
+// 12 (10) CTAs / SM; the fp64 quadrotor is limited to 6 by shared memory anyway and may use up to 170 registers
+template <int NX, int NU, typename S, int WPB, int V>
+__global__ void __launch_bounds__(WPB * 32, (NX + NU <= 8) ? 12 : (sizeof(S) == 4 ? 10 : 6))
+k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restrict__ q_g,
+                    const S* __restrict__ xu_g, S* __restrict__ lam_g, S* __restrict__ rho_g, S* fac_g,
+                    const S* __restrict__ G_g, const S* __restrict__ c_g, S* __restrict__ d_g,
+                    S* __restrict__ merit_g, double* __restrict__ rentry_g, int* __restrict__ status_g,
+                    S* __restrict__ debug_g, const Ctl* __restrict__ ctl) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  grid_dep_wait();
+  const int mode = ctl->mode;
+  if (mode == MODE_DONE) return;
+  PairCarry<S> carry;
+  const Layout<NX, NU> L(P.T, 0, V == 2, true);
+  factor_pair<NX, NU, S, WPB, V, false>(P, Qd_g, q_g, xu_g, lam_g, rho_g, fac_g, G_g, c_g, d_g, merit_g, rentry_g, status_g,
+                                        debug_g, mode, smem_raw, L.total, (int)(blockIdx.x * WPB + (threadIdx.x >> 5)) * 2, carry);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -983,7 +1026,7 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
 template <int NX, int NU, typename S, int WPB>
 __global__ void __launch_bounds__(WPB * 32)
 k_backward(int B, int T, const S* __restrict__ fac_g, const S* __restrict__ xu_g, const S* __restrict__ grad_g,
-           S* __restrict__ gQ_g, S* __restrict__ gq_g) {
+           const int* __restrict__ status_g, S* __restrict__ gQ_g, S* __restrict__ gq_g) {
   constexpr int NN = NX + NU;
   constexpr int LB = NN | 1;  // odd row stride of the staged blocks: rows AND columns per lane are conflict free
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1077,10 +1120,16 @@ k_backward(int B, int T, const S* __restrict__ fac_g, const S* __restrict__ xu_g
     __syncwarp();
     cur = nxt;
   }
-  // a factor with non-positive pivots (flagged in the forward status) yields no gradient instead of NaNs
+  // A factor with non-positive pivots (flagged in the forward status) yields no gradient instead of NaNs.  With the
+  // status the zeroing is limited to exactly those problems, so a non-finite UPSTREAM gradient propagates like in
+  // the reference (al_utils.py:585-597) instead of turning into an exact zero.
   bool fin = true;
-  for (int i = lane; i < N; i += 32) fin = fin && finite_(dv[i]);
-  fin = __all_sync(FULL, fin);
+  if (status_g) {
+    fin = (status_g[prob] & ALMPC_STATUS_CHOL_OK) != 0;
+  } else {
+    for (int i = lane; i < N; i += 32) fin = fin && finite_(dv[i]);
+    fin = __all_sync(FULL, fin);
+  }
   for (int i = lane; i < N; i += 32) {
     const S g = fin ? -dv[i] : S(0);
     gq_g[pN + i] = g;

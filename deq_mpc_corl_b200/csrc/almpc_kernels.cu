@@ -30,6 +30,9 @@
 #include "almpc_dynamics_kernels.cuh"
 #include "almpc_factor.cuh"
 #include "almpc_linesearch.cuh"
+#include "almpc_fused.cuh"
+
+#include <mutex>
 
 namespace almpc {
 
@@ -61,6 +64,8 @@ static KParams<S> make_params(const almpc_desc* d) {
   P.B = d->B; P.T = d->T; P.al_iter = d->al_iter; P.max_newton = d->max_newton;
   P.stream_mode = d->stream_mode; P.rho_f32 = d->rho_f32; P.flags = d->flags;
   P.part_off = 0; P.ticket_total = 0;
+  P.global_stop = 0; P.stop_stats = nullptr;
+  P.stagger = 0; P.n_sm = 1;
   P.n_obs = d->obstacles ? d->n_obs : 0;
   P.obs_r2 = (S)(d->obs_radius * d->obs_radius);
   P.obs = (const S*)d->obstacles;
@@ -79,17 +84,8 @@ static int check_desc(const almpc_desc* d) {
 }
 
 constexpr int kWPB = 4;
-constexpr int kMaxParts = 4;
 
-// optional per-kernel timing (bench.py): events around every launch of one forward call
-// (shared by the two translation units: defined in the fp64 unit)
-#if ALMPC_BUILD_F64 && !ALMPC_BUILD_SE
-int g_profile_on = 0;
-double g_profile[8] = {0};  // ms: [0] jacobian [1] factor_solve [2] line_search [3] final_dual, [4..7] launch counts
-#else
-extern int g_profile_on;
-extern double g_profile[8];
-#endif
+// Per-call profiling (desc.profile_ms != NULL): events around every launch of this forward call.
 struct ProfEv { cudaEvent_t a, b; int kind; };
 
 static int n_blocks(int B) { return (B + kWPB - 1) / kWPB; }
@@ -119,7 +115,11 @@ static WsPlan ws_plan(int B, int T, int nx, int nu, size_t es) {
   WsPlan w;
   size_t o = 0;
   w.ctl = o; o += 256;
-  w.partials = o; o = up(o + ((size_t)ls_geom(B, T).blocks + kMaxParts) * 4 * sizeof(double));
+  // one slot of statistics per CTA of the kernel that runs the line search: the stand-alone kernels use at most
+  // ls_geom().blocks CTAs, the fused Newton-tail kernel one CTA per 4 problems
+  size_t slots = (size_t)ls_geom(B, T).blocks;
+  if (slots < (size_t)(B + 3) / 4) slots = (size_t)(B + 3) / 4;
+  w.partials = o; o = up(o + (slots + 4) * 4 * sizeof(double));
   w.merit = o; o = up(o + (size_t)B * es);
   w.rentry = o; o = up(o + (size_t)B * sizeof(double));
   w.status = o; o = up(o + (size_t)B * sizeof(int32_t));
@@ -147,18 +147,31 @@ static cudaError_t launch_k(void (*k)(KArgs...), unsigned grid, unsigned block, 
   return cudaLaunchKernelEx(&cfg, k, KArgs(args)...);
 }
 
+// Opt-in dynamic shared memory of a kernel, raised to everything the device allows next to the kernel's static
+// shared memory.  Plans are cached per horizon while this limit is an attribute of the FUNCTION: with the maximum set
+// once, a plan made for a short horizon never lowers the limit under a cached plan for a longer one.
+template <typename F>
+static cudaError_t allow_max_smem(F fn, int optin) {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, (const void*)fn);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+}
+
 constexpr int kWLS = 4;  // warps per CTA of the warp-synchronous line search
+constexpr int kDefaultStagger = 8000;  // cycles per warp slot, k_newton_pair (measured: profiles/r02_stagger_sweep.md)
 
 struct LsWarpCfg { const void* fn; int grid_cap; size_t smem; int pw; };
 
 template <class M, typename S, int TM1, int V>
-static cudaError_t ls_warp_cfg(LsWarpCfg& c, int n_sm, int n_obs) {
+static cudaError_t ls_warp_cfg(LsWarpCfg& c, int n_sm, int n_obs, int smem_optin) {
   constexpr int PW = (8 / TM1) > 0 ? (8 / TM1) : 1;
   const LsLayout<M::NX, M::NU> LL(TM1 + 1, n_obs, V == 2);
   auto k = k_line_search_warp<M, S, TM1, kWLS, V>;
   size_t smem = (size_t)kWLS * PW * LL.part * sizeof(S);
   if (smem < (size_t)kWLS * 32 * 3 * sizeof(double)) smem = (size_t)kWLS * 32 * 3 * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > (size_t)smem_optin) return cudaErrorInvalidValue;
+  cudaError_t e = allow_max_smem(k, smem_optin);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kWLS * 32, smem);
@@ -172,11 +185,150 @@ static cudaError_t ls_warp_cfg(LsWarpCfg& c, int n_sm, int n_obs) {
 
 // the half-warp-per-problem factor kernel exists for blocks that fit a half-warp (n <= 16, nx + 1 <= 16) and
 // for the variants without obstacle rows
-constexpr int kWPP = 2;  // warps per CTA of the pair kernel (4 problems per CTA)
+constexpr int kWPP = 2;  // warps per CTA of the pair kernels (4 problems per CTA)
 template <int NX, int NU, typename S, int V>
 static auto pair_kernel() -> decltype(&k_factor_solve<NX, NU, S, kWPB, V>) {
   if constexpr (NX + NU <= 16 && NX + 1 <= 16 && V != 1) return &k_factor_solve_pair<NX, NU, S, kWPP, V>;
   else return nullptr;
+}
+template <typename S>
+using FusedFn = void (*)(const KParams<S>, const S*, const S*, const S*, S*, S*, S*, S*, const S*, const S*, S*, int*, int*,
+                         S*, Ctl*, double*);
+template <class M, typename S, int V>
+static FusedFn<S> fused_kernel() {
+  if constexpr (M::NX + M::NU <= 16 && M::NX + 1 <= 16 && V != 1) return &k_newton_pair<M, S, kWPP, V>;
+  else return nullptr;
+}
+
+// Launch plan of one (model, dtype, variant) for a given (device, T, n_obs, kernel selection): kernel choice,
+// shared-memory sizes, occupancy-derived grid caps.  Function attributes and occupancy queries cost ~10 us per
+// forward call when redone every time (a fifth of a 200-problem solve), so they are resolved once and cached.
+struct Plan {
+  int dev = -1, T = 0, n_obs = -1, select = -1;
+  int n_sm = 0;
+  bool use_pair = false, fused = false;
+  size_t smem_fac = 0, smem_ls = 0, smem_fin = 0, smem_fused = 0;
+  int fac_threads = 0, fac_per_cta = 0, fin_ppw = 1, ls_grid_cap = 0, fused_grid_cap = 0;
+  LsWarpCfg lw{nullptr, 0, 0, 1};
+};
+
+template <class M, typename S, int V>
+static int make_plan(Plan& pl, int dev, int T, int n_obs, int select) {
+  constexpr int NX = M::NX, NU = M::NU;
+  constexpr bool SE = (V == 2);
+  const Layout<NX, NU> L(T, n_obs, SE);
+  const LsLayout<NX, NU> LL(T, n_obs, SE);
+  const LsGeom lg = ls_geom(1, T);
+  pl.dev = dev; pl.T = T; pl.n_obs = n_obs; pl.select = select;
+  cudaError_t e = cudaDeviceGetAttribute(&pl.n_sm, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return cuda_err(e, "cudaDeviceGetAttribute");
+  // every kernel gets the device maximum of opt-in shared memory once (allow_max_smem); the occupancy queries below
+  // use the actual launch sizes
+  int optin = 0;
+  e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return cuda_err(e, "cudaDeviceGetAttribute");
+  pl.smem_fac = (size_t)kWPB * L.total * sizeof(S);
+  pl.smem_ls = 2 * (size_t)lg.pls * LL.total * sizeof(S);  // double-buffered staging
+  if (pl.smem_ls < (size_t)lg.threads * 3 * sizeof(double)) pl.smem_ls = (size_t)lg.threads * 3 * sizeof(double);
+  pl.fin_ppw = 32 / (T - 1);  // problems per warp of the final kernel: its threads share the (problem, stage) items
+  pl.fin_ppw = pl.fin_ppw < 1 ? 1 : (pl.fin_ppw > 8 ? 8 : pl.fin_ppw);
+  pl.smem_fin = (size_t)kWPB * pl.fin_ppw * (L.N + L.neq) * sizeof(S);
+  if (pl.smem_fac + 1024 > 227 * 1024 || pl.smem_ls + 1024 > 227 * 1024 || pl.smem_fin > (size_t)optin)
+    return set_err(-11, "horizon too long for the shared-memory layout");
+  auto kfac = &k_factor_solve<NX, NU, S, kWPB, V>;
+  pl.fac_threads = kWPB * 32; pl.fac_per_cta = kWPB;
+  pl.use_pair = pl.fused = false;
+  if (auto kp = pair_kernel<NX, NU, S, V>(); kp && !(select & ALMPC_SELECT_FAC_SINGLE)) {
+    // Both kernels are bound by (latency of one problem) / (problems resident per SM): take the pair kernel
+    // unless its larger shared-memory footprint (long horizons) leaves it with clearly fewer resident problems.
+    const size_t smem_pair = (size_t)2 * kWPP * Layout<NX, NU>(T, 0, SE, true).total * sizeof(S);
+    int occ_single = 0, occ_pair = 0;
+    bool use_pair = smem_pair + 1024 <= 227 * 1024;
+    if (use_pair) {
+      cudaError_t e1 = allow_max_smem(kp, optin);
+      cudaError_t e2 = allow_max_smem(kfac, optin);
+      if (e1 == cudaSuccess && e2 == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pair, kp, kWPP * 32, smem_pair) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_single, kfac, kWPB * 32, pl.smem_fac) == cudaSuccess)
+        use_pair = occ_pair * 2 * kWPP * 5 >= occ_single * kWPB * 4;  // pair wins down to 0.8x the resident problems
+      else
+        (void)cudaGetLastError();
+    }
+    if (use_pair) {
+      pl.use_pair = true;
+      pl.fac_threads = kWPP * 32;
+      pl.fac_per_cta = 2 * kWPP;
+      pl.smem_fac = smem_pair;
+      // fused Newton tail (factor + line search in one kernel): needs the warp line-search item layout, (T-1) | 32
+      if (auto kf = fused_kernel<M, S, V>(); kf && !(select & ALMPC_SELECT_NO_FUSE) && (32 % (T - 1) == 0)) {
+        const size_t smem_fused = (size_t)2 * kWPP * fused_smem_per_problem<NX, NU>(T, SE) * sizeof(S);
+        if (smem_fused + 1024 <= 227 * 1024 &&
+            allow_max_smem(kf, optin) == cudaSuccess) {
+          int occ = 0;
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, kWPP * 32, smem_fused) != cudaSuccess || occ < 1) {
+            (void)cudaGetLastError();
+            occ = 1;
+          }
+          pl.fused = true;
+          pl.smem_fused = smem_fused;
+          pl.fused_grid_cap = occ * pl.n_sm;  // persistent warps: as many CTAs as are resident at once
+        } else {
+          (void)cudaGetLastError();
+        }
+      }
+    }
+  }
+  if (!pl.use_pair) {
+    e = allow_max_smem(kfac, optin);
+    if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(factor_solve)");
+  }
+  auto kls = k_line_search<M, S, V>;
+  auto kfin = k_final_dual<M, S, kWPB, V>;
+  e = allow_max_smem(kls, optin);
+  if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(line_search)");
+  e = allow_max_smem(kfin, optin);
+  if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(final_dual)");
+  // persistent line-search grid: as many CTAs as fit on the device at once
+  int ls_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ls_per_sm, kls, lg.threads, pl.smem_ls);
+  if (e != cudaSuccess) return cuda_err(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  pl.ls_grid_cap = pl.n_sm * (ls_per_sm > 0 ? ls_per_sm : 1);
+  // warp-synchronous line search when the stage items of a candidate fit a power-of-two lane group
+  pl.lw = LsWarpCfg{nullptr, 0, 0, 1};
+  if (!(select & ALMPC_SELECT_LS_CTA) && !pl.fused) {
+    switch (T - 1) {
+      case 1: e = ls_warp_cfg<M, S, 1, V>(pl.lw, pl.n_sm, n_obs, optin); break;
+      case 2: e = ls_warp_cfg<M, S, 2, V>(pl.lw, pl.n_sm, n_obs, optin); break;
+      case 4: e = ls_warp_cfg<M, S, 4, V>(pl.lw, pl.n_sm, n_obs, optin); break;
+      case 8: e = ls_warp_cfg<M, S, 8, V>(pl.lw, pl.n_sm, n_obs, optin); break;
+      case 16: e = ls_warp_cfg<M, S, 16, V>(pl.lw, pl.n_sm, n_obs, optin); break;
+      case 32: e = ls_warp_cfg<M, S, 32, V>(pl.lw, pl.n_sm, n_obs, optin); break;
+      default: break;
+    }
+    if (e != cudaSuccess) return cuda_err(e, "line-search (warp) configuration");
+  }
+  return 0;
+}
+
+template <class M, typename S, int V>
+static int get_plan(Plan& out, int T, int n_obs, int select) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_err(e, "cudaGetDevice");
+  // a handful of entries per instantiation, looked up under a lock: re-entrant, no per-call CUDA queries
+  static std::mutex mu;
+  static Plan cache[8];
+  static int next = 0;
+  std::lock_guard<std::mutex> lk(mu);
+  for (const Plan& p : cache)
+    if (p.dev == dev && p.T == T && p.n_obs == n_obs && p.select == select) { out = p; return 0; }
+  Plan pl;
+  const int rc = make_plan<M, S, V>(pl, dev, T, n_obs, select);
+  if (rc) return rc;
+  cache[next] = pl;
+  next = (next + 1) % 8;
+  out = pl;
+  return 0;
 }
 
 template <class M, typename S, int V>
@@ -191,80 +343,18 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   constexpr bool OBS = (V == 1), SE = (V == 2);
   const int n_obs = OBS ? d->n_obs : 0;
   const Layout<NX, NU> L(T, n_obs, SE);
-  const LsLayout<NX, NU> LL(T, n_obs, SE);
-  const LsGeom lg = ls_geom(B, T);
-  size_t smem_fac = (size_t)kWPB * L.total * sizeof(S);
-  if (const char* pad = getenv("ALMPC_FAC_SMEM_PAD")) smem_fac += (size_t)atoi(pad);  // occupancy experiments
-  size_t smem_ls = 2 * (size_t)lg.pls * LL.total * sizeof(S);  // double-buffered staging
-  if (smem_ls < (size_t)lg.threads * 3 * sizeof(double)) smem_ls = (size_t)lg.threads * 3 * sizeof(double);
-  int fin_ppw = 32 / (T - 1);  // problems per warp of the final kernel: its threads share the (problem, stage) items
-  fin_ppw = fin_ppw < 1 ? 1 : (fin_ppw > 8 ? 8 : fin_ppw);
-  const size_t smem_fin = (size_t)kWPB * fin_ppw * (L.N + L.neq) * sizeof(S);
-  if (smem_fac + 1024 > 227 * 1024 || smem_ls + 1024 > 227 * 1024)
-    return set_err(-11, "horizon too long for the shared-memory layout");
+  Plan pl;
+  if (int rc = get_plan<M, S, V>(pl, T, n_obs, d->select)) return rc;
+  const bool global_stop = d->stop_reduce != nullptr;
+  if (global_stop && !d->stop_stats) return set_err(-13, "stop_reduce needs the device buffer stop_stats");
   auto kjac = k_jacobian<M, S, V>;
   auto kfac = &k_factor_solve<NX, NU, S, kWPB, V>;
-  int fac_threads = kWPB * 32, fac_per_cta = kWPB;
-  if (auto kp = pair_kernel<NX, NU, S, V>(); kp && !getenv("ALMPC_FAC_SINGLE")) {  // env: A/B against the row-per-lane kernel
-    // Both kernels are bound by (latency of one problem) / (problems resident per SM): take the pair kernel
-    // unless its larger shared-memory footprint (long horizons) leaves it with clearly fewer resident problems.
-    const size_t smem_pair = (size_t)2 * kWPP * Layout<NX, NU>(T, 0, SE, true).total * sizeof(S);
-    int occ_single = 0, occ_pair = 0;
-    bool use_pair = smem_pair + 1024 <= 227 * 1024;
-    if (use_pair) {
-      cudaError_t e1 = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair);
-      cudaError_t e2 = cudaFuncSetAttribute(kfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fac);
-      if (e1 == cudaSuccess && e2 == cudaSuccess &&
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pair, kp, kWPP * 32, smem_pair) == cudaSuccess &&
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_single, kfac, kWPB * 32, smem_fac) == cudaSuccess)
-        use_pair = occ_pair * 2 * kWPP * 5 >= occ_single * kWPB * 4;  // pair wins down to 0.8x the resident problems
-      else
-        (void)cudaGetLastError();
-    }
-    if (getenv("ALMPC_FAC_PAIR")) use_pair = smem_pair + 1024 <= 227 * 1024;
-    if (use_pair) {
-      kfac = kp;
-      fac_threads = kWPP * 32;
-      fac_per_cta = 2 * kWPP;
-      smem_fac = smem_pair;
-      if (const char* pad = getenv("ALMPC_FAC_SMEM_PAD")) smem_fac += (size_t)atoi(pad);
-    }
-  }
+  if (pl.use_pair) kfac = pair_kernel<NX, NU, S, V>();
+  auto kfused = fused_kernel<M, S, V>();
   auto kls = k_line_search<M, S, V>;
   auto kfin = k_final_dual<M, S, kWPB, V>;
-  cudaError_t e;
-  e = cudaFuncSetAttribute(kfac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fac);
-  if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(factor_solve)");
-  e = cudaFuncSetAttribute(kls, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ls);
-  if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(line_search)");
-  e = cudaFuncSetAttribute(kfin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fin);
-  if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(final_dual)");
-  // persistent line-search grid: as many CTAs as fit on the device at once
-  int ls_per_sm = 0, n_sm = 0, dev = 0;
-  e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return cuda_err(e, "cudaGetDevice");
-  e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  if (e != cudaSuccess) return cuda_err(e, "cudaDeviceGetAttribute");
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ls_per_sm, kls, lg.threads, smem_ls);
-  if (e != cudaSuccess) return cuda_err(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-  int ls_grid = n_sm * (ls_per_sm > 0 ? ls_per_sm : 1);
-  if (ls_grid > lg.blocks) ls_grid = lg.blocks;
-  // warp-synchronous line search when the stage items of a candidate fit a power-of-two lane group
-  LsWarpCfg lw{nullptr, 0, 0, 1};
-  if (!getenv("ALMPC_LS_CTA")) {
-    switch (T - 1) {
-      case 1: e = ls_warp_cfg<M, S, 1, V>(lw, n_sm, n_obs); break;
-      case 2: e = ls_warp_cfg<M, S, 2, V>(lw, n_sm, n_obs); break;
-      case 4: e = ls_warp_cfg<M, S, 4, V>(lw, n_sm, n_obs); break;
-      case 8: e = ls_warp_cfg<M, S, 8, V>(lw, n_sm, n_obs); break;
-      case 16: e = ls_warp_cfg<M, S, 16, V>(lw, n_sm, n_obs); break;
-      case 32: e = ls_warp_cfg<M, S, 32, V>(lw, n_sm, n_obs); break;
-      default: break;
-    }
-    if (e != cudaSuccess) return cuda_err(e, "line-search (warp) configuration");
-  }
+  const LsGeom lg = ls_geom(B, T);
   KParams<S> P = make_params<S>(d);
-  const bool prof_requested = g_profile_on != 0;
   const WsPlan w = ws_plan(B, T, NX, NU, sizeof(S));
   unsigned char* ws = (unsigned char*)workspace;
   Ctl* ctl = (Ctl*)(ws + w.ctl);
@@ -275,78 +365,37 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   S* c_g = (S*)(ws + w.c);
   S* d_g = (S*)(ws + w.d);
   S* G_g = (S*)(ws + w.G);
-  e = cudaMemsetAsync(ctl, 0, 256, st);
+  cudaError_t e = cudaMemsetAsync(ctl, 0, 256, st);
   if (e != cudaSuccess) return cuda_err(e, "cudaMemsetAsync(ctl)");
   e = cudaMemsetAsync(info_out, 0, ALMPC_INFO_INTS * sizeof(int32_t), st);
   if (e != cudaSuccess) return cuda_err(e, "cudaMemsetAsync(info)");
-  // Optional (ALMPC_PARTS=2..4, default 1): process the batch in contiguous parts on separate streams so that
-  // the LSU-bound factor kernel of one part could overlap the FMA-bound jacobian / line-search kernels of
-  // another.  All parts feed the same batch-global statistics (one ticket counter) and the streams join
-  // after every Newton step.  Measured on B200 (quadrotor, 64K): no gain — k_factor_solve fills the SM's
-  // registers and shared memory, so CTAs of other kernels do not co-reside; kept as an experiment knob.
-  int nparts = 1;
-  {
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(st, &cs);
-    const char* env = getenv("ALMPC_PARTS");
-    if (env) nparts = atoi(env);
-    if (nparts < 1) nparts = 1;
-    if (nparts > kMaxParts) nparts = kMaxParts;
-    if (cs != cudaStreamCaptureStatusNone || prof_requested) nparts = 1;
+  // launch geometry of this batch
+  int ls_grid;
+  if (pl.fused) {
+    ls_grid = (B + 2 * kWPP - 1) / (2 * kWPP);
+    if (ls_grid > pl.fused_grid_cap) ls_grid = pl.fused_grid_cap;
+    P.n_sm = pl.n_sm;
+    // start-up stagger per warp slot of an SM (cycles): spreads the factor / line-search phases of the resident warps
+    P.stagger = d->tune[0] > 0 ? d->tune[0] : (d->tune[0] < 0 ? 0 : kDefaultStagger);
+  } else if (pl.lw.fn) {
+    const int groups = (B + pl.lw.pw - 1) / pl.lw.pw;
+    const int ctas = (groups + kWLS - 1) / kWLS;
+    ls_grid = pl.lw.grid_cap < ctas ? pl.lw.grid_cap : ctas;
+  } else {
+    const int groups = (B + lg.pls - 1) / lg.pls;
+    ls_grid = pl.ls_grid_cap < groups ? pl.ls_grid_cap : groups;
   }
-  static thread_local cudaStream_t aux[kMaxParts] = {nullptr};
-  static thread_local cudaEvent_t ev_fork = nullptr, ev_part[kMaxParts] = {nullptr};
-  static thread_local int aux_dev = -1;
-  if (nparts > 1 && (aux_dev != dev || !ev_fork)) {
-    for (int p = 0; p < kMaxParts; ++p) {
-      if (p > 0) { e = cudaStreamCreateWithFlags(&aux[p], cudaStreamNonBlocking); if (e != cudaSuccess) return cuda_err(e, "cudaStreamCreate"); }
-      e = cudaEventCreateWithFlags(&ev_part[p], cudaEventDisableTiming);
-      if (e != cudaSuccess) return cuda_err(e, "cudaEventCreate");
-    }
-    e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
-    if (e != cudaSuccess) return cuda_err(e, "cudaEventCreate");
-    aux_dev = dev;
-  }
-  struct Part { int lo, n, ls_grid, nb; unsigned jac_blocks; cudaStream_t s; KParams<S> P; };
-  Part parts[kMaxParts];
-  const int chunk = ((B + nparts - 1) / nparts + 7) & ~7;
-  int ticket_total = 0, np = 0;
-  for (int p = 0; p < nparts; ++p) {
-    const int lo = p * chunk;
-    if (lo >= B) break;
-    Part& pt = parts[np];
-    pt.lo = lo;
-    pt.n = (lo + chunk <= B) ? chunk : B - lo;
-    if (lw.fn) {
-      const int groups = (pt.n + lw.pw - 1) / lw.pw;
-      const int ctas = (groups + kWLS - 1) / kWLS;
-      pt.ls_grid = lw.grid_cap < ctas ? lw.grid_cap : ctas;
-    } else {
-      const int groups = (pt.n + lg.pls - 1) / lg.pls;
-      pt.ls_grid = ls_grid < groups ? ls_grid : groups;
-    }
-    pt.nb = (pt.n + fac_per_cta - 1) / fac_per_cta;
-    pt.jac_blocks = (unsigned)(((long)pt.n * (T - 1) * (NN - M::NTRIV) + 127) / 128);
-    pt.s = (np == 0) ? st : aux[np];
-    pt.P = P;
-    pt.P.B = pt.n;
-    pt.P.part_off = ticket_total;
-    if (pt.P.obs) pt.P.obs = P.obs + (size_t)lo * T * P.n_obs * 3;
-    ticket_total += pt.ls_grid;
-    ++np;
-  }
-  for (int p = 0; p < np; ++p) parts[p].P.ticket_total = ticket_total;
-  const size_t FE = factor_elems<NX, NU>(T), GE = (size_t)(T - 1) * NX * NN, DBG = 2 * (size_t)L.N + 24;
-  if (np > 1) {
-    e = cudaEventRecord(ev_fork, st);
-    if (e != cudaSuccess) return cuda_err(e, "cudaEventRecord");
-    for (int p = 1; p < np; ++p) cudaStreamWaitEvent(parts[p].s, ev_fork, 0);
-  }
+  P.part_off = 0;
+  P.ticket_total = ls_grid;
+  P.global_stop = global_stop ? 1 : 0;
+  P.stop_stats = d->stop_stats;
+  const int nb = (B + pl.fac_per_cta - 1) / pl.fac_per_cta;
+  const unsigned jac_blocks = (unsigned)(((long)B * (T - 1) * (NN - M::NTRIV) + 127) / 128);
   const int launches = d->al_iter * d->max_newton;
-  const bool pdl = !prof_requested && np == 1 && getenv("ALMPC_PDL");  // measured: no gain on B200, off by default
+  const bool pdl = !d->profile_ms && (d->select & ALMPC_SELECT_PDL);  // measured: no gain on B200, off by default
   ProfEv pe[3 * ALMPC_MAX_AL_ITER * 8 + 1];
   int npe = 0;
-  const bool prof = prof_requested && launches * 3 + 1 <= (int)(sizeof(pe) / sizeof(pe[0]));
+  const bool prof = d->profile_ms && launches * 3 + 1 <= (int)(sizeof(pe) / sizeof(pe[0]));
   auto tic = [&](int kind) {
     if (!prof) return;
     cudaEventCreate(&pe[npe].a);
@@ -360,78 +409,88 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
     ++npe;
   };
   for (int i = 0; i < launches; ++i) {
-    for (int p = 0; p < np; ++p) {
-      const Part& pt = parts[p];
-      const size_t lo = (size_t)pt.lo;
-      S* dbg = debug_out ? debug_out + lo * DBG : nullptr;
-      tic(0);
-      launch_k(kjac, pt.jac_blocks, 128, 0, pt.s, pdl, pt.P, x0 + lo * NX, xu + lo * L.N, G_g + lo * GE,
-               c_g + lo * L.neq, ctl);
-      toc();
+    tic(0);
+    e = launch_k(kjac, jac_blocks, 128, 0, st, pdl, P, x0, xu, G_g, c_g, ctl);
+    if (e != cudaSuccess) return cuda_err(e, "k_jacobian launch");
+    toc();
+    if (pl.fused) {
+      if constexpr (NX + NU <= 16 && NX + 1 <= 16 && V != 1) {
+        tic(1);
+        e = launch_k(kfused, (unsigned)ls_grid, kWPP * 32, pl.smem_fused, st, pdl, P, x0, Qd, q, xu, lam, rho, factor, G_g,
+                     c_g, merit, status, info_out, debug_out, ctl, partials);
+        if (e != cudaSuccess) return cuda_err(e, "k_newton_pair launch");
+        toc();
+      }
+    } else {
       tic(1);
-      launch_k(kfac, pt.nb, fac_threads, smem_fac, pt.s, pdl, pt.P, Qd + lo * L.N, q + lo * L.N, xu + lo * L.N,
-               lam + lo * L.m, rho + lo, factor + lo * FE, G_g + lo * GE, c_g + lo * L.neq, d_g + lo * L.N,
-               merit + lo, rentry + lo, status + lo, dbg, ctl);
+      e = launch_k(kfac, nb, pl.fac_threads, pl.smem_fac, st, pdl, P, Qd, q, xu, lam, rho, factor, G_g, c_g, d_g, merit,
+                   rentry, status, debug_out, ctl);
+      if (e != cudaSuccess) return cuda_err(e, "k_factor_solve launch");
       toc();
       tic(2);
-      if (lw.fn) {
-        const S *a_x0 = x0 + lo * NX, *a_Qd = Qd + lo * L.N, *a_q = q + lo * L.N, *a_lam = lam + lo * L.m;
-        const S *a_rho = rho + lo, *a_d = d_g + lo * L.N;
-        S *a_xu = xu + lo * L.N, *a_merit = merit + lo;
-        const double* a_re = rentry + lo;
-        int* a_st = status + lo;
-        void* args[] = {(void*)&pt.P, &a_x0, &a_Qd, &a_q, &a_xu, &a_lam, &a_rho, &a_d, &a_merit, &a_re, &a_st,
-                        &info_out, &dbg, &ctl, &partials};
+      if (pl.lw.fn) {
+        const S *a_x0 = x0, *a_Qd = Qd, *a_q = q, *a_lam = lam, *a_rho = rho, *a_d = d_g;
+        S *a_xu = xu, *a_merit = merit;
+        const double* a_re = rentry;
+        int* a_st = status;
+        void* args[] = {(void*)&P, &a_x0, &a_Qd, &a_q, &a_xu, &a_lam, &a_rho, &a_d, &a_merit, &a_re, &a_st,
+                        &info_out, &debug_out, &ctl, &partials};
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(pt.ls_grid);
+        cfg.gridDim = dim3(ls_grid);
         cfg.blockDim = dim3(kWLS * 32);
-        cfg.dynamicSmemBytes = lw.smem;
-        cfg.stream = pt.s;
+        cfg.dynamicSmemBytes = pl.lw.smem;
+        cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at;
         cfg.numAttrs = pdl ? 1 : 0;
-        e = cudaLaunchKernelExC(&cfg, lw.fn, args);
+        e = cudaLaunchKernelExC(&cfg, pl.lw.fn, args);
         if (e != cudaSuccess) return cuda_err(e, "k_line_search_warp launch");
       } else {
-        launch_k(kls, pt.ls_grid, lg.threads, smem_ls, pt.s, pdl, pt.P, lg.pls, x0 + lo * NX, Qd + lo * L.N,
-                 q + lo * L.N, xu + lo * L.N, lam + lo * L.m, rho + lo, d_g + lo * L.N, merit + lo, rentry + lo,
-                 status + lo, info_out, dbg, ctl, partials);
+        e = launch_k(kls, ls_grid, lg.threads, pl.smem_ls, st, pdl, P, lg.pls, x0, Qd, q, xu, lam, rho, d_g, merit, rentry,
+                     status, info_out, debug_out, ctl, partials);
+        if (e != cudaSuccess) return cuda_err(e, "k_line_search launch");
       }
       toc();
     }
-    if (np > 1) {  // join: every part must see the control block written by the globally last CTA
-      for (int p = 0; p < np; ++p) cudaEventRecord(ev_part[p], parts[p].s);
-      for (int p = 0; p < np; ++p)
-        for (int o = 0; o < np; ++o)
-          if (o != p) cudaStreamWaitEvent(parts[p].s, ev_part[o], 0);
+    if (global_stop) {
+      // The last CTA of the line search left this rank's (sum ||c+||^2 entry, sum exit, max rho) in stop_stats
+      // instead of steering.  The caller's hook enqueues the reduction over the ranks on this stream (two SUMs and
+      // a MAX: 24 bytes, latency only), then one tiny kernel takes the reference's batch-GLOBAL decisions
+      // (al_utils.py:551-564, AL_mpc.py:412) identically on every rank.
+      const int rc = d->stop_reduce(d->stop_stats, (void*)st, d->stop_reduce_user);
+      if (rc) return set_err(-14, "stop_reduce hook failed");
+      e = launch_k(k_steer<S>, 1u, 32u, 0, st, false, P, ctl, info_out);
+      if (e != cudaSuccess) return cuda_err(e, "k_steer launch");
     }
   }
   tic(3);
-  launch_k(kfin, (B + kWPB * fin_ppw - 1) / (kWPB * fin_ppw), kWPB * 32, smem_fin, st, pdl, P, x0, xu, lam, rho, x_out,
-           u_out, dyn_res_out, info_out, ctl, fin_ppw);
+  e = launch_k(kfin, (B + kWPB * pl.fin_ppw - 1) / (kWPB * pl.fin_ppw), kWPB * 32, pl.smem_fin, st, pdl, P, x0, xu, lam, rho,
+               x_out, u_out, dyn_res_out, info_out, ctl, pl.fin_ppw);
+  if (e != cudaSuccess) return cuda_err(e, "k_final_dual launch");
   toc();
-  if (prof) {  // profiling mode synchronises (never used on the timed path)
+  if (prof) {  // profiling mode synchronises (never used on a timed or captured path)
     cudaStreamSynchronize(st);
-    for (int k = 0; k < 8; ++k) g_profile[k] = 0;
+    double acc[8] = {0};
     for (int i = 0; i < npe; ++i) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, pe[i].a, pe[i].b);
       if (ms > 0.02f || pe[i].kind == 3) {  // skip the no-op launches after the solve finished
-        g_profile[pe[i].kind] += ms;
-        g_profile[4 + pe[i].kind] += 1;
+        acc[pe[i].kind] += ms;
+        acc[4 + pe[i].kind] += 1;
       }
       cudaEventDestroy(pe[i].a);
       cudaEventDestroy(pe[i].b);
     }
+    for (int k = 0; k < 8; ++k) d->profile_ms[k] = acc[k];
   }
   return cuda_err(cudaGetLastError(), "almpc_forward launch");
 }
 
 template <int NX, int NU, typename S>
-static int backward_impl(const almpc_desc* d, const S* factor, const S* xu, const S* grad_xu, S* grad_Q, S* grad_q,
-                         cudaStream_t st) {
+static int backward_impl(const almpc_desc* d, const S* factor, const S* xu, const S* grad_xu, const int32_t* status,
+                         S* grad_Q, S* grad_q, cudaStream_t st) {
   if (d->B == 0) return 0;
   if (!factor || !xu || !grad_xu || !grad_q) return set_err(-10, "null buffer");
   constexpr int NN = NX + NU;
@@ -442,7 +501,7 @@ static int backward_impl(const almpc_desc* d, const S* factor, const S* xu, cons
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(backward)");
   }
-  kern<<<n_blocks(d->B), kWPB * 32, smem, st>>>(d->B, d->T, factor, xu, grad_xu, grad_Q, grad_q);
+  kern<<<n_blocks(d->B), kWPB * 32, smem, st>>>(d->B, d->T, factor, xu, grad_xu, status, grad_Q, grad_q);
   return cuda_err(cudaGetLastError(), "almpc_backward launch");
 }
 
@@ -524,12 +583,12 @@ static int forward_any(const almpc_desc* d, const S* x0, const S* Qd, const S* q
 }
 
 template <typename S>
-static int backward_any(const almpc_desc* d, const S* factor, const S* xu, const S* grad_xu, S* grad_Q, S* grad_q,
-                        void* stream) {
+static int backward_any(const almpc_desc* d, const S* factor, const S* xu, const S* grad_xu, const int32_t* status,
+                        S* grad_Q, S* grad_q, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  ALMPC_DISPATCH(d->dyn_id, (backward_impl<M::NX, M::NU, S>(d, factor, xu, grad_xu, grad_Q, grad_q, st)))
+  ALMPC_DISPATCH(d->dyn_id, (backward_impl<M::NX, M::NU, S>(d, factor, xu, grad_xu, status, grad_Q, grad_q, st)))
 }
 
 template <typename S>
@@ -657,14 +716,14 @@ int almpc_forward_f32(const almpc_desc* d, const float* x0, const float* Qd, con
 #endif
 #if ALMPC_BUILD_F64
 int almpc_backward_f64(const almpc_desc* d, const double* factor, const double* xu, const double* grad_xu,
-                       double* grad_Q, double* grad_q, void* stream) {
-  return backward_any<double>(d, factor, xu, grad_xu, grad_Q, grad_q, stream);
+                       const int32_t* status, double* grad_Q, double* grad_q, void* stream) {
+  return backward_any<double>(d, factor, xu, grad_xu, status, grad_Q, grad_q, stream);
 }
 #endif
 #if ALMPC_BUILD_F32
 int almpc_backward_f32(const almpc_desc* d, const float* factor, const float* xu, const float* grad_xu,
-                       float* grad_Q, float* grad_q, void* stream) {
-  return backward_any<float>(d, factor, xu, grad_xu, grad_Q, grad_q, stream);
+                       const int32_t* status, float* grad_Q, float* grad_q, void* stream) {
+  return backward_any<float>(d, factor, xu, grad_xu, status, grad_Q, grad_q, stream);
 }
 #endif
 #if ALMPC_BUILD_F64
@@ -732,10 +791,6 @@ int almpc_blocktri_f32(int32_t B, int32_t T, int32_t nx, int32_t nu, int32_t do_
 }
 #endif
 #if ALMPC_BUILD_F64
-void almpc_set_profiling(int32_t on) { g_profile_on = on; }
-void almpc_get_profile(double* out8) {
-  for (int k = 0; k < 8; ++k) out8[k] = g_profile[k];
-}
 const char* almpc_last_error(void) { return g_err; }
 const char* almpc_version(void) { return "almpc 0.1 (sm_100a)"; }
 

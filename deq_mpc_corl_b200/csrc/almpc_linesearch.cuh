@@ -10,6 +10,44 @@ namespace almpc {
 // ------------------------------------------------------------------------------------------------
 // Executed by the LAST CTA of the line-search launch: deterministic reduction of the per-CTA statistics and the
 // batch-global decisions of the reference (stop rule al_utils.py:560-564, rho_max exit AL_mpc.py:412).
+// The reference's batch-global decisions from the batch statistics (s0 = sum ||c+||^2 at the entry point, s1 = at the
+// exit point, s2 = max rho used): stop rule al_utils.py:560-564, rho_max exit AL_mpc.py:412.  One thread.
+template <typename S>
+__device__ __forceinline__ void steer_decide(const KParams<S>& P, Ctl* ctl, int* info_g, double s0, double s1, double s2,
+                                             int al_a, int nk) {
+  const double R_entry = sqrt(s0), R_exit = sqrt(s1), rho_max_used = s2;
+  const double res_old = (nk == 0) ? R_entry : ctl->res_old;
+  // al_utils.py:560-564 — evaluated exactly as written there (NaN compares false -> no break)
+  bool stop = (fabs(res_old - R_exit) / R_exit < 1e-3) || (R_exit < 1e-3);
+  const int steps_done = nk + 1;
+  if (steps_done >= P.max_newton) stop = true;
+  ctl->ticket = 0;
+  ctl->total_newton += 1;
+  info_g[ALMPC_INFO_TOTAL_NEWTON] = ctl->total_newton;
+  if (!stop) {
+    ctl->k = steps_done;
+    ctl->mode = MODE_CONT;
+    ctl->res_old = R_exit;
+  } else {
+    info_g[ALMPC_INFO_NEWTON0 + al_a] = steps_done;
+    info_g[ALMPC_INFO_AL_DONE] = al_a + 1;
+    double rho_next = rho_max_used * P.rho_mult;
+    if (P.rho_f32) rho_next = (double)(float)rho_next;
+    ctl->rho_final_max = rho_next;
+    const bool exceed = P.stream_mode && (rho_next > P.rho_max);
+    if (al_a + 1 >= P.al_iter || exceed) {
+      ctl->mode = MODE_DONE;
+    } else {
+      ctl->a = al_a + 1;
+      ctl->k = 0;
+      ctl->mode = MODE_DUAL_NEWTON;
+    }
+  }
+}
+
+// Executed by the LAST CTA of the kernel that ran the line search: deterministic reduction of the per-CTA statistics,
+// then either the decisions (single shard) or the hand-over of this shard's totals to the caller's reduction
+// (P.global_stop: k_steer decides after the all-reduce).
 template <typename S>
 __device__ __forceinline__ void steer_solve(const KParams<S>& P, Ctl* ctl, int* info_g, const double* partials,
                                             double (*fin_red)[3], int tid, int nthr, int al_a, int nk) {
@@ -29,35 +67,22 @@ __device__ __forceinline__ void steer_solve(const KParams<S>& P, Ctl* ctl, int* 
   if (tid == 0) {
     double s0 = 0, s1 = 0, s2 = 0;
     for (int i = 0; i < nthr; ++i) { s0 += fin_red[i][0]; s1 += fin_red[i][1]; s2 = fmax(s2, fin_red[i][2]); }
-    const double R_entry = sqrt(s0), R_exit = sqrt(s1), rho_max_used = s2;
-    const double res_old = (nk == 0) ? R_entry : ctl->res_old;
-    // al_utils.py:560-564 — evaluated exactly as written there (NaN compares false -> no break)
-    bool stop = (fabs(res_old - R_exit) / R_exit < 1e-3) || (R_exit < 1e-3);
-    const int steps_done = nk + 1;
-    if (steps_done >= P.max_newton) stop = true;
-    ctl->ticket = 0;
-    ctl->total_newton += 1;
-    info_g[ALMPC_INFO_TOTAL_NEWTON] = ctl->total_newton;
-    if (!stop) {
-      ctl->k = steps_done;
-      ctl->mode = MODE_CONT;
-      ctl->res_old = R_exit;
+    if (P.global_stop) {
+      P.stop_stats[0] = s0;
+      P.stop_stats[1] = s1;
+      P.stop_stats[2] = s2;
+      ctl->ticket = 0;
     } else {
-      info_g[ALMPC_INFO_NEWTON0 + al_a] = steps_done;
-      info_g[ALMPC_INFO_AL_DONE] = al_a + 1;
-      double rho_next = rho_max_used * P.rho_mult;
-      if (P.rho_f32) rho_next = (double)(float)rho_next;
-      ctl->rho_final_max = rho_next;
-      const bool exceed = P.stream_mode && (rho_next > P.rho_max);
-      if (al_a + 1 >= P.al_iter || exceed) {
-        ctl->mode = MODE_DONE;
-      } else {
-        ctl->a = al_a + 1;
-        ctl->k = 0;
-        ctl->mode = MODE_DUAL_NEWTON;
-      }
+      steer_decide<S>(P, ctl, info_g, s0, s1, s2, al_a, nk);
     }
   }
+}
+
+// global-stop mode: the decisions, from the statistics the caller reduced over all shards (one thread)
+template <typename S>
+__global__ void k_steer(const KParams<S> P, Ctl* ctl, int* info_g) {
+  if (threadIdx.x != 0 || ctl->mode == MODE_DONE) return;
+  steer_decide<S>(P, ctl, info_g, P.stop_stats[0], P.stop_stats[1], P.stop_stats[2], ctl->a, ctl->k);
 }
 
 // One line-search item: candidate alpha = 2^-kk, stage t.  Evaluates the stage's share of the merit

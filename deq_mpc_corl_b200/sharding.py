@@ -9,11 +9,17 @@ places, both here:
 * ``gather_batch`` — optional re-assembly of per-shard outputs (evaluation / tests).
 
 Stop-rule semantics under sharding: the reference's Newton stop test is a statistic of the WHOLE
-batch (qpth/al_utils.py:486,552,560-564).  Each rank applies the same rule to ITS shard
-("per-shard stopping"); realised Newton-step counts are reported per rank.  A sharded run is
-therefore bit-identical to the reference run on each shard, not to the reference run on the
+batch (qpth/al_utils.py:486,552,560-564), and so is the rho_max exit of the streaming solve (qpth/AL_mpc.py:412).
+Default: each rank applies the same rule to ITS shard ("per-shard stopping"); realised Newton-step counts are
+reported per rank, and a sharded run is bit-identical to the reference run on each shard.
+``GlobalStop`` (pass it as ``MPC.global_stop``) restores the reference's whole-batch decisions: after every line search
+the library hands this rank's three statistics to a hook that all-reduces them over the group on the solver's stream
+(two 8-byte SUMs and a MAX over NVLink: latency only, no host synchronisation), and a one-thread kernel takes the
+decision identically on every rank — a sharded run then realises the Newton-step counts of the single-GPU run on the
 concatenated batch.
 """
+import ctypes
+
 from typing import Callable, Dict, Iterable, List, Optional, Sequence
 
 import torch
@@ -101,6 +107,39 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, averag
         size += g.numel() * g.element_size()
     flush()
     return n_coll
+
+
+class GlobalStop:
+    """Batch-global stop rule across shards (include/almpc.h: ``almpc_desc.stop_stats`` / ``stop_reduce``).
+
+    ``stats`` is the 4-double device buffer the solver's last line-search CTA fills with (sum ||c+||^2 at the entry
+    point, at the exit point, max rho) of this rank's shard; ``hook`` is the C callback the library invokes at
+    enqueue time, once per Newton-step slot.  The all-reduces are issued on the current stream (the one the
+    solver launches on), so everything stays stream-ordered.  Every rank must call the solver with the same
+    ``al_iter`` / ``max_newton`` (same number of collectives)."""
+
+    def __init__(self, device, group=None):
+        from . import _lib
+
+        self.group = group
+        self.stats = torch.zeros(4, dtype=torch.float64, device=device)
+        self.calls = 0
+        self.error = None
+
+        def _reduce(stats_ptr, stream, user):
+            try:
+                if stats_ptr != self.stats.data_ptr():
+                    raise RuntimeError("stop_reduce called with a foreign buffer")
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                    dist.all_reduce(self.stats[:2], op=dist.ReduceOp.SUM, group=self.group)
+                    dist.all_reduce(self.stats[2:3], op=dist.ReduceOp.MAX, group=self.group)
+                self.calls += 1
+                return 0
+            except Exception as exc:  # never let an exception cross the C boundary
+                self.error = exc
+                return 1
+
+        self.hook = _lib.STOP_REDUCE_FN(_reduce)  # keep a reference: the library stores the raw pointer only
 
 
 def allreduce_stop_statistic(sum_sq: torch.Tensor, group=None) -> torch.Tensor:

@@ -33,8 +33,36 @@ class SolveConfig:
     obs_radius: float = 0.0
     state_estimator: bool = False  # MPC(state_estimator=True): dynamics rows only, controls are data (al_utils_se.py)
     graph_cache: object = None     # a GraphCache: replay the forward launch sequence as one CUDA graph
+    global_stop: object = None     # a sharding.GlobalStop: batch-global stop rule across shards (NCCL all-reduce hook)
+    profile: bool = False          # per-kernel CUDA-event timing of the next forward (synchronises): raw_forward's "profile_ms"
 
     def desc(self, B):
+        """The C descriptor of this configuration.  Filling the 70-field ctypes struct costs ~25 us, so the filled
+        struct is cached per batch size and only the per-call fields are refreshed."""
+        cache = self.__dict__.setdefault("_desc_cache", {})
+        key = (B, self.al_iter, self.max_newton, self.stream_mode, self.rho_f32, self.skip_final_dual)
+        d = cache.get(key)
+        if d is None:
+            if len(cache) > 16:
+                cache.clear()
+            d = cache[key] = self._fill_desc(B)
+        d.select = _lib.env_select()
+        for i, v in enumerate(_lib.env_tune()):
+            d.tune[i] = v
+        if self.obstacles is not None:
+            d.n_obs = int(self.obstacles.shape[2])
+            d.obs_radius = float(self.obs_radius)
+            d.obstacles = self.obstacles.data_ptr()
+        d.profile_ms = None
+        if self.global_stop is not None:
+            d.stop_stats = self.global_stop.stats.data_ptr()
+            d.stop_reduce = ctypes.cast(self.global_stop.hook, ctypes.c_void_p)
+        else:
+            d.stop_stats = None
+            d.stop_reduce = None
+        return d
+
+    def _fill_desc(self, B):
         d = _lib.Desc()
         d.B, d.T, d.dyn_id = B, self.T, self.dyn.dyn_id
         d.al_iter, d.max_newton = self.al_iter, self.max_newton
@@ -49,10 +77,6 @@ class SolveConfig:
         for i in range(self.dyn.nu):
             d.u_lower[i] = float(self.u_lower[i])
             d.u_upper[i] = float(self.u_upper[i])
-        if self.obstacles is not None:
-            d.n_obs = int(self.obstacles.shape[2])
-            d.obs_radius = float(self.obs_radius)
-            d.obstacles = self.obstacles.data_ptr()
         return d
 
 
@@ -84,6 +108,10 @@ def raw_forward(cfg: SolveConfig, x0, Qd, q, xu, lam, rho):
         raise _lib.AlmpcError("inconsistent AL-MPC buffer shapes")
     dev, dt = xu.device, xu.dtype
     d = cfg.desc(B)
+    prof = None
+    if cfg.profile:
+        prof = (ctypes.c_double * 8)()
+        d.profile_ms = ctypes.cast(prof, ctypes.POINTER(ctypes.c_double))
     out = dict(
         factor=torch.empty(B, lib.almpc_factor_elems(ctypes.byref(d)), dtype=dt, device=dev),
         x=torch.empty(B, T, nx, dtype=torch.float32, device=dev),
@@ -103,6 +131,8 @@ def raw_forward(cfg: SolveConfig, x0, Qd, q, xu, lam, rho):
         _lib.check(rc, "almpc_forward")
     else:
         out["info"].zero_()
+    if prof is not None:
+        out["profile_ms"] = list(prof)
     return out
 
 
@@ -156,10 +186,13 @@ class GraphCache:
         xu.copy_(ent["static"]["xu"])
         lam.copy_(ent["static"]["lam"])
         rho.copy_(ent["static"]["rho"])
-        return {k: (None if v is None else v.clone()) for k, v in ent["out"].items()}
+        return {k: (v.clone() if torch.is_tensor(v) else v) for k, v in ent["out"].items()}
 
 
-def raw_backward(cfg: SolveConfig, factor, xu, grad_xu, need_Q=True):
+def raw_backward(cfg: SolveConfig, factor, xu, grad_xu, need_Q=True, status=None):
+    """status = the forward's per-problem status bits (int32[B]) or None: with it, only problems whose factor is
+    flagged broken (STATUS_CHOL_OK cleared) get a zero gradient; a non-finite upstream gradient propagates like in
+    the reference instead of being hidden."""
     lib = _lib.load()
     _lib.require_cuda(grad_xu, "grad_xu")
     B = xu.shape[0]
@@ -170,8 +203,8 @@ def raw_backward(cfg: SolveConfig, factor, xu, grad_xu, need_Q=True):
     if B > 0:
         with torch.cuda.device(xu.device):
             rc = getattr(lib, "almpc_backward_" + _lib.suffix(xu.dtype))(
-                ctypes.byref(d), _lib.ptr(factor), _lib.ptr(xu), _lib.ptr(grad_xu), _lib.ptr(gQ), _lib.ptr(gq),
-                _lib.stream_ptr())
+                ctypes.byref(d), _lib.ptr(factor), _lib.ptr(xu), _lib.ptr(grad_xu), _lib.ptr(status), _lib.ptr(gQ),
+                _lib.ptr(gq), _lib.stream_ptr())
         _lib.check(rc, "almpc_backward")
     return gQ, gq
 
@@ -188,14 +221,14 @@ class ALSolve(torch.autograd.Function):
         fwd = raw_forward if cfg.graph_cache is None or cfg.debug else cfg.graph_cache.forward
         out = fwd(cfg, x0.detach().contiguous(), Qd.detach().contiguous(), q.detach().contiguous(), xu, lam, rho)
         ctx.cfg = cfg
-        ctx.save_for_backward(out["factor"], xu)
+        ctx.save_for_backward(out["factor"], xu, out["status"])
         dbg = out["debug"] if out["debug"] is not None else torch.empty(0, device=xu.device)
         ctx.mark_non_differentiable(xu, lam, rho, out["dyn_res"], out["status"], out["info"], dbg)
         return out["x"], out["u"], xu, lam, rho, out["dyn_res"], out["status"], out["info"], dbg
 
     @staticmethod
     def backward(ctx, gx, gu, *unused):
-        factor, xu = ctx.saved_tensors
+        factor, xu, status = ctx.saved_tensors
         nx = ctx.cfg.dyn.nx
         if gx is None:
             gx = torch.zeros(xu.shape[0], xu.shape[1], nx, dtype=xu.dtype, device=xu.device)
@@ -203,5 +236,5 @@ class ALSolve(torch.autograd.Function):
             gu = torch.zeros(xu.shape[0], xu.shape[1], xu.shape[2] - nx, dtype=xu.dtype, device=xu.device)
         grad_xu = torch.cat([gx.to(xu.dtype), gu.to(xu.dtype)], dim=2)
         need_Q = ctx.needs_input_grad[0]
-        gQ, gq = raw_backward(ctx.cfg, factor, xu, grad_xu, need_Q=need_Q)
+        gQ, gq = raw_backward(ctx.cfg, factor, xu, grad_xu, need_Q=need_Q, status=status)
         return gQ, (gq if ctx.needs_input_grad[1] else None), None, None, None, None, None

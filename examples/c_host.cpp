@@ -74,7 +74,7 @@ int main(int argc, char** argv) {
 
   if (almpc_forward_f64(&d, x0_d, Qd_d, q_d, xu_d, lam_d, rho_d, factor_d, x_d, u_d, dyn_res_d, status_d, info_d, nullptr,
                         ws_d, st)) { printf("forward: %s\n", almpc_last_error()); return 1; }
-  if (almpc_backward_f64(&d, factor_d, xu_d, grad_d, gQ_d, gq_d, st)) { printf("backward: %s\n", almpc_last_error()); return 1; }
+  if (almpc_backward_f64(&d, factor_d, xu_d, grad_d, status_d, gQ_d, gq_d, st)) { printf("backward: %s\n", almpc_last_error()); return 1; }
   CK(cudaStreamSynchronize(st));
 
   std::vector<int32_t> info(ALMPC_INFO_INTS), status(B);

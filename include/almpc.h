@@ -3,7 +3,8 @@
  *
  * This is the drop-in boundary for the reference's AL-MPC hot path.  Every entry point takes plain
  * device pointers + sizes + a CUDA stream; there are no torch types, no allocations and no host
- * synchronisation inside the library (all calls are CUDA-graph capturable).  Return value: 0 = ok,
+ * synchronisation inside the library (all calls are CUDA-graph capturable), and no global state: everything a
+ * call needs travels in its descriptor (thread-safe, re-entrant).  Return value: 0 = ok,
  * <0 = bad argument, >0 = cudaError_t of the failing runtime call; almpc_last_error() gives text.
  *
  * What each entry point replaces in the reference (paths relative to the reference repo):
@@ -64,6 +65,19 @@ enum almpc_dyn_id {
  * its gradient see the states only (al_utils_se.py:272-305); the Hessian keeps diag(Q) on the controls. */
 #define ALMPC_FLAG_STATE_ESTIMATOR 2
 
+/* desc.select: kernel-selection switches for A/B measurements and differential tests (0 = the library's choice) */
+#define ALMPC_SELECT_FAC_SINGLE 1 /* row-per-lane factor kernel even where the half-warp-per-problem one applies */
+#define ALMPC_SELECT_NO_FUSE 2    /* factor and line search as separate kernels (no k_newton_pair) */
+#define ALMPC_SELECT_LS_CTA 4     /* CTA line-search kernel even where the warp-synchronous one applies */
+#define ALMPC_SELECT_PDL 8        /* launch the step kernels with programmatic stream serialization */
+
+/* Hook for the reference's batch-GLOBAL decisions under batch sharding (qpth/al_utils.py:486,552,560-564: the
+ * Newton stop rule is a statistic of the WHOLE batch; qpth/AL_mpc.py:412: max(rho) over the batch).  Called on the
+ * host, at enqueue time, once per Newton-step slot: it must enqueue on `stream` an in-place reduction over all
+ * shards of stats[0], stats[1] (SUM) and stats[2] (MAX) — e.g. two NCCL all-reduces — and return 0.  No host
+ * synchronisation is required or performed. */
+typedef int (*almpc_stop_reduce_fn)(double* stats_dev, void* stream, void* user);
+
 typedef struct almpc_desc {
   int32_t B;          /* problems in the batch */
   int32_t T;          /* horizon */
@@ -82,9 +96,22 @@ typedef struct almpc_desc {
    * the position x[0..2]; rows follow the 2*nu control rows of each stage (al_utils.py:313-323).  obstacles is a
    * DEVICE pointer to [B][T][n_obs][3] scalars of the solver dtype (NULL / n_obs = 0: plain MPC). */
   int32_t n_obs;
-  int32_t reserved;
+  int32_t select;     /* ALMPC_SELECT_* */
   double obs_radius;
   const void* obstacles;
+  /* Optional per-kernel timing of THIS call: HOST pointer to 8 doubles or NULL.  When set, almpc_forward_* brackets
+   * every launch with CUDA events and SYNCHRONISES at the end (never set it on a timed or graph-captured path):
+   * [0..3] = total ms of k_jacobian, factor (k_factor_solve* or the fused k_newton_pair), k_line_search*,
+   * k_final_dual (no-op launches after the solve finished excluded), [4..7] = launches counted. */
+  double* profile_ms;
+  /* Batch-global stop rule across shards (NULL = every shard applies the rule to its own problems):
+   * stop_stats = DEVICE buffer of 4 doubles owned by the caller, stop_reduce = the reduction hook above. */
+  double* stop_stats;
+  almpc_stop_reduce_fn stop_reduce;
+  void* stop_reduce_user;
+  /* Tuning values for measurements (0 = the library's default).  tune[0]: start-up stagger of the persistent fused
+   * Newton-tail kernel in clock cycles per warp slot (-1 = none). */
+  int32_t tune[4];
 } almpc_desc;
 
 /* info_out layout (int32, device memory, ALMPC_INFO_INTS entries) */
@@ -118,11 +145,14 @@ int almpc_forward_f32(const almpc_desc* d, const float* x0, const float* Qd, con
                       void* workspace, void* stream);
 
 /* Implicit backward: gbar = -H^{-1} grad_xu with the cached factor; grad_q = gbar,
- * grad_Q = gbar * xu (grad_Q may be NULL when Q needs no gradient). */
+ * grad_Q = gbar * xu (grad_Q may be NULL when Q needs no gradient).
+ * status = the forward's status_out or NULL.  With it, a problem whose factor is flagged broken
+ * (ALMPC_STATUS_CHOL_OK cleared) gets a zero gradient and every other problem the plain result — a NaN / Inf in
+ * grad_xu propagates as in the reference.  Without it, any non-finite result is replaced by zero. */
 int almpc_backward_f64(const almpc_desc* d, const double* factor, const double* xu, const double* grad_xu,
-                       double* grad_Q, double* grad_q, void* stream);
+                       const int32_t* status, double* grad_Q, double* grad_q, void* stream);
 int almpc_backward_f32(const almpc_desc* d, const float* factor, const float* xu, const float* grad_xu,
-                       float* grad_Q, float* grad_q, void* stream);
+                       const int32_t* status, float* grad_Q, float* grad_q, void* stream);
 
 /* Stand-alone dynamics: xn[R][nx] = f(x[R][nx], u[R][nu]); optional Jx[R][nx][nx], Ju[R][nx][nu]
  * (Jx[r][i][j] = d xn_i / d x_j, al_utils.py:237-248).  Uses d->dyn_id / d->dyn_params only. */
@@ -167,13 +197,6 @@ int almpc_blocktri_f32(int32_t B, int32_t T, int32_t nx, int32_t nu, int32_t do_
  * number of floating-point operations performed (2 per FMA). */
 int almpc_fma_peak_f64(int32_t blocks, int32_t iters, double* sink, double* flops, void* stream);
 int almpc_fma_peak_f32(int32_t blocks, int32_t iters, float* sink, double* flops, void* stream);
-
-/* Optional per-kernel timing for benchmarks: when on, almpc_forward_* brackets every launch with CUDA
- * events and SYNCHRONISES at the end (never enable it on a timed or graph-captured path).
- * almpc_get_profile: out8[0..3] = total ms of k_jacobian, k_factor_solve, k_line_search, k_final_dual of the
- * last profiled forward (no-op launches after the solve finished excluded), out8[4..7] = launches counted. */
-void almpc_set_profiling(int32_t on);
-void almpc_get_profile(double* out8);
 
 const char* almpc_last_error(void);
 const char* almpc_version(void);

@@ -8,7 +8,13 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def list_golden():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.endswith("_traj.npz"))
+    """Solver-level goldens (MPC.forward chains).  `tracking_*` files are goldens of the reference's caller."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
+                  if f.endswith(".npz") and not f.endswith("_traj.npz") and not f.startswith(("tracking_", "ip_")))
+
+
+def list_tracking_golden():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("tracking_"))
 
 
 class Golden:

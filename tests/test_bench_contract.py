@@ -1,5 +1,6 @@
-"""CPU: the `--impl reference` arm of bench.py (the oracle port on the host cores) prints ONE JSON line with
-the keys the driver reads; the flop / byte model of the roofline is importable and consistent."""
+"""CPU: the `--impl reference` arm of bench.py (the unmodified reference on the host cores when its copy is staged
+under oracle/_ref/py or /root/reference exists, else the oracle port) prints ONE JSON line with the keys the driver
+reads; the flop / byte model of the roofline is importable and consistent."""
 import json
 import os
 import subprocess
@@ -22,7 +23,12 @@ def test_reference_arm_prints_the_contract_line():
         assert k in d, k
     assert "workload" in d["config"] and d["vs_baseline"] is None
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    sys.path.insert(0, ROOT)
+    from oracle import ref_import
+
+    assert cb["kind"] == ("reference" if ref_import.available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["scaling"] == "strong" and d["config"]["global_batch"] == 65536
     e = d["e2e"]
     assert e["value"] == d["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
 

@@ -13,7 +13,7 @@ import types
 import pytest
 import torch
 
-from golden_util import Golden, list_golden, max_rel_err_rows, rel_err
+from golden_util import Golden, list_golden, list_tracking_golden, max_rel_err_rows, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -29,15 +29,40 @@ if cuda:
 DEV = "cuda:0"
 
 
-def tolerances(rho_out_max, dtype):
+def tolerances(rho_out_max, dtype, c=None):
+    rho_used = rho_out_max / 10.0
     if dtype != torch.float64:
-        return dict(xu=2e-3, lam=1e-2, grad=1e-2)
+        # north_star: 1e-4 in fp32.  Asserted as such for the solution in the regime where fp32 can deliver it
+        # (rho <= 1e2, i.e. a cold al_iter = 2 call: SURVEY A.5 — from rho ~ 1e4 on H is no longer numerically SPD in
+        # fp32 and the reference's own behaviour is backend-specific).  Multipliers and gradients amplify the fp32
+        # rounding of the factorisation by cond(H): the fp32 goldens therefore carry the SAME scenario run by the
+        # reference in fp64 (keys ref64_*, oracle/gen_golden.py), and the budget is max(1e-4, 2 x the distance
+        # between the reference's own fp32 and fp64 results) — measured 2.8e-4 (lam) and 6.5e-4 (q_grad) on
+        # quad_T5_f32_cold, where two fp32 runs of the unmodified reference differ by 2.5e-4 in q_grad between
+        # themselves.  Measured errors per golden: profiles/r02_parity_errors.md.
+        tol = dict(xu=max(1e-4, 1e-6 * rho_used), lam=max(1e-4, 1e-5 * rho_used), grad=max(1e-4, 1e-5 * rho_used))
+        if c is not None and "ref64_xu64" in c:
+            floor = dict(xu=rel_err(c["xu64"], c["ref64_xu64"]), lam=rel_err(c["lam_out"], c["ref64_lam_out"]),
+                         grad=max(rel_err(c["q_grad"], c["ref64_q_grad"]), rel_err(c["Q_grad"], c["ref64_Q_grad"])))
+            tol = {k: max(tol[k], 2 * floor[k]) if k != "xu" else tol[k] for k in tol}
+            tol["reference_fp32_vs_fp64"] = floor
+        return tol
     # x, u: the 1e-6 relative bar of the task.  lam = lam + rho c amplifies an iterate difference e_xu by rho, and
     # cond(H) ~ rho / R limits the agreement of any two correct factorizations, so the multiplier and gradient
     # budgets grow with the largest penalty used in the call (same rule as tests/test_oracle_golden.py; measured
     # spread between two builds of this library that differ only in rounding order: 5e-7 vs 2e-6 at rho = 1e5)
-    rho_used = rho_out_max / 10.0
     return dict(xu=max(1e-6, 1e-14 * rho_used), lam=max(1e-6, 1e-10 * rho_used), grad=max(1e-6, 1e-11 * rho_used))
+
+
+def log_parity(**rec):
+    """Measured errors go to $ALMPC_PARITY_LOG (json lines) so that the widening of a tolerance is evidence, not
+    allowance: tools/parity_table.py turns the log into profiles/r02_parity_errors.md."""
+    path = os.environ.get("ALMPC_PARITY_LOG")
+    if path:
+        import json
+
+        with open(path, "a") as f:
+            f.write(json.dumps(rec) + "\n")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -130,7 +155,7 @@ def test_solve_matches_reference_golden(name):
         x, u, status = ctrl(x0, QuadCost(Qleaf, q, None), dyn, dyn)
         Qg, qg = torch.autograd.grad((x, u), (Qleaf, q), (c["gx"].to(DEV), c["gu"].to(DEV)))
         Qg = Qg.diagonal(dim1=-2, dim2=-1)
-        tol = tolerances(float(c["rho_out"].double().max()), gold.dtype)
+        tol = tolerances(float(c["rho_out"].double().max()), gold.dtype, c)
         assert ctrl.newton_steps() == c["nsteps"].tolist(), f"{name} call {ci}: Newton-step counts"
         assert bool(status) == bool(c["status"])
         assert (ctrl.last_status.cpu() == 3).all()
@@ -141,6 +166,8 @@ def test_solve_matches_reference_golden(name):
         e_q = rel_err(qg.cpu(), c["q_grad"])
         e_Q = rel_err(Qg.cpu(), c["Q_grad"])
         print(f"{name} c{ci}: xu {e_xu:.1e} lam {e_lam:.1e} q_grad {e_q:.1e} Q_grad {e_Q:.1e} (tol {tol})")
+        log_parity(test="solve_vs_reference_golden", golden=name, call=ci, rho_used=float(c["rho_out"].double().max()) / 10,
+                   xu=e_xu, lam=e_lam, q_grad=e_q, Q_grad=e_Q, tol=tol, newton_steps=ctrl.newton_steps())
         assert e_xu < tol["xu"], f"{name} call {ci}: xu {e_xu}"
         assert e_lam < tol["lam"], f"{name} call {ci}: lam {e_lam}"
         assert e_q < tol["grad"] and e_Q < tol["grad"], f"{name} call {ci}: grads {e_q} {e_Q}"
@@ -151,10 +178,11 @@ def test_solve_matches_reference_golden(name):
 
 
 @pytest.mark.parametrize("name", ["quad_T5_f64_cold", "pendulum_T5_f64_chain", "flying_T10_f64_cold", "cartpole1l_T5_f64_stream",
-                                  "quad_se_T5_f64_chain", "cartpole1l_se_T9_f64"] if cuda else [])
+                                  "quad_se_T5_f64_chain", "cartpole1l_se_T9_f64", "quad_T5_f32_cold"] if cuda else [])
 def test_first_newton_step_trace(name):
     """Step-level parity: gradient, Newton direction, the 20 merits, argmin and accept of the first
-    Newton step against the reference's own intermediate values."""
+    Newton step against the reference's own intermediate values.  fp64: 1e-12 / 1e-9; fp32 (rho = 1, the regime of
+    SURVEY A.5): the north_star bar of 1e-4, argmin and accept exact."""
     from deq_mpc_corl_b200.solver import SolveConfig, raw_forward
 
     gold = Golden(name)
@@ -171,12 +199,27 @@ def test_first_newton_step_trace(name):
                       c["lam_in"].to(dt).to(DEV).contiguous(), c["rho_in"].to(dt).reshape(-1).to(DEV).contiguous())
     dbg = out["debug"].cpu()
     N = T * n
-    assert rel_err(dbg[:, :N], c["step_grad"][0]) < 1e-12
-    assert max_rel_err_rows(dbg[:, N:2 * N], c["step_dir"][0].reshape(B, -1)) < 1e-9
-    assert rel_err(dbg[:, 2 * N:2 * N + 20].T, c["step_merits"][0]) < 1e-12
-    assert torch.equal(dbg[:, 2 * N + 20].long(), c["step_idx"][0])
+    f64 = dt == torch.float64
+    e = dict(grad=rel_err(dbg[:, :N], c["step_grad"][0]),
+             dir=max_rel_err_rows(dbg[:, N:2 * N], c["step_dir"][0].reshape(B, -1)),
+             merits=rel_err(dbg[:, 2 * N:2 * N + 20].T, c["step_merits"][0]),
+             merit_in=rel_err(dbg[:, 2 * N + 22], c["step_merit_in"][0]))
+    print(f"{name} first Newton step: " + " ".join(f"{k} {v:.1e}" for k, v in e.items()))
+    log_parity(test="first_newton_step", golden=name, **e)
+    # fp32: the north_star bar is 1e-4; measured 5e-8 / 6e-7 / 9e-8 (profiles/r02_parity_errors.md), asserted at 1e-5
+    assert e["grad"] < (1e-12 if f64 else 1e-5)
+    assert e["dir"] < (1e-9 if f64 else 1e-5)
+    assert e["merits"] < (1e-12 if f64 else 1e-5)
+    idx, ref_idx = dbg[:, 2 * N + 20].long(), c["step_idx"][0]
+    if f64:
+        assert torch.equal(idx, ref_idx)
+    else:  # fp32: identical except at ties of the reference's own merits (two fp32 runs of the reference differ there too)
+        gm = c["step_merits"][0].double()
+        b = torch.arange(B)
+        gap = (gm[idx, b] - gm[ref_idx, b]).abs() / gm[ref_idx, b].abs().clamp_min(1e-300)
+        assert (gap[idx != ref_idx] < 1e-6).all()
     assert torch.equal(dbg[:, 2 * N + 21].bool(), c["step_accept"][0])
-    assert rel_err(dbg[:, 2 * N + 22], c["step_merit_in"][0]) < 1e-12
+    assert e["merit_in"] < (1e-12 if f64 else 1e-5)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -361,11 +404,21 @@ def test_generic_callable_mode_user_model_matches_oracle(T, B, dtype):
 
 @pytest.mark.parametrize("model,T,B", [("rex_quadrotor", 5, 128), ("cartpole1l", 5, 128)])
 def test_cuda_matches_oracle_f32(model, T, B):
-    """fp32 solver vs the fp32 oracle: both sit on the fp32 noise floor of the algorithm
-    (SURVEY.md §7.3 item 2), so the budget is the measured oracle-vs-reference fp32 gap, not 1e-4."""
+    """fp32 solver vs the fp32 oracle on 128 seeded problems.  Both sit on the fp32 noise floor of the algorithm:
+    the batch-global stop statistic can land on either side of its 1e-3 threshold (one Newton step more or less),
+    and a problem whose 20 merits tie in fp32 takes a different step.  So the step counts may differ by one and the
+    bulk of the problems must agree to the fp32 bar, with a small budget of tie-broken outliers."""
     r = solve_both(model, T, B, 777, torch.float32)
     assert abs(sum(r["c"]["steps"]) - sum(r["o"]["steps"])) <= 1
-    assert rel_err(r["c"]["xu"], r["o"]["xu"]) < 3e-2
+    a, b = r["c"]["xu"].double().reshape(B, -1), r["o"]["xu"].double().reshape(B, -1)
+    rows = ((a - b).norm(dim=1) / b.norm(dim=1).clamp_min(1e-300))
+    med, frac_ok, tot = rows.median().item(), (rows < 1e-3).float().mean().item(), rel_err(r["c"]["xu"], r["o"]["xu"])
+    print(f"fp32 {model}: steps {r['c']['steps']} vs {r['o']['steps']}, xu median row err {med:.1e}, rows < 1e-3: {frac_ok:.2f}, total {tot:.1e}")
+    log_parity(test="cuda_vs_oracle_f32", model=model, median_row=med, frac_rows_below_1e_3=frac_ok, total=tot,
+               steps=r["c"]["steps"], oracle_steps=r["o"]["steps"])
+    assert tot < 3e-2
+    if r["c"]["steps"] == r["o"]["steps"]:
+        assert med < 1e-4 and frac_ok > 0.9
 
 
 # --------------------------------------------------------------------------------------------------
@@ -545,6 +598,52 @@ def test_tracking_mpc_fused_cost_and_chain_rule():
     assert tm.ctrl.warm_starting and isinstance(st3, bool) and torch.isfinite(x3).all()
 
 
+@pytest.mark.parametrize("name", list_tracking_golden() if cuda else [])
+def test_tracking_mpc_matches_reference_golden(name):
+    """`tracking.Tracking_MPC` against the reference's OWN `Tracking_MPC.forward` (deqmpc/policies.py:1236-1283,
+    golden written by oracle/gen_golden.py::run_tracking_scenario from the unmodified reference): a chain of cold
+    calls, then `warm_start_initialize` and streaming calls up to the rho_max exit; outputs, carried duals /
+    penalties and the gradients w.r.t. the fp32 network outputs x_ref, u_ref, q_scaling.  The solver state (lam, rho,
+    warm start) is carried by OUR module across the whole chain, never re-synchronised with the golden."""
+    from deq_mpc_corl_b200.tracking import Tracking_MPC
+
+    gold = Golden(name)
+    spec = MODEL_SPECS[gold.model]
+    nx, nu, T, B = spec["nx"], spec["nu"], gold.T, gold.B
+    dyn = make_dyn(gold.model, dt=spec["dt"])
+    args = types.SimpleNamespace(T=T, bsz=B, Q=gold.t("Q"), R=gold.t("R"), dtype="double" if gold.dtype == torch.float64 else "float",
+                                 device=DEV, solver_type="al", env=gold.model, rho_init_max=gold.rho_init_max)
+    env = types.SimpleNamespace(nx=nx, nu=nu, nq=None, dt=spec["dt"], dynamics=dyn, dynamics_derivatives=dyn,
+                                action_space=types.SimpleNamespace(low=gold.t("u_lower").numpy(), high=gold.t("u_upper").numpy()))
+    tm = Tracking_MPC(args, env)
+    x0 = gold.t("x0").to(DEV)
+    tm.reinitialize(gold.call(0)["x_ref"].to(DEV), None)
+    for ci in range(gold.n_calls):
+        c = gold.call(ci)
+        if gold.stream_after == ci:
+            tm.warm_start_initialize(c["x_ref"].to(DEV), c["u_ref"].to(DEV))
+        xr = c["x_ref"].to(DEV).requires_grad_(True)
+        ur = c["u_ref"].to(DEV).requires_grad_(True)
+        qs = c["q_scaling"].to(DEV).requires_grad_(True) if "q_scaling" in c else None
+        x, u, status = tm(x0, None, xr, ur, q_scaling=qs, al_iters=int(c["al_iters"]))
+        ins = (xr, ur) + ((qs,) if qs is not None else ())
+        grads = torch.autograd.grad((x, u), ins, (c["gx"].to(DEV), c["gu"].to(DEV)))
+        tol = tolerances(float(c["rho_out"].double().max()), gold.dtype)
+        assert bool(status) == bool(c["status"]), f"{name} call {ci}: status"
+        assert torch.equal(tm.ctrl.rho_prev.cpu().double(), c["rho_out"].double())
+        e = dict(x=rel_err(x.detach().cpu(), c["x"]), u=rel_err(u.detach().cpu(), c["u"]),
+                 lam=rel_err(tm.ctrl.lamda_prev.cpu(), c["lam_out"]),
+                 g_x_ref=rel_err(grads[0].cpu(), c["g_x_ref"]), g_u_ref=rel_err(grads[1].cpu(), c["g_u_ref"]))
+        if qs is not None:
+            e["g_q_scaling"] = rel_err(grads[2].cpu(), c["g_q_scaling"])
+        print(f"{name} c{ci}: " + " ".join(f"{k} {v:.1e}" for k, v in e.items()) + f" (tol {tol})")
+        assert x.dtype == c["x"].dtype and grads[0].dtype == c["g_x_ref"].dtype
+        # x, u are fp32 casts of the fp64 iterate: 1e-6 is below one fp32 ulp of the larger entries -> 2e-7 floor of the cast
+        assert e["x"] < max(tol["xu"], 1e-6) and e["u"] < max(tol["xu"] * 10, 1e-6), (ci, e)
+        assert e["lam"] < tol["lam"], (ci, e)
+        assert all(e[k] < max(tol["grad"], 2e-6) for k in e if k.startswith("g_")), (ci, e)
+
+
 def test_tracking_mpc_obstacle_and_state_estimator_routes():
     """Tracking_MPC picks Obstacle_MPC for `"obstacles" in args.env` (policies.py:1180-1198) and forwards
     state_estimator=True (policies.py:321); both must equal the corresponding MPC called directly."""
@@ -602,12 +701,13 @@ def test_c_abi_used_directly_like_integration_md():
                     ("rho_f32", ctypes.c_int32), ("flags", ctypes.c_int32),
                     ("rho_mult", ctypes.c_double), ("rho_max", ctypes.c_double),
                     ("dyn_params", ctypes.c_double * 48), ("u_lower", ctypes.c_double * 8), ("u_upper", ctypes.c_double * 8),
-                    ("n_obs", ctypes.c_int32), ("reserved", ctypes.c_int32), ("obs_radius", ctypes.c_double),
-                    ("obstacles", ctypes.c_void_p)]
+                    ("n_obs", ctypes.c_int32), ("select", ctypes.c_int32), ("obs_radius", ctypes.c_double),
+                    ("obstacles", ctypes.c_void_p), ("profile_ms", ctypes.c_void_p), ("stop_stats", ctypes.c_void_p),
+                    ("stop_reduce", ctypes.c_void_p), ("stop_reduce_user", ctypes.c_void_p), ("tune", ctypes.c_int32 * 4)]
 
     lib = ctypes.CDLL(product_lib.LIB_PATH)
     vp = ctypes.c_void_p
-    for fn, nargs in (("almpc_forward_f64", 15), ("almpc_backward_f64", 6)):
+    for fn, nargs in (("almpc_forward_f64", 15), ("almpc_backward_f64", 7)):
         getattr(lib, fn).argtypes = [ctypes.POINTER(Desc)] + [vp] * nargs
         getattr(lib, fn).restype = ctypes.c_int
     for fn in ("almpc_factor_elems", "almpc_workspace_bytes"):
@@ -646,7 +746,7 @@ def test_c_abi_used_directly_like_integration_md():
     g = torch.Generator().manual_seed(5)
     grad = torch.randn(B, T, n, generator=g, dtype=torch.float64).to(DEV)
     gQ, gq = torch.empty_like(xu), torch.empty_like(xu)
-    rc = lib.almpc_backward_f64(ctypes.byref(d), p(factor), p(xu), p(grad), p(gQ), p(gq), stream)
+    rc = lib.almpc_backward_f64(ctypes.byref(d), p(factor), p(xu), p(grad), p(status), p(gQ), p(gq), stream)
     assert rc == 0, lib.almpc_last_error()
     torch.cuda.synchronize()
     # the Python drop-in on the same inputs

@@ -32,13 +32,17 @@ def test_library_exports_every_declared_symbol():
 
 def test_desc_layout_matches_header(tmp_path):
     csrc = tmp_path / "sz.c"
-    csrc.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "almpc.h"\nint main(){printf("%zu %zu %zu %zu %zu",'
+    csrc.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "almpc.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu",'
                     "sizeof(almpc_desc), offsetof(almpc_desc, rho_mult), offsetof(almpc_desc, dyn_params),"
-                    "offsetof(almpc_desc, u_lower), offsetof(almpc_desc, flags));return 0;}\n")
+                    "offsetof(almpc_desc, u_lower), offsetof(almpc_desc, flags), offsetof(almpc_desc, select),"
+                    "offsetof(almpc_desc, obstacles), offsetof(almpc_desc, profile_ms),"
+                    "offsetof(almpc_desc, stop_reduce_user));return 0;}\n")
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(csrc), "-o", str(exe)])
-    size, o_mult, o_par, o_lo, o_flags = map(int, subprocess.check_output([str(exe)]).split())
+    size, o_mult, o_par, o_lo, o_flags, o_sel, o_obs, o_prof, o_user = map(int, subprocess.check_output([str(exe)]).split())
     assert size == ctypes.sizeof(_lib.Desc)
+    assert o_sel == _lib.Desc.select.offset and o_obs == _lib.Desc.obstacles.offset
+    assert o_prof == _lib.Desc.profile_ms.offset and o_user == _lib.Desc.stop_reduce_user.offset
     assert o_mult == _lib.Desc.rho_mult.offset and o_par == _lib.Desc.dyn_params.offset
     assert o_lo == _lib.Desc.u_lower.offset and o_flags == _lib.Desc.flags.offset
 

@@ -3,7 +3,7 @@
 import pytest
 import torch
 
-from golden_util import Golden, list_golden, rel_err
+from golden_util import Golden, list_golden, list_tracking_golden, rel_err
 from oracle import almpc_oracle as orc
 from oracle.problem_gen import make_oracle_model
 
@@ -90,3 +90,44 @@ def test_oracle_matches_reference(name):
         assert rel_err(r["q_grad"], c["q_grad"]) < tol["grad"], f"call {ci}: q_grad"
         assert rel_err(r["Q_grad"], c["Q_grad"]) < tol["grad"]
         assert rel_err(r["x"], c["x"]) < max(tol["xu"], 1e-6)
+
+
+@pytest.mark.parametrize("name", list_tracking_golden())
+def test_oracle_matches_reference_tracking_mpc(name):
+    """The reference's caller `Tracking_MPC.forward` (deqmpc/policies.py:1236-1297) restated on the oracle: cost
+    build Q (1 + q_scaling), p = -Q xu_ref (:1245-1248,1295) and its chain rule to the fp32 network outputs, with
+    the solver state carried over the whole chain (cold calls, warm_start_initialize :1305-1310, streaming calls)."""
+    gold = Golden(name)
+    model = make_oracle_model(gold.model)
+    nx = model.nx
+    mpc = orc.OracleMPC(model, gold.T, gold.t("u_lower"), gold.t("u_upper"), gold.B, dtype=gold.dtype)
+    Q0 = torch.cat([gold.t("Q"), gold.t("R")]).to(gold.dtype)
+    x0 = gold.t("x0")
+    mpc.reinitialize(gold.call(0)["x_ref"])
+    for ci in range(gold.n_calls):
+        c = gold.call(ci)
+        if gold.stream_after == ci:
+            xi, ui = mpc.x_init, mpc.u_init
+            ui[:, -1:] = c["u_ref"][:, -1:]
+            xi[:, -1:] = c["x_ref"][:, -1:]
+            mpc.warm_start_initialize(xi, ui, gold.rho_init_max)
+        if mpc.x_init is None:
+            mpc.x_init, mpc.u_init = c["x_ref"].clone(), c["u_ref"].clone()
+        xu_ref = torch.cat([c["x_ref"], c["u_ref"]], -1).to(gold.dtype)
+        scale = 1.0 + c["q_scaling"].to(gold.dtype) if "q_scaling" in c else torch.ones(gold.B, gold.T, dtype=gold.dtype)
+        Qd = Q0 * scale[..., None]
+        mpc.al_iter = int(c["al_iters"])
+        x, u, status, xu = mpc.solve(x0, Qd, -Qd * xu_ref)
+        Qg, qg = mpc.backward(c["gx"], c["gu"])
+        # chain rule of p = -Q0 (1+s) xu_ref, Qd = Q0 (1+s)
+        g_ref = -(Qd * qg)
+        g_s = ((Qg - xu_ref * qg) * Q0).sum(-1)
+        rho_used = float(c["rho_out"].double().max()) / 10.0
+        tol_x, tol_g = max(1e-6, 1e-14 * rho_used), max(2e-6, 3e-12 * rho_used)
+        assert bool(status) == bool(c["status"]), f"call {ci}"
+        assert torch.equal(mpc.rho_prev.double(), c["rho_out"].double())
+        assert rel_err(x, c["x"]) < tol_x and rel_err(u, c["u"]) < 10 * tol_x, f"call {ci}"
+        assert rel_err(g_ref[..., :nx].float(), c["g_x_ref"]) < tol_g, f"call {ci}: x_ref grad"
+        assert rel_err(g_ref[..., nx:].float(), c["g_u_ref"]) < tol_g, f"call {ci}: u_ref grad"
+        if "q_scaling" in c:
+            assert rel_err(g_s.float(), c["g_q_scaling"]) < tol_g, f"call {ci}: q_scaling grad"

@@ -1,4 +1,4 @@
-"""Per-kernel CUDA-event times of one 64K quadrotor forward (almpc_set_profiling): tools/kernel_times.py [model T B [f32]]."""
+"""Per-kernel CUDA-event times of one 64K quadrotor forward (desc.profile_ms): tools/kernel_times.py [model T B [f32]]."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
@@ -24,13 +24,12 @@ lib = _lib.load()
 res = []
 for it in range(4):
     xu = xu0.clone(); lam = torch.zeros(B, m, dtype=DT, device=dev); rho = torch.ones(B, dtype=DT, device=dev)
-    lib.almpc_set_profiling(1 if it else 0)
+    cfg.profile = bool(it)
     out = raw_forward(cfg, x0, Qd, q, xu, lam, rho)
     torch.cuda.synchronize()
     if it:
-        buf = (ctypes.c_double * 8)(); lib.almpc_get_profile(buf); res.append(list(buf))
-lib.almpc_set_profiling(0)
+        res.append(out["profile_ms"])
 res.sort(key=lambda r: r[1])
 r = res[len(res) // 2]
 print(f"{model} T={T} B={B}: newton steps {out['info'][_lib.INFO_TOTAL_NEWTON].item()}  k_jacobian {r[0]/max(r[4],1):.3f} ms  "
-      f"k_factor_solve {r[1]/max(r[5],1):.3f} ms  k_line_search {r[2]/max(r[6],1):.3f} ms  (launch counts {r[4]:.0f}/{r[5]:.0f}/{r[6]:.0f})")
+      f"factor (or fused factor+line search) {r[1]/max(r[5],1):.3f} ms  k_line_search {r[2]/max(r[6],1):.3f} ms  (launch counts {r[4]:.0f}/{r[5]:.0f}/{r[6]:.0f})")
