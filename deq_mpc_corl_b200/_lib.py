@@ -47,32 +47,22 @@ class Desc(ctypes.Structure):
         ("stop_stats", ctypes.c_void_p),
         ("stop_reduce", ctypes.c_void_p),
         ("stop_reduce_user", ctypes.c_void_p),
-        ("tune", ctypes.c_int32 * 4),
     ]
 
 
 # int (*almpc_stop_reduce_fn)(double* stats_dev, void* stream, void* user)
 STOP_REDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
 
-SELECT_FAC_SINGLE, SELECT_NO_FUSE, SELECT_LS_CTA, SELECT_PDL = 1, 2, 4, 8
-
-
-def env_tune():
-    """desc.tune from ALMPC_TUNE="a,b,c,d" (measurement knobs; empty = library defaults)."""
-    v = os.environ.get("ALMPC_TUNE", "")
-    out = [0, 0, 0, 0]
-    for i, t in enumerate(v.split(",")[:4]):
-        if t.strip():
-            out[i] = int(t)
-    return out
+SELECT_FAC_SINGLE, SELECT_FUSE, SELECT_LS_CTA, SELECT_PDL, SELECT_NO_RING = 1, 2, 4, 8, 16
 
 
 def env_select():
-    """desc.select from the environment (A/B measurements, differential tests): ALMPC_FAC_SINGLE, ALMPC_NO_FUSE,
-    ALMPC_LS_CTA, ALMPC_PDL.  Read per call on the host side; the library itself has no global state."""
+    """desc.select from the environment (A/B measurements, differential tests): ALMPC_FAC_SINGLE, ALMPC_FUSE,
+    ALMPC_LS_CTA, ALMPC_PDL, ALMPC_NO_RING.  Read per call on the host side; the library itself has no global state."""
     e = os.environ
-    return ((SELECT_FAC_SINGLE if e.get("ALMPC_FAC_SINGLE") else 0) | (SELECT_NO_FUSE if e.get("ALMPC_NO_FUSE") else 0)
-            | (SELECT_LS_CTA if e.get("ALMPC_LS_CTA") else 0) | (SELECT_PDL if e.get("ALMPC_PDL") else 0))
+    return ((SELECT_FAC_SINGLE if e.get("ALMPC_FAC_SINGLE") else 0) | (SELECT_FUSE if e.get("ALMPC_FUSE") else 0)
+            | (SELECT_LS_CTA if e.get("ALMPC_LS_CTA") else 0) | (SELECT_PDL if e.get("ALMPC_PDL") else 0)
+            | (SELECT_NO_RING if e.get("ALMPC_NO_RING") else 0))
 
 
 FLAG_SKIP_FINAL_DUAL = 1

@@ -124,35 +124,36 @@ class MPC(Module):
         # ---- dual warm start
         m = self.neq + self.nineq
         lam = self.lamda_prev
-        if lam is None or lam.shape != (n_batch, m):
+        if lam is None:
             lam = torch.zeros(n_batch, m, dtype=self.dtype, device=dev)
+        elif lam.shape != (n_batch, m):
+            # the reference would fail inside its first residual expression; silently restarting the duals from zero
+            # (wrong batch size, missing reinitialize(), a subclass that changed nineq) would change results unnoticed
+            raise _lib.AlmpcError(f"lamda_prev has shape {tuple(lam.shape)}, expected {(n_batch, m)}: call reinitialize() "
+                                  "for a new batch")
         rho = self.rho_prev
         if not torch.is_tensor(rho):
             rho = torch.full((n_batch, 1), float(rho), dtype=self.dtype, device=dev)
         rho_dtype = rho.dtype
-        common = dict(T=self.T, al_iter=int(self.al_iter), max_newton=self.max_newton_steps,
-                      stream_mode=bool(self.warm_starting),
-                      rho_f32=(rho_dtype == torch.float32 and self.dtype == torch.float64), rho_max=self.rho_max,
-                      state_estimator=bool(self.state_estimator))
         extra = self._extra_constraints(dev)
         if dyn is not None:
             solve = ALSolve
-            cfg = SolveConfig(dyn=dyn, u_lower=self._bounds_host[0], u_upper=self._bounds_host[1], **common, **extra)
-            cfg.global_stop = self.global_stop
-            if self.cuda_graph and self.global_stop is None:
-                if self._graph_cache is None:
-                    from .solver import GraphCache
-
-                    self.__dict__["_graph_cache"] = GraphCache()
-                cfg.graph_cache = self._graph_cache
+            cfg = self._solve_config(dyn, rho_dtype, extra)
         else:
             if extra:
                 raise _lib.AlmpcError("obstacle constraints need a native dynamics functor")
             solve = GenericALSolve
             cfg = GenericConfig(dx=dx, dx_jac=dx_jac, nx=self.n_state, nu=self.n_ctrl,
                                 u_lower=self.u_lower.to(dev).to(self.dtype), u_upper=self.u_upper.to(dev).to(self.dtype),
-                                **common)
-        xu0 = torch.cat([x.to(self.dtype), u.to(self.dtype)], dim=2)
+                                T=self.T, al_iter=int(self.al_iter), max_newton=self.max_newton_steps,
+                                stream_mode=bool(self.warm_starting),
+                                rho_f32=(rho_dtype == torch.float32 and self.dtype == torch.float64), rho_max=self.rho_max,
+                                state_estimator=bool(self.state_estimator))
+        # one fresh [B,T,n] buffer, filled by two converting copies (instead of two casts + a concatenation)
+        xu0 = torch.empty(n_batch, self.T, self.n_state + self.n_ctrl, dtype=self.dtype, device=dev)
+        xu0[:, :, :self.n_state].copy_(x)
+        xu0[:, :, self.n_state:].copy_(u)
+        cfg.__dict__["_owns_xu"] = True
         xo, uo, xu, lam_new, rho_new, dyn_res, status, info, _ = solve.apply(
             Qd, q, x0.to(self.dtype), xu0, lam.to(dev).to(self.dtype), rho.to(dev).to(self.dtype).reshape(-1), cfg)
 
@@ -170,6 +171,32 @@ class MPC(Module):
     def _extra_constraints(self, dev):
         """Hook for subclasses (Obstacle_MPC): extra SolveConfig fields."""
         return {}
+
+    def _solve_config(self, dyn, rho_dtype, extra):
+        """The SolveConfig of this call.  Cached per (dynamics object, al_iter, mode): building it — and the C
+        descriptor it carries — on every forward cost a fifth of a 200-problem solve."""
+        cache = self.__dict__.setdefault("_cfg_cache", {})
+        key = (id(dyn), int(self.al_iter), bool(self.warm_starting), rho_dtype, self.max_newton_steps, self.rho_max)
+        cfg = cache.get(key)
+        if cfg is None or cfg.dyn is not dyn:
+            if len(cache) > 32:
+                cache.clear()
+            cfg = cache[key] = SolveConfig(
+                dyn=dyn, u_lower=self._bounds_host[0], u_upper=self._bounds_host[1], T=self.T, al_iter=int(self.al_iter),
+                max_newton=self.max_newton_steps, stream_mode=bool(self.warm_starting),
+                rho_f32=(rho_dtype == torch.float32 and self.dtype == torch.float64), rho_max=self.rho_max,
+                state_estimator=bool(self.state_estimator))
+        cfg.obstacles = extra.get("obstacles")
+        cfg.obs_radius = extra.get("obs_radius", 0.0)
+        cfg.global_stop = self.global_stop
+        cfg.graph_cache = None
+        if self.cuda_graph and self.global_stop is None:
+            if self._graph_cache is None:
+                from .solver import GraphCache
+
+                self.__dict__["_graph_cache"] = GraphCache()
+            cfg.graph_cache = self._graph_cache
+        return cfg
 
     @staticmethod
     def _resolve(dx, dx_jac):

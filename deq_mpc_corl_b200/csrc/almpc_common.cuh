@@ -61,7 +61,13 @@ struct KParams {
   double rho_mult, rho_max;
   int B, T, al_iter, max_newton, stream_mode, rho_f32, flags;
   int part_off, ticket_total;  // line search: slot offset of the CTA partials / CTAs that take a ticket
-  int stagger, n_sm;           // k_newton_pair: start-up delay (cycles) per warp slot of an SM / SMs of the device
+  // Scratch ring for block factors that only this launch reads (the backward sweep of the same kernel): every Newton
+  // step of an AL iteration that cannot be the last one.  A CTA claims one of kRingSlots slots of its SM (bit mask in
+  // ring_mask[smid % kRingSMs]) and writes its problems' factors there instead of into the caller's `factor` buffer;
+  // the slots are overwritten ~20 times per launch while their lines are still in L2, so most of these 16 KB per
+  // problem never reach HBM.  NULL: every step streams its factor to `factor` (what round 1 did).
+  S* ring;
+  int* ring_mask;
   int global_stop;             // 1: the last CTA publishes this shard's statistics instead of steering (k_steer does)
   double* stop_stats;          // device [4]: sum ||c+||^2 at entry, at exit, max rho — reduced over the shards by the caller
   int n_obs;                   // obstacle rows per stage (Obstacle_MPC), 0 = none
@@ -89,6 +95,30 @@ template <typename S> __device__ __forceinline__ S fmax0(S x) { return x < S(0) 
 // fused multiply-adds.  Every kernel that evaluates a merit uses THIS form, so entry merit and candidates agree.
 template <typename S> __device__ __forceinline__ S cost_term(S z, S Q, S q) { return z * (S(0.5) * (Q * z) + q); }
 template <typename S> __device__ __forceinline__ bool finite_(S x) { return (x - x) == S(0); }
+
+constexpr int kRingSMs = 160;   // mask words (>= SMs of the device; %smid is folded into this range)
+constexpr int kRingSlots = 8;   // scratch slots per mask word
+
+// Claims a scratch slot for this CTA (one thread calls it): slot index, or -1 when the ring is off for this launch or
+// all slots of this SM are taken (the CTA then simply uses the caller's factor buffer — never waits).
+template <typename S>
+__device__ __forceinline__ int ring_claim(const KParams<S>& P, const Ctl* ctl) {
+  if (!P.ring || P.stream_mode || ctl->a + 1 >= P.al_iter) return -1;  // this AL iteration may be the last: keep the factor
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  int* m = P.ring_mask + (smid % kRingSMs);
+  for (int tries = 0; tries < 4; ++tries) {
+    const int old = *(volatile int*)m;
+    const int bit = __ffs(~old) - 1;
+    if (bit < 0 || bit >= kRingSlots) return -1;
+    if (atomicCAS(m, old, old | (1 << bit)) == old) return (int)(smid % kRingSMs) * kRingSlots + bit;
+  }
+  return -1;
+}
+template <typename S>
+__device__ __forceinline__ void ring_release(const KParams<S>& P, int slot) {
+  atomicAnd(P.ring_mask + slot / kRingSlots, ~(1 << (slot % kRingSlots)));
+}
 
 // Programmatic dependent launch: the step kernels are launched with stream serialization relaxed, so a kernel's
 // CTAs are scheduled while the previous kernel drains; nothing of the predecessor may be read before this wait.

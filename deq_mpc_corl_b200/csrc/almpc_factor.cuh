@@ -223,16 +223,22 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
   constexpr int LB = NN | 1;  // odd row stride of the staged G / E blocks (bank-conflict free rows)
   constexpr bool OBS = (V == 1), SE = (V == 2);  // variant: 0 plain, 1 obstacle rows, 2 state estimator
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_ring;
   grid_dep_wait();
   const int mode = ctl->mode;
   if (mode == MODE_DONE) return;
+  if (threadIdx.x == 0) s_ring = ring_claim(P, ctl);
+  __syncthreads();
+  const int ring_slot = s_ring;
   const int T = P.T;
   const int n_obs = OBS ? P.n_obs : 0;
   const Layout<NX, NU> L(T, n_obs, SE);
   const int SI = OBS ? L.SI : 2 * NU;  // compile-time constant without obstacle rows
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int prob = blockIdx.x * WPB + warp;
-  if (prob >= P.B) return;
+  if (prob >= P.B) {  // (warp 0 always has a problem, so the release below is reached)
+    return;
+  }
   S* sm = reinterpret_cast<S*>(smem_raw) + (size_t)warp * L.total;
   S* xu = sm + L.xu;
   S* dv = sm + L.dv;
@@ -246,7 +252,8 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
   S* lam = lam_g + (size_t)prob * L.m;
   const S* cres = c_g + (size_t)prob * L.neq;
   const S* Gp = G_g + (size_t)prob * (T - 1) * NX * NN;
-  S* fac = fac_g + (size_t)prob * factor_elems<NX, NU>(T);
+  S* fac = (ring_slot >= 0) ? P.ring + ((size_t)ring_slot * 4 + warp) * factor_elems<NX, NU>(T)
+                            : fac_g + (size_t)prob * factor_elems<NX, NU>(T);
   S* dbg = debug_g ? debug_g + (size_t)prob * (2 * L.N + 24) : nullptr;
   const S* obs = OBS ? P.obs + (size_t)prob * T * n_obs * 3 : nullptr;
 
@@ -554,6 +561,10 @@ k_factor_solve(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restri
     if (!ok) status &= ~ALMPC_STATUS_CHOL_OK;
     status_g[prob] = status;
   }
+  if (ring_slot >= 0) {  // every warp of the CTA is done with the scratch factors
+    __syncthreads();
+    if (threadIdx.x == 0) ring_release(P, ring_slot);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -653,7 +664,7 @@ __device__ __forceinline__ bool factor_pair(const KParams<S>& P, const S* __rest
                                             S* __restrict__ d_g, S* __restrict__ merit_g,
                                             double* __restrict__ rentry_g, int* __restrict__ status_g,
                                             S* __restrict__ debug_g, const int mode, unsigned char* smem_raw,
-                                            const int smem_per_problem, const int pw, PairCarry<S>& out) {
+                                            const int smem_per_problem, const int pw, S* ring_cta, PairCarry<S>& out) {
   constexpr int NN = NX + NU;
   static_assert(NN <= 16 && NX + 1 <= 16, "pair mapping: both row sets must fit a half-warp");
   constexpr int LD = ScrLd<NN>::LD;
@@ -685,7 +696,9 @@ __device__ __forceinline__ bool factor_pair(const KParams<S>& P, const S* __rest
   S* lam = lam_g + (size_t)prob * L.m;
   const S* cres = c_g + (size_t)prob * L.neq;
   const S* Gp = G_g + (size_t)prob * (T - 1) * NX * NN;
-  S* fac = fac_g + (size_t)prob * factor_elems<NX, NU>(T);
+  // ring_cta: this CTA's scratch slot (4 factors) when nobody reads the factor after this launch, else NULL
+  S* fac = ring_cta ? ring_cta + (size_t)(warp * 2 + (live ? half : 0)) * factor_elems<NX, NU>(T)
+                    : fac_g + (size_t)prob * factor_elems<NX, NU>(T);
   S* dbg = (debug_g && live) ? debug_g + (size_t)prob * (2 * L.N + 24) : nullptr;
 
   if (T > 1) half_copy_block_async<NX, NN, LB>(Gt, Gp, hl);
@@ -1011,13 +1024,24 @@ k_factor_solve_pair(const KParams<S> P, const S* __restrict__ Qd_g, const S* __r
                     S* __restrict__ merit_g, double* __restrict__ rentry_g, int* __restrict__ status_g,
                     S* __restrict__ debug_g, const Ctl* __restrict__ ctl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_ring;
+  static_assert(WPB * 2 <= 4, "a scratch slot holds 4 factors");
   grid_dep_wait();
   const int mode = ctl->mode;
   if (mode == MODE_DONE) return;
+  if (threadIdx.x == 0) s_ring = ring_claim(P, ctl);
+  __syncthreads();
+  const int ring_slot = s_ring;
   PairCarry<S> carry;
   const Layout<NX, NU> L(P.T, 0, V == 2, true);
+  S* ring_cta = (ring_slot >= 0) ? P.ring + (size_t)ring_slot * 4 * factor_elems<NX, NU>(P.T) : nullptr;
   factor_pair<NX, NU, S, WPB, V, false>(P, Qd_g, q_g, xu_g, lam_g, rho_g, fac_g, G_g, c_g, d_g, merit_g, rentry_g, status_g,
-                                        debug_g, mode, smem_raw, L.total, (int)(blockIdx.x * WPB + (threadIdx.x >> 5)) * 2, carry);
+                                        debug_g, mode, smem_raw, L.total, (int)(blockIdx.x * WPB + (threadIdx.x >> 5)) * 2,
+                                        ring_cta, carry);
+  if (ring_slot >= 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) ring_release(P, ring_slot);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -8,12 +8,15 @@
 //   steering       (steer_solve)                     batch-global stop rule / rho_max exit by the last CTA
 //                                                                                                al_utils.py:551-564
 //
-// Why one kernel: the factor phase is bound by the latency of its dependent chains (FP64 pipe ~20 % busy), the line
-// search by the FP64 pipe; as separate kernels the two never overlap.  Here every warp runs factor -> line search on
-// its own two problems, warps drift apart, and the line-search FMAs of one warp fill the issue slots the pivot
-// chains of the others leave empty.  The direction, the entry merit / residual and the problem's inputs no longer
-// cross HBM between the two phases (north_star (3): "line search and the dual / penalty updates run in the same
-// persistent kernel loop").
+// Why it exists: north_star (3) asks for the line search and the dual / penalty updates "in the same persistent
+// kernel loop"; the direction, the entry merit / residual and the problem's inputs then no longer cross HBM between
+// the two phases.  Why it is NOT the default (ALMPC_SELECT_FUSE opts in): measured on B200 (quadrotor T=5, 64K
+// problems, fp64) the fused kernel takes 1.44 ms against 0.83 + 0.40 ms for k_factor_solve_pair + k_line_search_warp.
+// Both phases are bound by the latency of one warp's dependent chain times the warps an SM can hold; fusing them
+// makes every warp carry both chains at the factor phase's occupancy (12 warps/SM at 168 registers, where the
+// stand-alone line search runs 16 warps/SM at 128), and the hoped-for overlap of FP64-bound line-search warps with
+// latency-bound factor warps does not materialise: staggering the phases of an SM's warps changed nothing
+// (profiles/r02_fused_newton_tail.md).
 //
 // Mapping: the pair mapping of k_factor_solve_pair (1 half-warp = 1 problem, 2 problems per warp); the line search
 // spreads the 2 x 20 x (T-1) (problem, candidate, stage) items of the warp over its 32 lanes, the T-1 stage items of
@@ -47,6 +50,7 @@ k_newton_pair(const KParams<S> P, const S* __restrict__ x0_g, const S* __restric
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double wred[WPB][3];
   __shared__ bool is_last;
+  __shared__ int s_ring;
   grid_dep_wait();
   const int mode = ctl->mode;
   if (mode == MODE_DONE) return;
@@ -58,24 +62,21 @@ k_newton_pair(const KParams<S> P, const S* __restrict__ x0_g, const S* __restric
   const LsLayout<NX, NU> LL(T, 0, SE);
 
   double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;  // this warp's statistics (identical on all lanes)
-  // Persistent warps: warp g of the grid owns the problem pairs g, g + #warps, ... (static assignment: the order in
-  // which a warp's statistics are summed is fixed -> deterministic).  Left alone, all warps of an SM would sit in
-  // the same phase at the same time (they start together and every pair takes about as long), and the FP64-bound
-  // line search would never meet the latency-bound factor phase; a start-up delay proportional to the warp's slot
-  // on its SM spreads the phases.
+  // One warp = one pair of problems.  (Measured on B200, quadrotor 64K: persistent warps looping over pairs, with
+  // or without a start-up stagger that spreads the phases of the warps of an SM, were 7-20 % slower than one CTA
+  // per 4 problems — profiles/r02_fused_newton_tail.md.)
+  if (tid == 0) s_ring = ring_claim(P, ctl);
+  __syncthreads();
+  const int ring_slot = s_ring;
+  S* ring_cta = (ring_slot >= 0) ? P.ring + (size_t)ring_slot * 4 * factor_elems<NX, NU>(T) : nullptr;
   const int npairs = (P.B + 1) >> 1;
   const int gwarp = blockIdx.x * WPB + warp, nwarps = gridDim.x * WPB;
-  if (P.stagger > 0 && gwarp + nwarps < npairs) {  // only worth it when every warp iterates
-    const long long t0 = clock64();
-    const long long wait = (long long)P.stagger * (((int)blockIdx.x / P.n_sm) * WPB + warp);
-    while (clock64() - t0 < wait) __nanosleep(200);
-  }
   for (int pair = gwarp; pair < npairs; pair += nwarps) {
     const int pw = pair * 2;
     __syncwarp();  // the previous pair's line search is done with the staging area before G_0 of this pair lands in it
     PairCarry<S> pc;
     factor_pair<NX, NU, S, WPB, V, true>(P, Qd_g, q_g, xu_g, lam_g, rho_g, fac_g, G_g, c_g, nullptr, merit_g, nullptr,
-                                         status_g, debug_g, mode, smem_raw, spp, pw, pc);
+                                         status_g, debug_g, mode, smem_raw, spp, pw, ring_cta, pc);
     S* smw = reinterpret_cast<S*>(smem_raw) + (size_t)warp * 2 * spp;
     S* sm = smw + (size_t)half * spp;
     S* ls = sm + L.Gt;  // staging area of this half-warp's problem
@@ -236,6 +237,7 @@ k_newton_pair(const KParams<S> P, const S* __restrict__ x0_g, const S* __restric
   // ---- batch-global statistics: per-CTA partials (fixed order), the last CTA steers the solve
   if (lane == 0) { wred[warp][0] = acc0; wred[warp][1] = acc1; wred[warp][2] = acc2; }
   __syncthreads();
+  if (tid == 0 && ring_slot >= 0) ring_release(P, ring_slot);
   if (tid == 0) {
     double b0 = 0, b1 = 0, b2 = 0;
     for (int w = 0; w < WPB; ++w) { b0 += wred[w][0]; b1 += wred[w][1]; b2 = fmax(b2, wred[w][2]); }

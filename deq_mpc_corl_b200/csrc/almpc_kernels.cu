@@ -65,7 +65,7 @@ static KParams<S> make_params(const almpc_desc* d) {
   P.stream_mode = d->stream_mode; P.rho_f32 = d->rho_f32; P.flags = d->flags;
   P.part_off = 0; P.ticket_total = 0;
   P.global_stop = 0; P.stop_stats = nullptr;
-  P.stagger = 0; P.n_sm = 1;
+  P.ring = nullptr; P.ring_mask = nullptr;
   P.n_obs = d->obstacles ? d->n_obs : 0;
   P.obs_r2 = (S)(d->obs_radius * d->obs_radius);
   P.obs = (const S*)d->obstacles;
@@ -86,7 +86,7 @@ static int check_desc(const almpc_desc* d) {
 constexpr int kWPB = 4;
 
 // Per-call profiling (desc.profile_ms != NULL): events around every launch of this forward call.
-struct ProfEv { cudaEvent_t a, b; int kind; };
+struct ProfEv { cudaEvent_t a, b; int kind, slot; };
 
 static int n_blocks(int B) { return (B + kWPB - 1) / kWPB; }
 
@@ -107,14 +107,15 @@ static LsGeom ls_geom(int B, int T) {
 
 // device workspace carved out of the caller's buffer
 struct WsPlan {
-  size_t ctl, partials, merit, rentry, status, c, d, G, total;
+  size_t ctl, partials, merit, rentry, status, c, d, G, ring, total;
 };
+constexpr int kRingMinBatch = 8192;  // below this a whole batch of factors sits in L2 anyway
 static WsPlan ws_plan(int B, int T, int nx, int nu, size_t es) {
   const size_t nn = (size_t)nx + nu;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   WsPlan w;
   size_t o = 0;
-  w.ctl = o; o += 256;
+  w.ctl = o; o += 1024;  // control block (256 B) + the scratch-ring slot masks (kRingSMs ints)
   // one slot of statistics per CTA of the kernel that runs the line search: the stand-alone kernels use at most
   // ls_geom().blocks CTAs, the fused Newton-tail kernel one CTA per 4 problems
   size_t slots = (size_t)ls_geom(B, T).blocks;
@@ -126,6 +127,12 @@ static WsPlan ws_plan(int B, int T, int nx, int nu, size_t es) {
   w.c = o; o = up(o + (size_t)B * T * nx * es);
   w.d = o; o = up(o + (size_t)B * T * nn * es);
   w.G = o; o = up(o + (size_t)B * (T - 1) * nx * nn * es);
+  // scratch ring for the factors of Newton steps nobody differentiates through (KParams::ring): 4 factors per slot
+  w.ring = 0;
+  if (B >= kRingMinBatch) {
+    w.ring = o;
+    o = up(o + (size_t)kRingSMs * kRingSlots * 4 * ((size_t)T * nn * nn + (size_t)(T - 1) * nx * nn) * es);
+  }
   w.total = o;
   return w;
 }
@@ -159,7 +166,6 @@ static cudaError_t allow_max_smem(F fn, int optin) {
 }
 
 constexpr int kWLS = 4;  // warps per CTA of the warp-synchronous line search
-constexpr int kDefaultStagger = 8000;  // cycles per warp slot, k_newton_pair (measured: profiles/r02_stagger_sweep.md)
 
 struct LsWarpCfg { const void* fn; int grid_cap; size_t smem; int pw; };
 
@@ -208,7 +214,7 @@ struct Plan {
   int n_sm = 0;
   bool use_pair = false, fused = false;
   size_t smem_fac = 0, smem_ls = 0, smem_fin = 0, smem_fused = 0;
-  int fac_threads = 0, fac_per_cta = 0, fin_ppw = 1, ls_grid_cap = 0, fused_grid_cap = 0;
+  int fac_threads = 0, fac_per_cta = 0, fin_ppw = 1, ls_grid_cap = 0;
   LsWarpCfg lw{nullptr, 0, 0, 1};
 };
 
@@ -259,19 +265,13 @@ static int make_plan(Plan& pl, int dev, int T, int n_obs, int select) {
       pl.fac_threads = kWPP * 32;
       pl.fac_per_cta = 2 * kWPP;
       pl.smem_fac = smem_pair;
-      // fused Newton tail (factor + line search in one kernel): needs the warp line-search item layout, (T-1) | 32
-      if (auto kf = fused_kernel<M, S, V>(); kf && !(select & ALMPC_SELECT_NO_FUSE) && (32 % (T - 1) == 0)) {
+      // fused Newton tail (factor + line search in one kernel, opt-in): needs the warp line-search item layout, (T-1) | 32
+      if (auto kf = fused_kernel<M, S, V>(); kf && (select & ALMPC_SELECT_FUSE) && (32 % (T - 1) == 0)) {
         const size_t smem_fused = (size_t)2 * kWPP * fused_smem_per_problem<NX, NU>(T, SE) * sizeof(S);
         if (smem_fused + 1024 <= 227 * 1024 &&
             allow_max_smem(kf, optin) == cudaSuccess) {
-          int occ = 0;
-          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, kWPP * 32, smem_fused) != cudaSuccess || occ < 1) {
-            (void)cudaGetLastError();
-            occ = 1;
-          }
           pl.fused = true;
           pl.smem_fused = smem_fused;
-          pl.fused_grid_cap = occ * pl.n_sm;  // persistent warps: as many CTAs as are resident at once
         } else {
           (void)cudaGetLastError();
         }
@@ -365,7 +365,12 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   S* c_g = (S*)(ws + w.c);
   S* d_g = (S*)(ws + w.d);
   S* G_g = (S*)(ws + w.G);
-  cudaError_t e = cudaMemsetAsync(ctl, 0, 256, st);
+  static_assert(256 + kRingSMs * sizeof(int) <= 1024, "slot masks must fit the control region");
+  if (w.ring && !(d->select & ALMPC_SELECT_NO_RING) && !debug_out) {
+    P.ring = (S*)(ws + w.ring);
+    P.ring_mask = (int*)(ws + w.ctl + 256);
+  }
+  cudaError_t e = cudaMemsetAsync(ctl, 0, 1024, st);
   if (e != cudaSuccess) return cuda_err(e, "cudaMemsetAsync(ctl)");
   e = cudaMemsetAsync(info_out, 0, ALMPC_INFO_INTS * sizeof(int32_t), st);
   if (e != cudaSuccess) return cuda_err(e, "cudaMemsetAsync(info)");
@@ -373,10 +378,6 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   int ls_grid;
   if (pl.fused) {
     ls_grid = (B + 2 * kWPP - 1) / (2 * kWPP);
-    if (ls_grid > pl.fused_grid_cap) ls_grid = pl.fused_grid_cap;
-    P.n_sm = pl.n_sm;
-    // start-up stagger per warp slot of an SM (cycles): spreads the factor / line-search phases of the resident warps
-    P.stagger = d->tune[0] > 0 ? d->tune[0] : (d->tune[0] < 0 ? 0 : kDefaultStagger);
   } else if (pl.lw.fn) {
     const int groups = (B + pl.lw.pw - 1) / pl.lw.pw;
     const int ctas = (groups + kWLS - 1) / kWLS;
@@ -396,11 +397,13 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   ProfEv pe[3 * ALMPC_MAX_AL_ITER * 8 + 1];
   int npe = 0;
   const bool prof = d->profile_ms && launches * 3 + 1 <= (int)(sizeof(pe) / sizeof(pe[0]));
+  int slot = 0;
   auto tic = [&](int kind) {
     if (!prof) return;
     cudaEventCreate(&pe[npe].a);
     cudaEventCreate(&pe[npe].b);
     pe[npe].kind = kind;
+    pe[npe].slot = slot;
     cudaEventRecord(pe[npe].a, st);
   };
   auto toc = [&]() {
@@ -409,6 +412,7 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
     ++npe;
   };
   for (int i = 0; i < launches; ++i) {
+    slot = i;
     tic(0);
     e = launch_k(kjac, jac_blocks, 128, 0, st, pdl, P, x0, xu, G_g, c_g, ctl);
     if (e != cudaSuccess) return cuda_err(e, "k_jacobian launch");
@@ -472,11 +476,13 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   toc();
   if (prof) {  // profiling mode synchronises (never used on a timed or captured path)
     cudaStreamSynchronize(st);
+    int executed = 0;  // Newton steps the solve realised: the launches of the later slots found MODE_DONE and did nothing
+    cudaMemcpy(&executed, info_out + ALMPC_INFO_TOTAL_NEWTON, sizeof(int), cudaMemcpyDeviceToHost);
     double acc[8] = {0};
     for (int i = 0; i < npe; ++i) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, pe[i].a, pe[i].b);
-      if (ms > 0.02f || pe[i].kind == 3) {  // skip the no-op launches after the solve finished
+      if (pe[i].slot < executed || pe[i].kind == 3) {
         acc[pe[i].kind] += ms;
         acc[4 + pe[i].kind] += 1;
       }

@@ -34,22 +34,36 @@ class NativeDynamics(torch.nn.Module):
 
     # ---- parameter block -------------------------------------------------------------------
     def param_block(self):
-        p = [0.0] * _lib.MAX_PARAMS
-        p[0] = self.dt
-        self._fill_params(p)
-        return p
+        """The functor's parameter block (csrc/almpc_models.cuh).  Memoised: the quadrotor family inverts its inertia
+        tensor and rounds a dozen values through fp32 tensors here, which costs more than a small-batch solve when
+        it is redone on every call.  The model parameters are constructor arguments; change them -> build a new
+        object (or call ``invalidate()``)."""
+        pb = self.__dict__.get("_param_block")
+        if pb is None:
+            p = [0.0] * _lib.MAX_PARAMS
+            p[0] = self.dt
+            self._fill_params(p)
+            pb = self.__dict__["_param_block"] = tuple(p)
+        return list(pb)
+
+    def invalidate(self):
+        self.__dict__.pop("_param_block", None)
+        self.__dict__.pop("_dyn_desc", None)
 
     def _fill_params(self, p):
         pass
 
     def _desc(self):
-        d = _lib.Desc()
-        d.dyn_id = self.dyn_id
-        d.T = 2
-        d.al_iter = 1
-        d.max_newton = 1
-        for i, v in enumerate(self.param_block()):
-            d.dyn_params[i] = v
+        d = self.__dict__.get("_dyn_desc")
+        if d is None:
+            d = _lib.Desc()
+            d.dyn_id = self.dyn_id
+            d.T = 2
+            d.al_iter = 1
+            d.max_newton = 1
+            for i, v in enumerate(self.param_block()):
+                d.dyn_params[i] = v
+            self.__dict__["_dyn_desc"] = d
         return d
 
     # ---- dx / dx_jac -----------------------------------------------------------------------
@@ -202,13 +216,32 @@ def _attr(obj, name, default=None):
         return default
 
 
+_RESOLVED = {}  # id(reference dynamics object) -> (weakref to it, NativeDynamics): resolve() runs on every MPC.forward
+
+
 def resolve(dx):
-    """Map a dynamics object (ours or the reference's) to a NativeDynamics descriptor, or raise."""
+    """Map a dynamics object (ours or the reference's) to a NativeDynamics descriptor, or raise.  The descriptor of
+    a reference object is built once (reading its parameter tensors synchronises with the device) and cached for
+    the lifetime of that object."""
     if isinstance(dx, NativeDynamics):
         return dx
     native = _attr(dx, "almpc_native")
     if isinstance(native, NativeDynamics):
         return native
+    hit = _RESOLVED.get(id(dx))
+    if hit is not None and hit[0]() is dx:
+        return hit[1]
+    native = _resolve_uncached(dx)
+    try:
+        import weakref
+
+        _RESOLVED[id(dx)] = (weakref.ref(dx, lambda _r, k=id(dx): _RESOLVED.pop(k, None)), native)
+    except TypeError:  # object without weak-reference support: resolve every time
+        pass
+    return native
+
+
+def _resolve_uncached(dx):
     cls = _attr(dx, "original_name") or type(dx).__name__
     dt = _attr(dx, "dt")
     if cls in ("RexQuadrotor_dynamics", "RexQuadrotor_dynamics_jac"):
@@ -232,6 +265,7 @@ def resolve(dx):
     if pkg_name.startswith("cartpole2l"):
         return Cartpole2LDynamics(dt=float(dt))
     raise _lib.AlmpcError(
-        f"no native CUDA functor registered for dynamics object {cls!r}; pass a deq_mpc_corl_b200.dynamics."
-        "NativeDynamics (generic-callable dynamics are not fused yet, and there is no CPU fallback)"
+        f"no native CUDA functor registered for dynamics object {cls!r}: pass a deq_mpc_corl_b200.dynamics."
+        "NativeDynamics for the fused kernels, or callable dx AND dx_jac for the generic-callable mode (torch evaluates "
+        "them on the GPU, the block-tridiagonal linear algebra runs in CUDA); there is no CPU fallback"
     )

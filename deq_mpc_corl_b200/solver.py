@@ -47,8 +47,6 @@ class SolveConfig:
                 cache.clear()
             d = cache[key] = self._fill_desc(B)
         d.select = _lib.env_select()
-        for i, v in enumerate(_lib.env_tune()):
-            d.tune[i] = v
         if self.obstacles is not None:
             d.n_obs = int(self.obstacles.shape[2])
             d.obs_radius = float(self.obs_radius)
@@ -123,11 +121,18 @@ def raw_forward(cfg: SolveConfig, x0, Qd, q, xu, lam, rho):
     )
     ws = torch.empty(lib.almpc_workspace_bytes(ctypes.byref(d)), dtype=torch.uint8, device=dev)
     if B > 0:
-        with torch.cuda.device(dev):
-            rc = getattr(lib, "almpc_forward_" + _lib.suffix(dt))(
-                ctypes.byref(d), _lib.ptr(x0), _lib.ptr(Qd), _lib.ptr(q), _lib.ptr(xu), _lib.ptr(lam), _lib.ptr(rho),
+        fn = getattr(lib, "almpc_forward_" + _lib.suffix(dt))
+        args = (ctypes.byref(d), _lib.ptr(x0), _lib.ptr(Qd), _lib.ptr(q), _lib.ptr(xu), _lib.ptr(lam), _lib.ptr(rho),
                 _lib.ptr(out["factor"]), _lib.ptr(out["x"]), _lib.ptr(out["u"]), _lib.ptr(out["dyn_res"]),
-                _lib.ptr(out["status"]), _lib.ptr(out["info"]), _lib.ptr(out["debug"]), _lib.ptr(ws), _lib.stream_ptr())
+                _lib.ptr(out["status"]), _lib.ptr(out["info"]), _lib.ptr(out["debug"]), _lib.ptr(ws))
+        if torch.cuda.current_device() == dev.index:  # the device guard costs a few us: only when it is needed
+            rc = fn(*args, _lib.stream_ptr())
+        else:
+            with torch.cuda.device(dev):
+                rc = fn(*args, _lib.stream_ptr())
+        if cfg.global_stop is not None and cfg.global_stop.error is not None:
+            err, cfg.global_stop.error = cfg.global_stop.error, None
+            raise _lib.AlmpcError(f"stop_reduce hook failed: {err!r}")
         _lib.check(rc, "almpc_forward")
     else:
         out["info"].zero_()
@@ -215,7 +220,12 @@ class ALSolve(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, Qd, q, x0, xu_init, lam, rho, cfg):
-        xu = xu_init.detach().clone().contiguous()
+        # the solver updates xu / lam / rho in place: work on copies unless the caller handed over a buffer it built
+        # for this call (MPC.forward does, `_owns_xu`)
+        if cfg.__dict__.pop("_owns_xu", False) and xu_init.is_contiguous() and not xu_init.requires_grad:
+            xu = xu_init
+        else:
+            xu = xu_init.detach().clone().contiguous()
         lam = lam.detach().clone().contiguous()
         rho = rho.detach().clone().contiguous()
         fwd = raw_forward if cfg.graph_cache is None or cfg.debug else cfg.graph_cache.forward

@@ -67,9 +67,10 @@ enum almpc_dyn_id {
 
 /* desc.select: kernel-selection switches for A/B measurements and differential tests (0 = the library's choice) */
 #define ALMPC_SELECT_FAC_SINGLE 1 /* row-per-lane factor kernel even where the half-warp-per-problem one applies */
-#define ALMPC_SELECT_NO_FUSE 2    /* factor and line search as separate kernels (no k_newton_pair) */
+#define ALMPC_SELECT_FUSE 2       /* factor + line search + steering in ONE kernel (k_newton_pair) where it applies */
 #define ALMPC_SELECT_LS_CTA 4     /* CTA line-search kernel even where the warp-synchronous one applies */
 #define ALMPC_SELECT_PDL 8        /* launch the step kernels with programmatic stream serialization */
+#define ALMPC_SELECT_NO_RING 16   /* every Newton step streams its block factor to `factor` (no L2-resident scratch ring) */
 
 /* Hook for the reference's batch-GLOBAL decisions under batch sharding (qpth/al_utils.py:486,552,560-564: the
  * Newton stop rule is a statistic of the WHOLE batch; qpth/AL_mpc.py:412: max(rho) over the batch).  Called on the
@@ -109,9 +110,6 @@ typedef struct almpc_desc {
   double* stop_stats;
   almpc_stop_reduce_fn stop_reduce;
   void* stop_reduce_user;
-  /* Tuning values for measurements (0 = the library's default).  tune[0]: start-up stagger of the persistent fused
-   * Newton-tail kernel in clock cycles per warp slot (-1 = none). */
-  int32_t tune[4];
 } almpc_desc;
 
 /* info_out layout (int32, device memory, ALMPC_INFO_INTS entries) */

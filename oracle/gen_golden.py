@@ -232,7 +232,7 @@ def run_scenario(name, model_name, T, B, dtype_name, calls, seed, stream_after=N
         twin = run_scenario(name, model_name, T, B, "f64", calls, seed, stream_after, rho_init_max, obstacle_radius,
                             state_estimator, save=False)
         for ci in range(len(calls)):
-            for key in ("xu64", "lam_out", "q_grad", "Q_grad"):
+            for key in ("xu64", "lam_out", "q_grad", "Q_grad", "x", "u"):
                 out[f"c{ci}_ref64_{key}"] = twin[f"c{ci}_{key}"]
             out[f"c{ci}_ref64_nsteps"] = twin[f"c{ci}_nsteps"]
     meta = dict(model=model_name, dtype=dtype_name, torch=torch.__version__)

@@ -40,9 +40,13 @@ def import_reference(with_policies=False):
     for p in (root, os.path.join(root, "deqmpc")):
         if p not in sys.path:
             sys.path.insert(0, p)
+    import contextlib
+    import io
     import warnings
 
-    with warnings.catch_warnings():
+    # the reference prints at import time ("cvxpy not installed, skipping test"): keep stdout clean for callers that
+    # print machine-readable output (bench.py's one JSON line)
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
         warnings.simplefilter("ignore")
         from qpth import AL_mpc, al_utils
         import rex_quadrotor
