@@ -118,6 +118,9 @@ def load():
         f = getattr(lib, "almpc_blocktri_" + sfx)
         f.argtypes = [i32] * 5 + [vp] * 8
         f.restype = ctypes.c_int
+        f = getattr(lib, "almpc_kkt_solve_" + sfx)
+        f.argtypes = [i32] * 4 + [vp] * 5 + [dbl, i32] + [vp] * 10
+        f.restype = ctypes.c_int
     _lib = lib
     return lib
 
@@ -127,7 +130,7 @@ EXPORTS = [
     "almpc_forward_f64", "almpc_forward_f32", "almpc_backward_f64", "almpc_backward_f32",
     "almpc_dynamics_f64", "almpc_dynamics_f32", "almpc_fma_peak_f64", "almpc_fma_peak_f32",
     "almpc_tracking_cost_f64", "almpc_tracking_cost_f32", "almpc_tracking_cost_bwd_f64", "almpc_tracking_cost_bwd_f32",
-    "almpc_blocktri_f64", "almpc_blocktri_f32",
+    "almpc_blocktri_f64", "almpc_blocktri_f32", "almpc_kkt_solve_f64", "almpc_kkt_solve_f32",
     "almpc_last_error", "almpc_version",
 ]
 

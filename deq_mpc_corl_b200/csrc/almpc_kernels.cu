@@ -31,6 +31,7 @@
 #include "almpc_factor.cuh"
 #include "almpc_linesearch.cuh"
 #include "almpc_fused.cuh"
+#include "almpc_kkt.cuh"
 
 #include <mutex>
 
@@ -623,6 +624,31 @@ static int blocktri(int B, int T, int nx, int nu, int do_factor, const S* G, con
 }
 
 template <typename S>
+static int kkt_solve(int B, int nz, int nineq, int neq, const S* Q, const S* G, const S* A, const S* s, const S* z, double eps,
+                     int n_refine, const S* rx, const S* rs, const S* rz, const S* ry, S* dx, S* ds, S* dz, S* dy, int32_t* status,
+                     void* stream) {
+  if (B < 0 || nz < 1 || nineq < 0 || neq < 0 || n_refine < 0)
+    return set_err(-3, "kkt_solve: need nz >= 1, nineq >= 0, neq >= 0, n_refine >= 0");
+  if (B == 0) return 0;
+  if (!Q || !rx || !dx || (nineq && (!G || !s || !z || !rs || !rz || !ds || !dz)) || (neq && (!A || !ry || !dy)))
+    return set_err(-10, "null buffer");
+  const size_t smem = kkt_smem_elems(nz, nineq, neq) * sizeof(S);
+  int dev = 0, optin = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_err(e, "cudaGetDevice");
+  e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return cuda_err(e, "cudaDeviceGetAttribute");
+  if (smem > (size_t)optin)
+    return set_err(-11, "kkt_solve: (nz + neq)^2 scalars do not fit the shared memory of one CTA");
+  auto kern = k_kkt_solve<S>;
+  e = allow_max_smem(kern, optin);
+  if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(kkt_solve)");
+  kern<<<(unsigned)B, kKktThreads, smem, (cudaStream_t)stream>>>(B, nz, nineq, neq, Q, G, A, s, z, (S)eps, n_refine, rx, rs, rz, ry,
+                                                              dx, ds, dz, dy, status);
+  return cuda_err(cudaGetLastError(), "almpc_kkt_solve launch");
+}
+
+template <typename S>
 static int fma_peak(int blocks, int iters, S* sink, double* flops, void* stream) {
   if (blocks <= 0 || iters <= 0 || !sink) return set_err(-1, "bad fma_peak arguments");
   k_fma_peak<S><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
@@ -780,6 +806,20 @@ int almpc_tracking_cost_bwd_f32(int32_t B, int32_t T, int32_t nx, int32_t nu, co
                                 float* grad_x_ref, float* grad_u_ref, float* grad_scale, void* stream) {
   return tracking_cost_bwd<float>(B, T, nx, nu, Q0, x_ref, u_ref, scale, grad_Q, grad_q, grad_x_ref, grad_u_ref,
                                   grad_scale, stream);
+}
+#endif
+#if ALMPC_BUILD_F64
+int almpc_kkt_solve_f64(int32_t B, int32_t nz, int32_t nineq, int32_t neq, const double* Q, const double* G, const double* A,
+                        const double* s, const double* z, double eps, int32_t n_refine, const double* rx, const double* rs,
+                        const double* rz, const double* ry, double* dx, double* ds, double* dz, double* dy, int32_t* status, void* stream) {
+  return kkt_solve<double>(B, nz, nineq, neq, Q, G, A, s, z, eps, n_refine, rx, rs, rz, ry, dx, ds, dz, dy, status, stream);
+}
+#endif
+#if ALMPC_BUILD_F32
+int almpc_kkt_solve_f32(int32_t B, int32_t nz, int32_t nineq, int32_t neq, const float* Q, const float* G, const float* A,
+                        const float* s, const float* z, double eps, int32_t n_refine, const float* rx, const float* rs,
+                        const float* rz, const float* ry, float* dx, float* ds, float* dz, float* dy, int32_t* status, void* stream) {
+  return kkt_solve<float>(B, nz, nineq, neq, Q, G, A, s, z, eps, n_refine, rx, rs, rz, ry, dx, ds, dz, dy, status, stream);
 }
 #endif
 #if ALMPC_BUILD_F64

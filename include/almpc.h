@@ -190,6 +190,25 @@ int almpc_blocktri_f32(int32_t B, int32_t T, int32_t nx, int32_t nu, int32_t do_
                        const float* diagD, const float* rho, float* factor, const float* rhs, float* sol,
                        int32_t* status, void* stream);
 
+/* Interior-point path: the KKT solve of the reference's primal-dual interior-point QP solver,
+ * `solve_kkt` of qpth/solvers/pdipm/batch_LU.py:212-244 (called from its forward loop :70,155,175 and from
+ * DenseQPFunction.backward, qpth/qp.py:249-253).  Unknowns (x[nz], s[nineq], z[nineq], y[neq]) of
+ *     Ktilde l = -(rx, rs, rz, ry),   K = [Q 0 G^T A^T; 0 D(z) D(s) 0; G I 0 0; A 0 0 0],
+ *     Ktilde = K + eps diag(+1 on the x and s rows, -1 on the z and y rows)        (batch_LU.py:42,58-60,113-116)
+ * followed by n_refine steps of iterative refinement against K (the reference takes one).  The slack / multiplier blocks are
+ * eliminated in closed form and the quasi-definite reduced system of size nz + neq is factored as L D L^T in shared
+ * memory by one CTA per problem (instead of a pivoted LU of the dense (nz + 2 nineq + neq)^2 matrix).  The backward pass
+ * (reference: an LU of K itself) uses eps = 1e-7 with three refinement steps: eliminating the slack block of the
+ * unregularised K would put z_i / s_i ~ 1e12 of the active rows into the reduced matrix.  Q [B][nz][nz] symmetric, G [B][nineq][nz], A [B][neq][nz], s, z [B][nineq];
+ * (nz + neq)^2 scalars must fit the opt-in shared memory (error -11 otherwise).  status[B] (may be NULL): 1 = all
+ * pivots finite and non-zero. */
+int almpc_kkt_solve_f64(int32_t B, int32_t nz, int32_t nineq, int32_t neq, const double* Q, const double* G, const double* A,
+                        const double* s, const double* z, double eps, int32_t n_refine, const double* rx, const double* rs,
+                        const double* rz, const double* ry, double* dx, double* ds, double* dz, double* dy, int32_t* status, void* stream);
+int almpc_kkt_solve_f32(int32_t B, int32_t nz, int32_t nineq, int32_t neq, const float* Q, const float* G, const float* A,
+                        const float* s, const float* z, double eps, int32_t n_refine, const float* rx, const float* rs,
+                        const float* rz, const float* ry, float* dx, float* ds, float* dz, float* dy, int32_t* status, void* stream);
+
 /* FMA-pipe micro-benchmark used by bench.py to measure the FP64 / FP32 roofline denominators:
  * launches `blocks` x 256 threads, each doing `iters` x 8 independent FMAs; returns via *flops the
  * number of floating-point operations performed (2 per FMA). */

@@ -304,6 +304,120 @@ def run_tracking_scenario(name, model_name, T, B, dtype_name, calls, seed, strea
           [bool(out[f'c{c}_status']) for c in range(len(calls))])
 
 
+def ip_problem(kind, seed, B, dtype):
+    """Inputs of an interior-point golden.  kind = "random": a strictly convex QP with random inequality and equality
+    rows and the linear residual A x - b.  kind = "mpc_quad": the horizon-5 quadrotor QP the reference's IP path
+    builds (block-diagonal cost, control-bound rows +-I, linearised dynamics rows, qp_wrapper.py:612-653 layout
+    x_t | u_t per stage) with the NON-linear dynamics residual of qp_wrapper.py:316-342 as `dyn_res`."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    rnd = lambda *sh: torch.randn(*sh, generator=g, dtype=torch.float64)
+    if kind == "random":
+        nz, nineq, neq = 10, 6, 3
+        L = rnd(B, nz, nz)
+        Q = L @ L.transpose(1, 2) + 0.5 * torch.eye(nz, dtype=torch.float64)
+        p, G, A = rnd(B, nz), rnd(B, nineq, nz), rnd(B, neq, nz)
+        xs = rnd(B, nz)
+        h = (G @ xs.unsqueeze(-1)).squeeze(-1) + 0.1 + torch.rand(B, nineq, generator=g, dtype=torch.float64)
+        b = (A @ xs.unsqueeze(-1)).squeeze(-1)
+        out = dict(Q=Q, p=p, G=G, h=h, A=A, b=b)
+        return {k: v.to(dtype) for k, v in out.items()}, None
+    from oracle import problem_gen, ref_import
+
+    ref = ref_import.import_reference()
+    model, T = "rex_quadrotor", 5
+    spec = problem_gen.MODEL_SPECS[model]
+    nx, nu = spec["nx"], spec["nu"]
+    n = nx + nu
+    inp = problem_gen.make_inputs(model, T, B, seed)
+    env = ref.rex_quadrotor.RexQuadrotor(bsz=B)
+    # control references: hover-ish, above the upper bound (18.3), below the lower bound (11.5), hover-ish -> the
+    # solution has active upper AND lower bound rows
+    x_ref, u_ref = inp["x_ref"].double(), inp["u_ref"].double() + torch.tensor([15.0, 18.6, 11.2, 15.0], dtype=torch.float64)
+    xu_ref = torch.cat([x_ref, u_ref], -1)
+    Qd = torch.tensor(spec["Q"] + [1e-2] * nu, dtype=torch.float64)
+    Q = torch.diag(Qd.repeat(T)).expand(B, T * n, T * n).contiguous()
+    p = -(Qd * xu_ref).reshape(B, T * n)
+    # control bounds: u <= u_hi, -u <= -u_lo
+    G = torch.zeros(B, 2 * T * nu, T * n, dtype=torch.float64)
+    h = torch.zeros(B, 2 * T * nu, dtype=torch.float64)
+    for t in range(T):
+        for j in range(nu):
+            G[:, t * nu + j, t * n + nx + j] = 1.0
+            G[:, T * nu + t * nu + j, t * n + nx + j] = -1.0
+            h[:, t * nu + j] = spec["u_upper"][j]
+            h[:, T * nu + t * nu + j] = -spec["u_lower"][j]
+    # linearised dynamics rows F_t z_t - x_{t+1} = -f_t, then x_0 = x0
+    xs, us = x_ref[:, :-1].reshape(-1, nx), u_ref[:, :-1].reshape(-1, nu)
+    xn, (Jx, Ju) = env.dynamics_derivatives(xs.clone().requires_grad_(True), us.clone().requires_grad_(True))
+    xn, Jx, Ju = xn.detach(), Jx.detach(), Ju.detach()
+    F = torch.cat([Jx, Ju], -1).reshape(B, T - 1, nx, n).double()
+    f = (xn.double() - (Jx.double() @ xs.unsqueeze(-1)).squeeze(-1) - (Ju.double() @ us.unsqueeze(-1)).squeeze(-1)).reshape(B, T - 1, nx)
+    A = torch.zeros(B, T * nx, T * n, dtype=torch.float64)
+    b = torch.zeros(B, T * nx, dtype=torch.float64)
+    for t in range(T - 1):
+        A[:, t * nx:(t + 1) * nx, t * n:(t + 1) * n] = F[:, t]
+        A[:, t * nx:(t + 1) * nx, (t + 1) * n:(t + 1) * n + nx] = -torch.eye(nx, dtype=torch.float64)
+        b[:, t * nx:(t + 1) * nx] = -f[:, t]
+    A[:, (T - 1) * nx:, :nx] = torch.eye(nx, dtype=torch.float64)
+    b[:, (T - 1) * nx:] = inp["x0"].double()
+    x0 = inp["x0"].double()
+
+    def dyn_res(z):
+        zz = z.reshape(B, T, n)
+        x, u = zz[:, :, :nx], zz[:, :, nx:]
+        x_next = env.dynamics(x[:, :-1].reshape(-1, nx), u[:, :-1].reshape(-1, nu)).reshape(B, T - 1, nx)
+        return torch.cat(((x_next - x[:, 1:]).reshape(B, -1), x[:, 0] - x0), 1)
+
+    out = dict(Q=Q, p=p, G=G, h=h, A=A, b=b, x0=x0)
+    return {k: v.to(dtype) for k, v in out.items()}, dyn_res
+
+
+def run_ip_scenario(name, kind, B, dtype_name, seed):
+    """Golden of the reference's interior-point path: `qpth.qp.DenseQPFunction` (qp.py:187-270 -> pdipm/batch_LU.py)
+    forward + backward, with the per-iteration residual trace of its loop (hook on `solve_kkt`, no reference edits)."""
+    import torch
+    from oracle import ref_import
+
+    ref = ref_import.import_reference(with_policies=True)
+    dtype = torch.float64 if dtype_name == "f64" else torch.float32
+    prob, dyn_res = ip_problem(kind, seed, B, dtype)
+    Q, p, G, h, A, b = (prob[k].clone().requires_grad_(True) for k in ("Q", "p", "G", "h", "A", "b"))
+    if dyn_res is None:
+        dyn_res = lambda x: (A.detach() @ x.unsqueeze(-1)).squeeze(-1) - b.detach()
+    blu = ref.qp.pdipm_b_LU
+    n_solves = [0]
+    orig = blu.solve_kkt
+
+    def counting(*a, **k):
+        n_solves[0] += 1
+        return orig(*a, **k)
+
+    blu.solve_kkt = counting
+    try:
+        zhat = ref.qp.DenseQPFunction()(Q, p, G, h, A, b, dyn_res)
+    finally:
+        blu.solve_kkt = orig
+    g = torch.Generator().manual_seed(seed + 3)
+    dl = torch.randn(zhat.shape, generator=g, dtype=torch.float64).to(dtype)
+    grads = torch.autograd.grad(zhat, (Q, p, G, h, A, b), dl)
+    out = dict(prob)
+    out.update(zhat=zhat.detach(), dl_dzhat=dl, dQ=grads[0], dp=grads[1], dG=grads[2], dh=grads[3], dA=grads[4], db=grads[5],
+               n_solve_kkt=np.int64(n_solves[0]), B=np.int64(B), seed=np.int64(seed))
+    npz = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
+    npz["meta_kind"], npz["meta_dtype"], npz["meta_torch"] = np.array(kind), np.array(dtype_name), np.array(torch.__version__)
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **npz)
+    print(f"{name}: wrote {path} ({os.path.getsize(path)/1024:.0f} KB); solve_kkt calls in forward: {n_solves[0]}")
+
+
+IP_SCENARIOS = {
+    # name: (kind, B, dtype, seed)
+    "ip_random_f64": ("random", 6, "f64", 1083),
+    "ip_mpc_quad_f64": ("mpc_quad", 3, "f64", 1093),
+}
+
 TRACKING_SCENARIOS = {
     # name: (model, T, B, dtype, [(al_iters, q_scaling?)...], seed, stream_after)
     "tracking_quad_T5_f64": ("rex_quadrotor", 5, 6, "f64", [(2, False), (2, True), (2, False), (2, False), (2, True), (2, False)], 1073, 3),
@@ -327,7 +441,7 @@ SCENARIOS = {
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("names", nargs="*", default=list(SCENARIOS) + list(TRACKING_SCENARIOS))
+    ap.add_argument("names", nargs="*", default=list(SCENARIOS) + list(TRACKING_SCENARIOS) + list(IP_SCENARIOS))
     args = ap.parse_args()
     if len(args.names) > 1:
         # one fresh interpreter per scenario: TorchScript's profiling executor re-specialises the reference's
@@ -338,7 +452,9 @@ if __name__ == "__main__":
             subprocess.check_call([sys.executable, os.path.abspath(__file__), nm])
         sys.exit(0)
     for nm in args.names:
-        if nm in TRACKING_SCENARIOS:
+        if nm in IP_SCENARIOS:
+            run_ip_scenario(nm, *IP_SCENARIOS[nm])
+        elif nm in TRACKING_SCENARIOS:
             run_tracking_scenario(nm, *TRACKING_SCENARIOS[nm])
         else:
             run_scenario(nm, *SCENARIOS[nm])
