@@ -163,7 +163,8 @@ def cpu_reference_run(model, T, B, dtype, seed, stream_calls=0):
     from oracle import ref_import
 
     cores = os.cpu_count()
-    torch.set_num_threads(cores)
+    if torch.get_num_threads() != cores:  # (torchrun exports OMP_NUM_THREADS=1)
+        torch.set_num_threads(cores)
     if ref_import.available():
         from oracle import ref_runner
 
@@ -512,6 +513,117 @@ def streaming_entry(model, T, B, dtype, dev):
             "forward_calls": calls, "al_iterations_per_streaming_call": pattern}
 
 
+def ip_entry(B, dev, cpu_sample, no_cpu):
+    """the interior-point path on the horizon-5 quadrotor QP (nz = 80, 40 bound rows, 60 equality
+    rows, NON-linear dynamics residual): `qp.DenseQPFunction` forward + backward, every solve_kkt one launch of
+    almpc_kkt_solve; CPU leg = the unmodified reference's DenseQPFunction (dense 220 x 220 pivoted LU per solve)."""
+    from deq_mpc_corl_b200.dynamics import make as make_dyn
+    from deq_mpc_corl_b200.qp import DenseQPFunction
+
+    T, nx, nu = 5, 12, 4
+    n = nx + nu
+    inp = make_inputs("rex_quadrotor", T, B, 1003)
+    dyn = make_dyn("rex_quadrotor", dt=MODEL_SPECS["rex_quadrotor"]["dt"])
+    f64 = dict(dtype=torch.float64, device=dev)
+    x_ref = inp["x_ref"].double().to(dev)
+    u_ref = torch.tensor([15.0, 18.6, 11.2, 15.0], **f64).expand(B, T, nu)
+    xu_ref = torch.cat([x_ref, u_ref], -1)
+    Qd = torch.tensor(MODEL_SPECS["rex_quadrotor"]["Q"] + [1e-2] * nu, **f64)
+    Q = torch.diag(Qd.repeat(T)).expand(B, T * n, T * n).contiguous()
+    p = -(Qd * xu_ref).reshape(B, T * n)
+    G = torch.zeros(B, 2 * T * nu, T * n, **f64)
+    h = torch.zeros(B, 2 * T * nu, **f64)
+    for t in range(T):
+        for j in range(nu):
+            G[:, t * nu + j, t * n + nx + j] = 1.0
+            G[:, T * nu + t * nu + j, t * n + nx + j] = -1.0
+            h[:, t * nu + j] = MODEL_SPECS["rex_quadrotor"]["u_upper"][j]
+            h[:, T * nu + t * nu + j] = -MODEL_SPECS["rex_quadrotor"]["u_lower"][j]
+    xs, us = x_ref[:, :-1].reshape(-1, nx).contiguous(), u_ref[:, :-1].reshape(-1, nu).contiguous()
+    xn, (Jx, Ju) = dyn.jacobian(xs, us)
+    F = torch.cat([Jx, Ju], -1).reshape(B, T - 1, nx, n)
+    f = (xn - (Jx @ xs.unsqueeze(-1)).squeeze(-1) - (Ju @ us.unsqueeze(-1)).squeeze(-1)).reshape(B, T - 1, nx)
+    A = torch.zeros(B, T * nx, T * n, **f64)
+    b = torch.zeros(B, T * nx, **f64)
+    eye = torch.eye(nx, **f64)
+    for t in range(T - 1):
+        A[:, t * nx:(t + 1) * nx, t * n:(t + 1) * n] = F[:, t]
+        A[:, t * nx:(t + 1) * nx, (t + 1) * n:(t + 1) * n + nx] = -eye
+        b[:, t * nx:(t + 1) * nx] = -f[:, t]
+    x0 = inp["x0"].double().to(dev)
+    A[:, (T - 1) * nx:, :nx] = eye
+    b[:, (T - 1) * nx:] = x0
+
+    def make_res(step, x0_, Bc):
+        def dyn_res(z):
+            zz = z.reshape(Bc, T, n)
+            x, u = zz[:, :, :nx], zz[:, :, nx:]
+            xnext = step(x[:, :-1].reshape(-1, nx).contiguous(), u[:, :-1].reshape(-1, nu).contiguous()).reshape(Bc, T - 1, nx)
+            return torch.cat(((xnext - x[:, 1:]).reshape(Bc, -1), x[:, 0] - x0_), 1)
+        return dyn_res
+
+    gsrc = torch.randn(B, T * n, generator=torch.Generator().manual_seed(3), dtype=torch.float64).to(dev)
+
+    def run():
+        pl = p.clone().requires_grad_(True)
+        z = DenseQPFunction()(Q, pl, G, h, A, b, make_res(dyn, x0, B))
+        torch.autograd.grad(z, pl, gsrc)
+        return z
+
+    run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out = {"workload": f"interior-point path, rex_quadrotor horizon-5 QP (nz 80, 40 bound rows, 60 equality rows, non-linear "
+                       f"dyn_res), B={B}, fp64: DenseQPFunction forward (<= 20 predictor-corrector iterations, 2 KKT solves "
+                       "each) + backward", "value": B / (ms * 1e-3), "unit": "QP solves/s", "ms": ms}
+    if not no_cpu:
+        # The CPU leg runs in a FRESH interpreter under a timeout: torch's batched CPU lu_factor of the reference's
+        # dense 220 x 220 KKT matrices was observed to stall for minutes when called in a process that already holds a
+        # CUDA context and 16 intra-op threads (GPU box, this round); alone it takes ~2 s.
+        try:
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--ip-cpu-sample", str(cpu_sample)],
+                                 capture_output=True, text=True, timeout=240, cwd=ROOT)
+            line = [l for l in res.stdout.splitlines() if l.startswith("{")]
+            out["cpu_baseline"] = json.loads(line[-1]) if line else {"unavailable": (res.stderr or "no output")[-300:]}
+        except subprocess.TimeoutExpired:
+            out["cpu_baseline"] = {"unavailable": "the reference's DenseQPFunction did not finish within 240 s on this host"}
+    return out
+
+
+def ip_cpu_sample(S):
+    """Child-process leg of ip_entry: the unmodified reference's DenseQPFunction forward + backward on S quadrotor
+    horizon-5 QPs (same family as the GPU leg, built by oracle/gen_golden.py::ip_problem from the reference's own
+    dynamics modules).  Prints one JSON object."""
+    from oracle import ref_import
+    from oracle.gen_golden import ip_problem
+
+    if not ref_import.available():
+        print(json.dumps({"unavailable": "reference copy not staged"}))
+        return
+    ref = ref_import.import_reference(with_policies=True)
+    # NOT torch.set_num_threads(): in this torch build (2.11.0+cu128, oneMKL) any call of it makes the batched CPU
+    # lu_factor the reference relies on fail ("Parameter 6 was incorrect on entry to DLASWP") or hang; the default
+    # already is one intra-op thread per core
+    cores = torch.get_num_threads()
+    prob, dyn_res = ip_problem("mpc_quad", 1003, S, torch.float64)
+    pc = prob["p"].clone().requires_grad_(True)
+    best = None
+    for _ in range(2):  # first call warms the TorchScript dynamics
+        t0 = time.perf_counter()
+        z = ref.qp.DenseQPFunction()(prob["Q"], pc, prob["G"], prob["h"], prob["A"], prob["b"], dyn_res)
+        torch.autograd.grad(z, pc, torch.ones_like(z))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    print(json.dumps({"value": S / best, "unit": "QP solves/s", "cores": cores, "kind": "reference",
+                      "sample": f"{S} QPs of the same family, unmodified qpth.qp.DenseQPFunction forward + backward "
+                                f"(dense 220 x 220 pivoted LU per solve_kkt), {best:.1f} s, fresh process"}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -526,7 +638,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-suite", action="store_true", help="skip the other BASELINE configurations")
     ap.add_argument("--no-weak", action="store_true", help="N>1: skip the extra weak-scaling measurement")
+    ap.add_argument("--ip-cpu-sample", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.ip_cpu_sample:
+        ip_cpu_sample(args.ip_cpu_sample)
+        return
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.cpu_sample is None:
         args.cpu_sample = 4096 if args.impl == "b200" else 2048
@@ -753,6 +869,7 @@ def main():
         }
         if weak:
             line["weak"] = weak
+        print(f"[bench] headline done: {value:.4g} solves/s", file=sys.stderr, flush=True)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_entry(model, T, args.cpu_sample, dtype, GB)
         if world == 1 and not args.no_suite:
@@ -760,13 +877,22 @@ def main():
             torch.cuda.empty_cache()
             nc = args.no_cpu_baseline
             f32_peak = fma_peak(torch.float32, dev)
-            line["suite"] = {
-                "quadrotor_64k_f32": suite_entry("rex_quadrotor", 5, 65536, torch.float32, dev, 5, 1024, f32_peak, hbm_peak, known, nc),
-                "quadrotor_64k_deq_chain6": deq_chain_entry("rex_quadrotor", 5, 65536, torch.float64, dev, 6),
-                "pendulum_b200": suite_entry("pendulum", 5, 200, torch.float64, dev, 50, 200, peak_tflops, hbm_peak, known, nc),
-                "cartpole_4k_streaming": streaming_entry("cartpole1l", 5, 4096, torch.float64, dev),
-                "flying_cartpole_T10_16k": suite_entry("flying_cartpole", 10, 16384, torch.float64, dev, 5, 512, peak_tflops, hbm_peak, known, nc),
+            entries = {
+                "quadrotor_64k_f32": lambda: suite_entry("rex_quadrotor", 5, 65536, torch.float32, dev, 5, 1024, f32_peak, hbm_peak, known, nc),
+                "quadrotor_64k_deq_chain6": lambda: deq_chain_entry("rex_quadrotor", 5, 65536, torch.float64, dev, 6),
+                "pendulum_b200": lambda: suite_entry("pendulum", 5, 200, torch.float64, dev, 50, 200, peak_tflops, hbm_peak, known, nc),
+                "cartpole_4k_streaming": lambda: streaming_entry("cartpole1l", 5, 4096, torch.float64, dev),
+                "flying_cartpole_T10_16k": lambda: suite_entry("flying_cartpole", 10, 16384, torch.float64, dev, 5, 512, peak_tflops, hbm_peak, known, nc),
+                "ip_dense_qp_quadrotor_4k": lambda: ip_entry(4096, dev, 64, nc),
             }
+            line["suite"] = {}
+            for name, fn in entries.items():  # one failing side configuration must not cost the headline line
+                t0 = time.perf_counter()
+                try:
+                    line["suite"][name] = fn()
+                except Exception as exc:  # noqa: BLE001
+                    line["suite"][name] = {"error": repr(exc)[:300]}
+                print(f"[bench] suite {name}: {time.perf_counter() - t0:.1f} s", file=sys.stderr, flush=True)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -149,6 +149,8 @@ class GraphCache:
     itself neither allocates nor synchronises, which is what makes the capture legal
     (tests/test_gpu_parity.py::test_forward_backward_are_cuda_graph_capturable)."""
 
+    MAX_ENTRIES = 8  # every entry pins static inputs + a factor buffer of B * factor_elems scalars
+
     def __init__(self):
         self.entries = {}
 
@@ -181,7 +183,11 @@ class GraphCache:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 out = raw_forward(scfg, *(static[k] for k in names))
+            while len(self.entries) >= self.MAX_ENTRIES:  # least recently used first (dicts keep insertion order)
+                self.entries.pop(next(iter(self.entries)))
             ent = self.entries[key] = dict(static=static, cfg=scfg, graph=graph, out=out)
+        else:
+            self.entries[key] = self.entries.pop(key)  # mark as most recently used
         for k in names:
             ent["static"][k].copy_(live[k])
         if cfg.obstacles is not None:

@@ -90,7 +90,8 @@ def run(model, T, B, dtype, seed, chunk=4096, al_iter=2, threads=None, stream_ca
     """-> dict(seconds, solves_per_s, newton_steps (first chunk), cores)."""
     ref = ref_import.import_reference()
     threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
+    if torch.get_num_threads() != threads:
+        torch.set_num_threads(threads)
     inp = make_inputs(model, T, B, seed)
     t0 = time.perf_counter()
     steps = None
