@@ -110,6 +110,7 @@ static LsGeom ls_geom(int B, int T) {
 struct WsPlan {
   size_t ctl, partials, merit, rentry, status, c, d, G, ring, total;
 };
+constexpr int kPdlMaxBatch = 16384;   // batches up to this size launch their step kernels with PDL
 constexpr int kRingMinBatch = 8192;  // below this a whole batch of factors sits in L2 anyway
 static WsPlan ws_plan(int B, int T, int nx, int nu, size_t es) {
   const size_t nn = (size_t)nx + nu;
@@ -394,7 +395,11 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   const int nb = (B + pl.fac_per_cta - 1) / pl.fac_per_cta;
   const unsigned jac_blocks = (unsigned)(((long)B * (T - 1) * (NN - M::NTRIV) + 127) / 128);
   const int launches = d->al_iter * d->max_newton;
-  const bool pdl = !d->profile_ms && (d->select & ALMPC_SELECT_PDL);  // measured: no gain on B200, off by default
+  // Programmatic dependent launch (the next kernel's CTAs are scheduled while the previous kernel drains; every kernel
+  // starts with griddepcontrol.wait).  Measured on B200, quadrotor fp64 forward: 64K problems no gain, 16K -1.6 %,
+  // 8K -3.9 % (the drain / ramp-up of 24 dependent launches is a visible share of a 1.8 ms solve): on for small
+  // batches, selectable otherwise.
+  const bool pdl = !d->profile_ms && ((d->select & ALMPC_SELECT_PDL) || (B <= kPdlMaxBatch && !(d->select & ALMPC_SELECT_NO_PDL)));
   ProfEv pe[3 * ALMPC_MAX_AL_ITER * 8 + 1];
   int npe = 0;
   const bool prof = d->profile_ms && launches * 3 + 1 <= (int)(sizeof(pe) / sizeof(pe[0]));

@@ -952,3 +952,45 @@ def test_fp32_high_penalty_flags_instead_of_failing():
         assert ((st & _lib.STATUS_FINITE) == _lib.STATUS_FINITE).all()
         flagged = int(((st & _lib.STATUS_CHOL_OK) == 0).sum())
     assert flagged > 0  # at rho = 1e6..1e7 fp32 pivots do go non-positive for some problems
+
+
+def test_nan_propagation_and_dual_shape_check():
+    """Round-1 advisor items.  (1) A NaN that no dynamics row sees (last-stage control) must reach ||c+|| like
+    torch.clamp(min=0) propagates it (AL_mpc.py:317, al_utils.py:419), not vanish in max(x, 0).  (2) A NaN in the
+    UPSTREAM gradient propagates to that problem's q_grad (the reference's cholesky_solve would) instead of turning
+    into an exact zero; the other problems are untouched.  (3) `lamda_prev` of the wrong shape raises instead of
+    silently restarting the duals from zero."""
+    model, T, B = "rex_quadrotor", 5, 12
+    spec = MODEL_SPECS[model]
+    inp = make_inputs(model, T, B, 31)
+    Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"])
+    dyn = make_dyn(model)
+
+    def solve(u_ref, gx_mod=None):
+        ctrl = MPC(12, 4, T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B)
+        ctrl.reinitialize(inp["x_ref"].to(DEV))
+        ctrl.x_init, ctrl.u_init = inp["x_ref"].to(DEV), u_ref.to(DEV)
+        ql = q.to(DEV).requires_grad_(True)
+        x, u, _ = ctrl(inp["x0"].to(DEV), QuadCost(Qd.to(DEV), ql, None), dyn, dyn)
+        gx, gu = torch.ones_like(x), torch.ones_like(u)
+        if gx_mod is not None:
+            gx_mod(gx)
+        qg, = torch.autograd.grad((x, u), ql, (gx, gu))
+        return ctrl, x, u, qg
+
+    # (1)
+    u_nan = inp["u_ref"].clone()
+    u_nan[0, -1, 2] = float("nan")
+    ctrl, x, u, _ = solve(u_nan)
+    assert torch.isnan(ctrl.dyn_res_prev[0]) and torch.isfinite(ctrl.dyn_res_prev[1:]).all()
+    assert torch.isfinite(x[1:]).all() and torch.isfinite(u[1:]).all()
+    # (2)
+    def poison(gx):
+        gx[3, 2, 5] = float("nan")
+    ctrl, x, u, qg = solve(inp["u_ref"], poison)
+    assert (ctrl.last_status == 3).all()
+    assert torch.isnan(qg[3]).any() and torch.isfinite(qg[:3]).all() and torch.isfinite(qg[4:]).all()
+    # (3)
+    ctrl.lamda_prev = torch.zeros(B + 1, ctrl.neq + ctrl.nineq, dtype=torch.float64, device=DEV)
+    with pytest.raises(_lib.AlmpcError, match="lamda_prev"):
+        ctrl(inp["x0"].to(DEV), QuadCost(Qd.to(DEV), q.to(DEV), None), dyn, dyn)
