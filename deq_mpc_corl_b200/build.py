@@ -62,10 +62,12 @@ def build(force=False, verbose=False):
     if verbose:
         for _, err in results:
             print(err)
-    link = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + [o for o, _ in results]
+    tmp_out = out + ".tmp"  # link next to the target, then rename: a reader never sees a half-written library
+    link = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp_out] + [o for o, _ in results]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + res.stdout + res.stderr)
+    os.replace(tmp_out, out)
     for o, _ in results:  # objects are not needed once linked (keeps the gpurun snapshot small)
         os.remove(o)
     return out

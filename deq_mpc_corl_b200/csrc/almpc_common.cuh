@@ -29,6 +29,9 @@
 #ifndef ALMPC_NO_CP16
 #define ALMPC_NO_CP16 0
 #endif
+#ifndef ALMPC_F32_DMMA
+#define ALMPC_F32_DMMA 0  // 1: the fp32 solver assembles its Hessian blocks on the FP64 tensor-core path too (experiment)
+#endif
 #ifndef ALMPC_LS_MINB
 #define ALMPC_LS_MINB 4  // CTAs/SM the warp line search is compiled for
 #endif

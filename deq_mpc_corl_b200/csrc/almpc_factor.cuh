@@ -89,7 +89,7 @@ __device__ __forceinline__ void build_block(S* scr, const S* xu_t, const S* Gt, 
   constexpr int NN = NX + NU;
   constexpr int LD = ScrLd<NN>::LD;
   constexpr int LB = NN | 1;  // row stride of the staged G / E blocks
-  if constexpr (sizeof(S) == 8) {
+  if constexpr (sizeof(S) == 8 || ALMPC_F32_DMMA) {
     constexpr int NT = (NN + 7) / 8, KG = (NX + 3) / 4, NTX = (NX + 7) / 8, KE = (NN + 3) / 4;
     const int g = lane >> 2, q4 = lane & 3;
     // diagonal cost entries this lane will add in the epilogue: issued now, their latency hides under the MMAs

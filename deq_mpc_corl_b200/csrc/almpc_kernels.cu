@@ -73,7 +73,7 @@ static KParams<S> make_params(const almpc_desc* d) {
   return P;
 }
 
-static int check_desc(const almpc_desc* d) {
+[[maybe_unused]] static int check_desc(const almpc_desc* d) {
   if (!d) return set_err(-1, "null descriptor");
   if (d->dyn_id < 0 || d->dyn_id >= ALMPC_DYN_COUNT) return set_err(-2, "unknown dyn_id");
   if (d->B < 0) return set_err(-3, "negative batch");
@@ -89,7 +89,7 @@ constexpr int kWPB = 4;
 // Per-call profiling (desc.profile_ms != NULL): events around every launch of this forward call.
 struct ProfEv { cudaEvent_t a, b; int kind, slot; };
 
-static int n_blocks(int B) { return (B + kWPB - 1) / kWPB; }
+[[maybe_unused]] static int n_blocks(int B) { return (B + kWPB - 1) / kWPB; }
 
 // line-search launch geometry: `pls` problems per CTA, threads = one per (candidate, stage) item when it fits
 struct LsGeom { int pls, threads, blocks; };

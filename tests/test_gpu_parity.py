@@ -994,3 +994,33 @@ def test_nan_propagation_and_dual_shape_check():
     ctrl.lamda_prev = torch.zeros(B + 1, ctrl.neq + ctrl.nineq, dtype=torch.float64, device=DEV)
     with pytest.raises(_lib.AlmpcError, match="lamda_prev"):
         ctrl(inp["x0"].to(DEV), QuadCost(Qd.to(DEV), q.to(DEV), None), dyn, dyn)
+
+
+@pytest.mark.parametrize("model,T,B", [("rex_quadrotor", 5, 8192 + 5), ("flying_cartpole", 5, 8192 + 3), ("pendulum", 9, 8192)])
+def test_scratch_ring_is_transparent(model, T, B, monkeypatch):
+    """Batches >= 8192 write the block factors of non-final AL iterations into the L2-resident scratch ring instead of
+    `factor` (both factor kernels: half-warp-per-problem and row-per-lane).  Results, incl. the gradients that come
+    from the factor of the LAST step, must be bit-identical with the ring switched off."""
+    spec = MODEL_SPECS[model]
+    inp = make_inputs(model, T, B, 808)
+    Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"])
+    dyn = make_dyn(model, dt=spec["dt"])
+
+    def run(no_ring):
+        if no_ring:
+            monkeypatch.setenv("ALMPC_NO_RING", "1")
+        else:
+            monkeypatch.delenv("ALMPC_NO_RING", raising=False)
+        ctrl = MPC(spec["nx"], spec["nu"], T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B)
+        ctrl.reinitialize(inp["x_ref"].to(DEV))
+        ctrl.x_init, ctrl.u_init = inp["x_ref"].to(DEV), inp["u_ref"].to(DEV)
+        ctrl.al_iter = 3
+        ql = q.to(DEV).requires_grad_(True)
+        x, u, _ = ctrl(inp["x0"].to(DEV), QuadCost(Qd.to(DEV), ql, None), dyn, dyn)
+        g, = torch.autograd.grad((x, u), ql, (torch.ones_like(x), torch.ones_like(u)))
+        return ctrl.last_xu.clone(), ctrl.lamda_prev.clone(), g.clone(), ctrl.newton_steps(), ctrl.last_status.clone()
+
+    a, b = run(False), run(True)
+    assert a[3] == b[3] and (a[4] == 3).all()
+    for ta, tb in zip(a[:3], b[:3]):
+        assert torch.equal(ta, tb)
