@@ -29,8 +29,13 @@
 #ifndef ALMPC_NO_CP16
 #define ALMPC_NO_CP16 0
 #endif
+// The fp32 solver assembles its Hessian blocks on the FP64 tensor-core path too (operands widened, fp64 accumulation,
+// result rounded to fp32): no full-precision fp32 MMA exists, and the scalar triangle loop it replaces cost 5x the
+// instructions.  Measured (quadrotor 64K fp32): factor kernel 0.715 -> 0.553 ms, 7.38 -> 8.46 M solves/s; the block
+// is MORE accurate than the reference's fp32 bmm, and the results stay inside the reference's own fp32 noise floor
+// (q_grad vs the fp32 golden 5.4e-4, before 7.0e-4).  0 restores the scalar fp32 assembly.
 #ifndef ALMPC_F32_DMMA
-#define ALMPC_F32_DMMA 0  // 1: the fp32 solver assembles its Hessian blocks on the FP64 tensor-core path too (experiment)
+#define ALMPC_F32_DMMA 1
 #endif
 #ifndef ALMPC_LS_MINB
 #define ALMPC_LS_MINB 4  // CTAs/SM the warp line search is compiled for
