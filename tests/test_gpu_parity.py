@@ -1024,3 +1024,52 @@ def test_scratch_ring_is_transparent(model, T, B, monkeypatch):
     assert a[3] == b[3] and (a[4] == 3).all()
     for ta, tb in zip(a[:3], b[:3]):
         assert torch.equal(ta, tb)
+
+
+@pytest.mark.parametrize("name", list_tracking_golden() if cuda else [])
+def test_reference_policies_module_runs_on_our_mpc(name, monkeypatch):
+    """The one-import swap of INTEGRATION.md §1, exercised for real: the UNMODIFIED `deqmpc/policies.py` of the
+    reference (imported from its staged copy, oracle/ref_import.py) with `policies.al_mpc` / `policies.al_utils`
+    pointing at this package.  The reference's own `Tracking_MPC` code then constructs OUR `MPC` with its own
+    keyword list (policies.py:1200-1216), hands it the reference's TorchScript dynamics modules
+    (`dynamics.resolve` maps them to the CUDA functor), its diag-embedded [B,T,n,n] cost and its call sequence
+    (reinitialize / forward / warm_start_initialize) — and must reproduce the golden that the same class produced
+    on top of the reference's solver."""
+    from oracle import ref_import
+
+    if not ref_import.available():
+        pytest.skip("reference copy not staged (make -C oracle pyref)")
+    ref = ref_import.import_reference(with_policies=True)
+    from deq_mpc_corl_b200 import al_mpc as our_al_mpc, al_utils as our_al_utils
+
+    monkeypatch.setattr(ref.policies, "al_mpc", our_al_mpc)
+    monkeypatch.setattr(ref.policies, "al_utils", our_al_utils)
+    gold = Golden(name)
+    spec = MODEL_SPECS[gold.model]
+    T, B = gold.T, gold.B
+    env = ref.rex_quadrotor.RexQuadrotor(bsz=B)
+    args = types.SimpleNamespace(T=T, device=DEV, qp_iter=2, eps=1e-2, warm_start=True, bsz=B, Q=gold.t("Q"), R=gold.t("R"),
+                                 dtype="double", solver_type="al", env=gold.model, rho_init_max=gold.rho_init_max)
+    tm = ref.policies.Tracking_MPC(args, env)
+    assert type(tm.ctrl) is our_al_mpc.MPC
+    x0 = gold.t("x0").to(DEV)
+    tm.reinitialize(gold.call(0)["x_ref"].to(DEV), None)
+    for ci in range(gold.n_calls):
+        c = gold.call(ci)
+        if gold.stream_after == ci:
+            tm.warm_start_initialize(c["x_ref"].to(DEV), c["u_ref"].to(DEV))
+        xr = c["x_ref"].to(DEV).requires_grad_(True)
+        ur = c["u_ref"].to(DEV).requires_grad_(True)
+        qs = c["q_scaling"].to(DEV).requires_grad_(True) if "q_scaling" in c else None
+        x, u, status = tm(x0, None, xr, ur, q_scaling=qs, al_iters=int(c["al_iters"]))
+        ins = (xr, ur) + ((qs,) if qs is not None else ())
+        grads = torch.autograd.grad((x, u), ins, (c["gx"].to(DEV), c["gu"].to(DEV)))
+        tol = tolerances(float(c["rho_out"].double().max()), gold.dtype)
+        assert bool(status) == bool(c["status"]), f"call {ci}"
+        assert torch.equal(tm.ctrl.rho_prev.cpu().double(), c["rho_out"].double())
+        assert rel_err(x.detach().cpu(), c["x"]) < 1e-6 and rel_err(u.detach().cpu(), c["u"]) < 1e-5, f"call {ci}"
+        assert rel_err(tm.ctrl.lamda_prev.cpu(), c["lam_out"]) < tol["lam"], f"call {ci}"
+        assert rel_err(grads[0].cpu(), c["g_x_ref"]) < max(tol["grad"], 2e-6), f"call {ci}"
+        assert rel_err(grads[1].cpu(), c["g_u_ref"]) < max(tol["grad"], 2e-6), f"call {ci}"
+        if qs is not None:
+            assert rel_err(grads[2].cpu(), c["g_q_scaling"]) < max(tol["grad"], 2e-6), f"call {ci}"
