@@ -37,6 +37,16 @@
 #ifndef ALMPC_F32_DMMA
 #define ALMPC_F32_DMMA 1
 #endif
+// Backward sweep of the pair factor kernel: L / E blocks of stage t-1 by cp.async.bulk + mbarrier (one instruction
+// per 2 KB block, issued by one lane) instead of 8 + 12 per-lane cp.async.  Built, bit-identical, and measured on B200
+// (quadrotor 64K fp64): the per-lane 16-byte cp.async costs 240 shared-memory wavefronts per problem where 80 are
+// ideal (ncu source page, profiles/r02_factor_pair_smem_by_line.txt) and the bulk copy removes them — but the kernel
+// goes from 0.885 to 1.10 ms (fp32 0.553 -> 0.625): the copy has to hide behind ONE 16-step substitution (~700
+// cycles), and the round trip of a bulk copy through the TMA unit is longer than that of the L2-hitting cp.async it
+// replaces.  Off by default; -DALMPC_BULK_COPY=1 builds it.
+#ifndef ALMPC_BULK_COPY
+#define ALMPC_BULK_COPY 0
+#endif
 #ifndef ALMPC_LS_MINB
 #define ALMPC_LS_MINB 4  // CTAs/SM the warp line search is compiled for
 #endif
@@ -150,6 +160,40 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// Bulk asynchronous copies (sm_90+ / sm_100a: cp.async.bulk, executed by the TMA unit, completion through an mbarrier):
+// ONE instruction moves a whole contiguous block global -> shared with full-line shared-memory writes, where the
+// per-lane 16-byte cp.async above costs one instruction per lane and 16 bytes and — measured with ncu on the factor
+// kernel — three shared-memory wavefronts per ideal one (its data lands sector by sector).
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// orders this thread's earlier generic-proxy accesses (ordinary loads / stores, shared and global) before later
+// async-proxy operations (the bulk copies)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // copy COUNT scalars with copy width W bytes (W = widest size dividing EVERY block size of the problem, so
 // that all block offsets are W-aligned)
 template <int COUNT, int W, typename S>

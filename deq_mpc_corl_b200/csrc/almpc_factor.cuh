@@ -942,6 +942,23 @@ __device__ __forceinline__ bool factor_pair(const KParams<S>& P, const S* __rest
   S* Ecur = X;
   S* Enext = Y;
   constexpr int CW = CopyWidth<NX, NU, S>::W;
+  // Optional (ALMPC_BULK_COPY, measured slower — almpc_common.cuh): blocks whose byte sizes are multiples of 16
+  // (quadrotor: 2048 / 1536 B) come back by ONE bulk copy each (cp.async.bulk + mbarrier, issued by lane 0 of the
+  // half-warp) instead of 8 + 12 per-lane cp.async.  The E block is then staged unpadded: the sweep reads it
+  // column-per-lane, which is conflict-free at any row stride.
+  constexpr bool BULK = (CW == 16) && ALMPC_BULK_COPY;
+  constexpr int ES = BULK ? NN : LB;  // row stride of the staged E block
+  __shared__ unsigned long long s_mbar[WPB * 2];
+  unsigned long long* bar = &s_mbar[warp * 2 + half];
+  unsigned phase = 0;
+  if constexpr (BULK) {
+    // every lane: its factor rows (ordinary global stores of the forward sweep) and its last shared-memory accesses
+    // are ordered before the async-proxy copies that lane 0 issues after the warp barrier
+    fence_proxy_async();
+    if (hl == 0) mbar_init(bar, 1);
+    fence_mbar_init();
+    __syncwarp();
+  }
   auto copy_L = [&](const S* src) {
     constexpr int CHUNKS = NN * NN * (int)sizeof(S) / CW;
     for (int ch = hl; ch < CHUNKS; ch += 16) {
@@ -950,11 +967,35 @@ __device__ __forceinline__ bool factor_pair(const KParams<S>& P, const S* __rest
       else cp_async4((char*)Lsm + ch * 4, (const char*)src + ch * 4);
     }
   };
-  copy_L(fac + (size_t)(T - 1) * NN * NN);
+  // L_t -> Lsm and (with_E) E_t -> Enext
+  auto fetch = [&](int t, bool with_E) {
+    const S* srcL = fac + (size_t)t * NN * NN;
+    const S* srcE = fac + (size_t)T * NN * NN + (size_t)t * NX * NN;
+    if constexpr (BULK) {
+      if (hl == 0) {
+        constexpr unsigned bL = NN * NN * (unsigned)sizeof(S), bE = NX * NN * (unsigned)sizeof(S);
+        mbar_expect_tx(bar, with_E ? bL + bE : bL);
+        bulk_g2s(Lsm, srcL, bL, bar);
+        if (with_E) bulk_g2s(Enext, srcE, bE, bar);
+      }
+    } else {
+      copy_L(srcL);
+      if (with_E) half_copy_block_async<NX, NN, LB>(Enext, srcE, hl);
+    }
+  };
+  auto fetch_wait = [&]() {
+    if constexpr (BULK) {
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+    } else {
+      cp_async_wait_all();
+    }
+    __syncwarp();
+  };
+  fetch(T - 1, false);
   cp_async_commit();
   for (int t = T - 1; t >= 0; --t) {
-    cp_async_wait_all();
-    __syncwarp();
+    fetch_wait();
     S l[NN];
     if (hl < NN) {
 #pragma unroll
@@ -968,17 +1009,14 @@ __device__ __forceinline__ bool factor_pair(const KParams<S>& P, const S* __rest
       S s0 = S(0), s1 = S(0);
 #pragma unroll
       for (int i = 0; i + 1 < NX; i += 2) {
-        s0 += Ecur[i * LB + hl] * dv[(t + 1) * NN + i];
-        s1 += Ecur[(i + 1) * LB + hl] * dv[(t + 1) * NN + i + 1];
+        s0 += Ecur[i * ES + hl] * dv[(t + 1) * NN + i];
+        s1 += Ecur[(i + 1) * ES + hl] * dv[(t + 1) * NN + i + 1];
       }
-      if (NX & 1) s0 += Ecur[(NX - 1) * LB + hl] * dv[(t + 1) * NN + NX - 1];
+      if (NX & 1) s0 += Ecur[(NX - 1) * ES + hl] * dv[(t + 1) * NN + NX - 1];
       bb -= s0 + s1;
     }
     __syncwarp();
-    if (t > 0) {
-      copy_L(fac + (size_t)(t - 1) * NN * NN);
-      half_copy_block_async<NX, NN, LB>(Enext, fac + (size_t)T * NN * NN + (size_t)(t - 1) * NX * NN, hl);
-    }
+    if (t > 0) fetch(t - 1, true);
     cp_async_commit();
 #pragma unroll
     for (int r = NN - 1; r >= 0; --r) {
