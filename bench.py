@@ -513,6 +513,23 @@ def streaming_entry(model, T, B, dtype, dev):
             "forward_calls": calls, "al_iterations_per_streaming_call": pattern}
 
 
+def sweep_entry(dev):
+    """BASELINE config 5, reduced to one batch size so that it fits the default run: nx in {2, 4, 12} x T in {5, 10, 20}
+    at 64K problems (16K for the quadrotor at T = 20), fp64; the full 2^10..2^20 x fp64/fp32 table is
+    profiles/r02_sweep.md (tools/sweep.py)."""
+    out = []
+    for model in ("pendulum", "cartpole1l", "rex_quadrotor"):
+        for T in (5, 10, 20):
+            B = 16384 if (model == "rex_quadrotor" and T == 20) else 65536
+            pb = Problem(model, T, B, torch.float64, 1003, dev)
+            ms, o = timed(pb.device_step, 3, 2, torch.cuda.synchronize)
+            out.append({"model": model, "nx": pb.nx, "T": T, "B": B, "solves_per_s": 3 * B / (ms * 1e-3),
+                        "newton_steps_per_al_iter": pb.newton_counts(o)})
+            del pb
+            torch.cuda.empty_cache()
+    return {"workload": "synthetic sweep (BASELINE config 5), one batch size per (model, T), fp64, forward + backward", "rows": out}
+
+
 def ip_entry(B, dev, cpu_sample, no_cpu):
     """the interior-point path on the horizon-5 quadrotor QP (nz = 80, 40 bound rows, 60 equality
     rows, NON-linear dynamics residual): `qp.DenseQPFunction` forward + backward, every solve_kkt one launch of
@@ -884,6 +901,7 @@ def main():
                 "cartpole_4k_streaming": lambda: streaming_entry("cartpole1l", 5, 4096, torch.float64, dev),
                 "flying_cartpole_T10_16k": lambda: suite_entry("flying_cartpole", 10, 16384, torch.float64, dev, 5, 512, peak_tflops, hbm_peak, known, nc),
                 "ip_dense_qp_quadrotor_4k": lambda: ip_entry(4096, dev, 64, nc),
+                "synthetic_sweep_64k": lambda: sweep_entry(dev),
             }
             line["suite"] = {}
             for name, fn in entries.items():  # one failing side configuration must not cost the headline line
