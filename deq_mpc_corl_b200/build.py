@@ -12,7 +12,7 @@ SRC = os.path.join(HERE, "csrc", "almpc_kernels.cu")
 OUT = os.path.join(HERE, "libalmpc.so")
 DEPS = [SRC, os.path.join(ROOT, "include", "almpc.h")] + [
     os.path.join(HERE, "csrc", h) for h in ("almpc_models.cuh", "almpc_common.cuh", "almpc_dynamics_kernels.cuh",
-                                            "almpc_factor.cuh", "almpc_linesearch.cuh", "almpc_fused.cuh", "almpc_kkt.cuh")]
+                                            "almpc_factor.cuh", "almpc_factor_mma.cuh", "almpc_linesearch.cuh", "almpc_fused.cuh", "almpc_kkt.cuh")]
 
 
 def nvcc_path():

@@ -1,0 +1,468 @@
+// almpc_factor_mma.cuh — k_factor_solve_mma: the factor / solve step kernel with the block-tridiagonal Cholesky kept
+// in FP64 tensor-core FRAGMENT layout from assembly to write-out (part of libalmpc, see almpc_kernels.cu).
+//
+// Same inputs, outputs and factor layout as k_factor_solve / k_factor_solve_pair (almpc_factor.cuh); what changes is
+// where a problem's matrices live and which unit does the work:
+//   * 1 warp = 1 problem.  The n x n block D_t (n = 16), the nx rows of -rho G_t below it and the right-hand side
+//     are 7 accumulator tiles of mma.m8n8k4.f64 (14 doubles per lane) — not "one matrix row per lane" (32 doubles per
+//     lane and a shared-memory round trip for every pivot column).
+//   * blocked right-looking Cholesky, panel width 4 = the k of the FP64 MMA: per panel the 4x4 diagonal block is
+//     broadcast once through shared memory (16 doubles) and factored + inverted redundantly by every lane in
+//     registers; the panel solve  P = A21 W^T  (W = L11^{-1})  and the trailing update  A22 -= P P^T  are MMAs.
+//   * a symmetric permutation inside every 8-tile (logical index pi(g) = g/2 + 4 (g%2) for physical row / column g)
+//     makes the accumulator registers (c0, c1) of a tile its A/B fragments for the panel columns 0..3 / 4..7, and the
+//     panel-solve output the A/B fragment of the trailing update: no shuffles and no shared-memory transposes between
+//     the MMAs; E_{t-1} E_{t-1}^T, the coupling E_{t-1} y_{t-1} of the right-hand side, G_t^T G_t and G_t^T w are all
+//     MMAs on registers that are already fragments.
+// Shared memory per problem: gradient / cost diagonal / staged G (cp.async) / one L block for the backward sweep.
+#pragma once
+#include "almpc_factor.cuh"
+
+namespace almpc {
+
+template <int NX, int NU, typename S>
+struct MmaLayout {
+  static constexpr int NN = NX + NU;
+  static constexpr int LDG = NN + 16 / (int)sizeof(S);  // staged G rows stay 16-byte multiples
+  int N, neq, nin, m;
+  int dv, dg, bc, gs0, gs1, lsm, total;  // byte offsets (every region 16-byte aligned)
+  int xu, w, lin;                        // prologue-only arrays (double), aliased with lsm
+  __host__ __device__ MmaLayout(int T, bool se) {
+    const int SI = se ? 0 : 2 * NU;
+    N = T * NN; neq = se ? (T - 1) * NX : T * NX; nin = T * SI; m = neq + nin;
+    int o = 0;
+    auto take = [&](int bytes) { int at = o; o += (bytes + 15) & ~15; return at; };
+    dv = take(N * 8);
+    dg = take(N * 8);
+    bc = take(64 * 8);  // per panel parity: the 4x4 diagonal block, then the table of W / L11 entries
+    gs0 = take(NX * LDG * (int)sizeof(S));
+    gs1 = take(NX * LDG * (int)sizeof(S));
+    const int pro = (((N + 1) & ~1) + ((neq + 1) & ~1) + ((nin + 1) & ~1)) * 8;
+    const int lb = NN * NN * (int)sizeof(S);
+    lsm = take(pro > lb ? pro : lb);
+    xu = lsm; w = xu + ((N + 1) & ~1) * 8; lin = w + ((neq + 1) & ~1) * 8;
+    total = o;
+  }
+};
+
+// [ROWS][NN] block, contiguous in global memory -> shared rows of stride LD (16-byte chunks)
+template <int ROWS, int NN, int LD, typename S>
+__device__ __forceinline__ void warp_copy_rows16_async(S* dst, const S* src, int lane) {
+  constexpr int CPR = NN * (int)sizeof(S) / 16;
+  static_assert((NN * sizeof(S)) % 16 == 0 && (LD * sizeof(S)) % 16 == 0, "rows must be 16-byte multiples");
+  constexpr int CH = ROWS * CPR;
+  if constexpr (LD == NN) {  // contiguous on both sides
+#pragma unroll
+    for (int k = 0; k < (CH + 31) / 32; ++k)
+      if (CH % 32 == 0 || lane + 32 * k < CH) cp_async16((char*)dst + (lane + 32 * k) * 16, (const char*)src + (lane + 32 * k) * 16);
+  } else {
+    static_assert(32 % CPR == 0, "a lane keeps its chunk column");
+    const int r0 = lane / CPR, c = lane % CPR;
+    char* d0 = (char*)(dst + r0 * LD) + c * 16;
+    const char* s0 = (const char*)(src + r0 * NN) + c * 16;
+#pragma unroll
+    for (int k = 0; k < (CH + 31) / 32; ++k)
+      if (CH % 32 == 0 || lane + 32 * k < CH)
+        cp_async16(d0 + k * (32 / CPR) * LD * (int)sizeof(S), s0 + k * (32 / CPR) * NN * (int)sizeof(S));
+  }
+}
+
+#ifndef ALMPC_MMA_MINB
+#define ALMPC_MMA_MINB 5
+#endif
+
+template <int NX, int NU, typename S, int WPB, int V>
+__global__ void __launch_bounds__(WPB * 32, ALMPC_MMA_MINB)
+k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restrict__ q_g, const S* __restrict__ xu_g,
+                   S* __restrict__ lam_g, S* __restrict__ rho_g, S* fac_g, const S* __restrict__ G_g,
+                   const S* __restrict__ c_g, S* __restrict__ d_g, S* __restrict__ merit_g,
+                   double* __restrict__ rentry_g, int* __restrict__ status_g, S* __restrict__ debug_g,
+                   const Ctl* __restrict__ ctl) {
+  constexpr int NN = NX + NU;
+  static_assert(NN == 16 && NX >= 8 && NX < 16 && NX % 4 == 0, "tile mapping written for n = 16, 8 <= nx <= 12");
+  static_assert(V != 1, "obstacle rows are compiled for the row-per-lane kernel only");
+  constexpr bool SE = (V == 2);
+  constexpr int SI = 2 * NU;
+  constexpr int KG = NX / 4;                    // k-chunks of the contraction over the rows of G_t
+  constexpr int LDG = MmaLayout<NX, NU, S>::LDG;
+  constexpr int RHS = NX & 7;                   // logical in-tile row of the right-hand side (extra row NX, tile 1)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_ring;
+  grid_dep_wait();
+  const int mode = ctl->mode;
+  if (mode == MODE_DONE) return;
+  if (threadIdx.x == 0) s_ring = ring_claim(P, ctl);
+  __syncthreads();
+  const int ring_slot = s_ring;
+  const int T = P.T;
+  const MmaLayout<NX, NU, S> L(T, SE);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int prob = blockIdx.x * WPB + warp;
+  if (prob >= P.B) return;  // (warp 0 always has a problem, so the release below is reached)
+  const int g = lane >> 2, q = lane & 3, r4 = g >> 1, odd = g & 1;
+  const int pg = r4 + 4 * odd;  // logical in-tile index of physical row / column g
+  const bool rhs_lane = (pg == RHS);
+  unsigned char* sm = smem_raw + (size_t)warp * L.total;
+  double* dv = reinterpret_cast<double*>(sm + L.dv);
+  double* dg = reinterpret_cast<double*>(sm + L.dg);
+  double* bc = reinterpret_cast<double*>(sm + L.bc);
+  S* Gs0 = reinterpret_cast<S*>(sm + L.gs0);
+  S* Gs1 = reinterpret_cast<S*>(sm + L.gs1);
+  S* Lsm = reinterpret_cast<S*>(sm + L.lsm);
+  double* xu = reinterpret_cast<double*>(sm + L.xu);
+  double* wv = reinterpret_cast<double*>(sm + L.w);
+  double* lin = reinterpret_cast<double*>(sm + L.lin);
+  const size_t pN = (size_t)prob * L.N;
+  const S* Qd = Qd_g + pN;
+  const S* qv = q_g + pN;
+  S* lam = lam_g + (size_t)prob * L.m;
+  const S* cres = c_g + (size_t)prob * L.neq;
+  const S* Gp = G_g + (size_t)prob * (T - 1) * NX * NN;
+  S* fac = (ring_slot >= 0) ? P.ring + ((size_t)ring_slot * 4 + warp) * factor_elems<NX, NU>(T)
+                            : fac_g + (size_t)prob * factor_elems<NX, NU>(T);
+  S* dbg = debug_g ? debug_g + (size_t)prob * (2 * L.N + 24) : nullptr;
+
+  if (T > 1) warp_copy_rows16_async<NX, NN, LDG>(Gs0, Gp, lane);
+  cp_async_commit();
+  S rho_s = rho_g[prob];
+  // ---- prologue: dual / penalty update of the previous AL iteration (AL_mpc.py:316-317,325), entry residual
+  // ||c+||^2, merit at the entry point, w = lam_eq + rho c, and per z-entry the gradient without the G-terms
+  // (al_utils.py:113-117, 438-446) and the diagonal Qd + rho (I_x | active bounds) of the Hessian block.
+  constexpr int U = 3;
+  S p_c[U], p_l[U], p_li[U], p_Q[U], p_q[U], p_x[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int i = lane + 32 * u;
+    p_x[u] = (i < L.N) ? xu_g[pN + i] : S(0);
+    p_c[u] = (i < L.neq) ? cres[i] : S(0);
+    p_l[u] = (i < L.neq) ? lam[i] : S(0);
+    p_li[u] = (i < L.nin) ? lam[L.neq + i] : S(0);
+    p_Q[u] = (i < L.N) ? Qd[i] : S(0);
+    p_q[u] = (i < L.N) ? qv[i] : S(0);
+  }
+  for (int base = 0; base < L.N; base += 32 * U) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + lane + 32 * u;
+      if (i < L.N) xu[i] = (double)((base == 0) ? p_x[u] : xu_g[pN + i]);
+    }
+  }
+  const bool dual = (mode == MODE_DUAL_NEWTON);
+  const S rho_old = rho_s;
+  if (dual) rho_s = next_rho(rho_s, P.rho_mult, P.rho_f32);
+  const double rho = (double)rho_s;
+  __syncwarp();
+  {
+    S s2 = S(0), sl = S(0), cost = S(0);
+    for (int base = 0; base < L.neq; base += 32 * U) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + lane + 32 * u;
+        if (i < L.neq) {
+          const S cv = (base == 0) ? p_c[u] : cres[i];
+          S li = (base == 0) ? p_l[u] : lam[i];
+          if (dual) { li += rho_old * cv; lam[i] = li; }
+          s2 += cv * cv;
+          sl += li * cv;
+          wv[i] = (double)(li + rho_s * cv);
+        }
+      }
+    }
+    for (int base = 0; base < L.nin; base += 32 * U) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + lane + 32 * u;
+        if (i < L.nin) {
+          const int t = i / SI, sidx = i - t * SI;
+          const double* z_t = xu + t * NN;
+          const S ci = (sidx < NU) ? (S)z_t[NX + sidx] - P.uhi[sidx] : P.ulo[sidx - NU] - (S)z_t[NX + sidx - NU];
+          S li = (base == 0) ? p_li[u] : lam[L.neq + i];
+          if (dual) { li = fmax0(li + rho_old * ci); lam[L.neq + i] = li; }
+          lin[i] = (double)li;
+          const S cp = fmax0(ci);
+          s2 += cp * cp;
+          sl += li * ci;
+        }
+      }
+    }
+    __syncwarp();
+    for (int base = 0; base < L.N; base += 32 * U) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + lane + 32 * u;
+        if (i < L.N) {
+          const S Qv = (base == 0) ? p_Q[u] : Qd[i];
+          const S qq = (base == 0) ? p_q[u] : qv[i];
+          const S z = (S)xu[i];
+          const int t = i / NN, j = i - t * NN;
+          const bool in_cost = !SE || j < NX;  // state estimator: the cost sees the states only (al_utils_se.py:272-305)
+          if (in_cost) cost += cost_term(z, Qv, qq);
+          S gv = in_cost ? Qv * z + qq : S(0);
+          S dd = Qv;
+          if (j < NX) {
+            if (t > 0) gv += (S)wv[(t - 1) * NX + j];
+            else if (!SE) gv += (S)wv[(T - 1) * NX + j];  // the x_0 - x0 block
+            if (!SE || t > 0) dd += rho_s;
+          } else if (!SE) {
+            const int sidx = j - NX;
+            const S cu = z - P.uhi[sidx], cl = P.ulo[sidx] - z;
+            const S lu = (S)lin[t * SI + sidx], ll = (S)lin[t * SI + NU + sidx];
+            gv += (lu - ll) + rho_s * (fmax0(cu) - fmax0(cl));
+            dd += rho_s * ((cu >= S(0) ? S(1) : S(0)) + (cl >= S(0) ? S(1) : S(0)));
+          }
+          dv[i] = (double)gv;
+          dg[i] = (double)dd;
+        }
+      }
+    }
+    s2 = warp_sum(s2);
+    sl = warp_sum(sl);
+    cost = warp_sum(cost);
+    if (lane == 0) {
+      if (dual) rho_g[prob] = rho_s;
+      rentry_g[prob] = (double)s2;
+      if (mode != MODE_CONT) merit_g[prob] = cost + S(0.5) * rho_s * s2 + sl;
+    }
+  }
+  __syncwarp();
+
+  // ---- forward sweep over the stages
+  double Ep[4][2];  // E_{t-1} (+ y_{t-1} in the right-hand-side row): [k-chunk][extra tile], A/B fragments
+#pragma unroll
+  for (int p = 0; p < 4; ++p) Ep[p][0] = Ep[p][1] = 0.0;
+  S* Gc = Gs0;
+  S* Gn = Gs1;
+  const bool isdiag = (q == r4);
+  const int tl_idx = (q < r4) ? q * 4 + r4 : r4 * 5;  // table slot of L11[r4][q]
+  for (int t = 0; t < T; ++t) {
+    S* Lg = fac + (size_t)t * NN * NN;
+    S* Eg = fac + (size_t)T * NN * NN + (size_t)t * NX * NN;
+    const bool has_G = t < T - 1, has_E = t > 0;
+    cp_async_wait_all();
+    __syncwarp();
+    double Dt[3][2];     // tiles (0,0) (1,0) (1,1) of D_t
+    double X[2][2][2];   // extra rows: [extra tile][column tile][reg]: -rho G_t | rhs | 0
+#pragma unroll
+    for (int i = 0; i < 3; ++i) Dt[i][0] = Dt[i][1] = 0.0;
+    double rw[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // w^T G_t in the right-hand-side row
+    if (has_G) {
+      double f[2][KG];
+#pragma unroll
+      for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+        for (int kk = 0; kk < KG; ++kk) f[tl][kk] = (double)Gc[(4 * kk + q) * LDG + 8 * tl + pg];
+#pragma unroll
+      for (int kk = 0; kk < KG; ++kk) {
+        dmma884(Dt[0][0], Dt[0][1], f[0][kk], f[0][kk]);
+        dmma884(Dt[1][0], Dt[1][1], f[1][kk], f[0][kk]);
+        dmma884(Dt[2][0], Dt[2][1], f[1][kk], f[1][kk]);
+        const double wa = rhs_lane ? wv[t * NX + 4 * kk + q] : 0.0;
+        dmma884(rw[0][0], rw[0][1], wa, f[0][kk]);
+        dmma884(rw[1][0], rw[1][1], wa, f[1][kk]);
+      }
+    }
+    {
+      const double d0 = dg[t * NN + pg], d1 = dg[t * NN + 8 + pg];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { Dt[i][0] *= rho; Dt[i][1] *= rho; }
+      if (isdiag) {
+        if (odd) { Dt[0][1] += d0; Dt[2][1] += d1; }
+        else { Dt[0][0] += d0; Dt[2][0] += d1; }
+      }
+    }
+#pragma unroll
+    for (int xt = 0; xt < 2; ++xt)
+#pragma unroll
+      for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int row = 8 * xt + pg, col = 8 * ct + q + 4 * e;
+          double v = 0.0;
+          if (has_G && row < NX) v = -rho * (double)Gc[row * LDG + col];
+          if (xt == 1 && rhs_lane) {
+            v = dv[t * NN + col] - rw[ct][e];
+            if (dbg) dbg[t * NN + col] = (S)v;
+          }
+          X[xt][ct][e] = v;
+        }
+    __syncwarp();  // G_t has no reader left: prefetch G_{t+1} behind the factorisation
+    if (t + 1 < T - 1) warp_copy_rows16_async<NX, NN, LDG>(Gn, Gp + (size_t)(t + 1) * NX * NN, lane);
+    cp_async_commit();
+    if (has_E) {
+      double sy[3][2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) sy[i][0] = sy[i][1] = 0.0;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const double a0 = Ep[p][0], a1 = Ep[p][1];
+        const double b1 = (8 + pg < NX) ? a1 : 0.0;  // the y row (and the padding) is no column of E E^T
+        dmma884(sy[0][0], sy[0][1], a0, a0);
+        dmma884(sy[1][0], sy[1][1], a1, a0);
+        dmma884(sy[2][0], sy[2][1], a1, b1);
+      }
+      Dt[0][0] -= sy[0][0]; Dt[0][1] -= sy[0][1];
+      if (rhs_lane) {  // row NX of the product is y_{t-1} E_{t-1}^T: the coupling of the right-hand side
+        X[1][0][0] -= sy[1][0]; X[1][0][1] -= sy[1][1];
+        X[1][1][0] -= sy[2][0]; X[1][1][1] -= sy[2][1];
+      } else {
+        Dt[1][0] -= sy[1][0]; Dt[1][1] -= sy[1][1];
+        Dt[2][0] -= sy[2][0]; Dt[2][1] -= sy[2][1];
+      }
+    }
+    // ---- blocked elimination, panel width 4
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int tc = p >> 1, pp = p & 1;
+      const int dti = tc ? 2 : 0;
+      double* bcb = bc + pp * 32;
+      if (odd == pp) bcb[r4 * 4 + q] = Dt[dti][pp];
+      __syncwarp();
+      const double a00 = bcb[0];
+      const Vec2<double> r1 = *reinterpret_cast<const Vec2<double>*>(bcb + 4);
+      const Vec2<double> r2 = *reinterpret_cast<const Vec2<double>*>(bcb + 8);
+      const double a22 = bcb[10];
+      const Vec2<double> r3a = *reinterpret_cast<const Vec2<double>*>(bcb + 12);
+      const Vec2<double> r3b = *reinterpret_cast<const Vec2<double>*>(bcb + 14);
+      // 4x4 Cholesky and its inverse W = L11^{-1}, redundantly in every lane; a non-positive pivot turns into
+      // NaN / Inf and poisons the whole solution of the problem, which is what the end of the kernel tests
+      const double i0 = rsqrt_(a00);
+      const double l10 = r1.x * i0, l20 = r2.x * i0, l30 = r3a.x * i0;
+      const double i1 = rsqrt_(fma(-l10, l10, r1.y));
+      const double l21 = fma(-l20, l10, r2.y) * i1, l31 = fma(-l30, l10, r3a.y) * i1;
+      const double i2 = rsqrt_(fma(-l21, l21, fma(-l20, l20, a22)));
+      const double l32 = fma(-l31, l21, fma(-l30, l20, r3b.x)) * i2;
+      const double i3 = rsqrt_(fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, r3b.y))));
+      const double w10 = -(l10 * i0) * i1;
+      const double w20 = -fma(l21, w10, l20 * i0) * i2, w21 = -(l21 * i1) * i2;
+      const double w30 = -fma(l32, w20, fma(l31, w10, l30 * i0)) * i3, w31 = -fma(l32, w21, l31 * i1) * i3,
+                   w32 = -(l32 * i2) * i3;
+      // every lane holds all of W and L11; the entry [r4][q] a lane needs (B fragment of the panel solve: physical
+      // column 2c <-> column c of P; L11 for the write-out) is looked up through a 16-entry table in shared memory
+      // (8 stores by one lane, 2 loads per lane) — a register select tree costs 70 instructions per panel
+      {
+        Vec2<double>* tb = reinterpret_cast<Vec2<double>*>(bcb + 16);  // lower: W (diag 1/L_ii), upper (c,r): L[r][c]
+        if (lane == 0) {
+          tb[0] = Vec2<double>{i0, l10}; tb[1] = Vec2<double>{l20, l30};
+          tb[2] = Vec2<double>{w10, i1}; tb[3] = Vec2<double>{l21, l31};
+          tb[4] = Vec2<double>{w20, w21}; tb[5] = Vec2<double>{i2, l32};
+          tb[6] = Vec2<double>{w30, w31}; tb[7] = Vec2<double>{w32, i3};
+        }
+        __syncwarp();
+      }
+      const double wsel = bcb[16 + r4 * 4 + q];
+      const double lraw = bcb[16 + tl_idx];
+      const double lsel = (q <= r4) ? lraw : 0.0;
+      const double wb = (odd || q > r4) ? 0.0 : wsel;
+      // panel solve P = A W^T per row tile: c0 of the output is P[row][q], i.e. already the A/B fragment of the update
+      double P0 = 0.0, P1 = 0.0, PX0 = 0.0, PX1 = 0.0, junk;
+      if (p == 0) { junk = 0.0; dmma884(P0, junk, Dt[0][0], wb); }
+      if (p <= 1) { junk = 0.0; dmma884(P1, junk, Dt[1][pp], wb); }
+      if (p == 2) { junk = 0.0; dmma884(P1, junk, Dt[2][0], wb); }
+      junk = 0.0; dmma884(PX0, junk, X[0][tc][pp], wb);
+      junk = 0.0; dmma884(PX1, junk, X[1][tc][pp], wb);
+      // write-outs: L rows (zeros above the diagonal, 1/L_ii on it), E_t rows, y_t
+      {
+        double v0, v1;
+        if (p == 0) { v0 = odd ? P0 : lsel; v1 = P1; }
+        else if (p == 1) { v0 = odd ? lsel : 0.0; v1 = P1; }
+        else if (p == 2) { v0 = 0.0; v1 = odd ? P1 : lsel; }
+        else { v0 = 0.0; v1 = odd ? lsel : 0.0; }
+        Lg[pg * NN + 4 * p + q] = (S)v0;
+        Lg[(8 + pg) * NN + 4 * p + q] = (S)v1;
+        if (has_G) {
+          Eg[pg * NN + 4 * p + q] = (S)PX0;
+          if (8 + pg < NX) Eg[(8 + pg) * NN + 4 * p + q] = (S)PX1;
+        }
+        if (rhs_lane) dv[t * NN + 4 * p + q] = PX1;
+      }
+      Ep[p][0] = PX0;
+      Ep[p][1] = PX1;
+      // trailing update A22 -= P P^T (columns inside the panel's own tile half are masked out of the B fragment)
+      if (p == 0) {
+        const double nb = odd ? -P0 : 0.0, nb1 = -P1;
+        dmma884(Dt[0][0], Dt[0][1], P0, nb);
+        dmma884(Dt[1][0], Dt[1][1], P1, nb);
+        dmma884(X[0][0][0], X[0][0][1], PX0, nb);
+        dmma884(X[1][0][0], X[1][0][1], PX1, nb);
+        dmma884(Dt[2][0], Dt[2][1], P1, nb1);
+        dmma884(X[0][1][0], X[0][1][1], PX0, nb1);
+        dmma884(X[1][1][0], X[1][1][1], PX1, nb1);
+      } else if (p == 1) {
+        const double nb1 = -P1;
+        dmma884(Dt[2][0], Dt[2][1], P1, nb1);
+        dmma884(X[0][1][0], X[0][1][1], PX0, nb1);
+        dmma884(X[1][1][0], X[1][1][1], PX1, nb1);
+      } else if (p == 2) {
+        const double nb = odd ? -P1 : 0.0;
+        dmma884(Dt[2][0], Dt[2][1], P1, nb);
+        dmma884(X[0][1][0], X[0][1][1], PX0, nb);
+        dmma884(X[1][1][0], X[1][1][1], PX1, nb);
+      }
+    }
+    S* tmp = Gc; Gc = Gn; Gn = tmp;
+  }
+  // ---- backward sweep, d = -H^{-1} g.  L_tt / E_t come back from the streamed factor (L2) through cp.async: the
+  // blocks of stage t-1 are in flight while the substitution of stage t runs.
+  cp_async_wait_all();
+  __syncwarp();
+  S* Ecur = Gc;
+  S* Enext = Gn;
+  auto fetch = [&](int t, bool with_E) {
+    warp_copy_rows16_async<NN, NN, NN>(Lsm, fac + (size_t)t * NN * NN, lane);
+    if (with_E) warp_copy_rows16_async<NX, NN, NN>(Enext, fac + (size_t)T * NN * NN + (size_t)t * NX * NN, lane);
+  };
+  fetch(T - 1, false);
+  cp_async_commit();
+  for (int t = T - 1; t >= 0; --t) {
+    cp_async_wait_all();
+    __syncwarp();
+    // lane j < n owns column j of L^T.  Its own 1/L_jj is taken out of the staged block (and replaced by 0), so the
+    // column needs no masks: the stored factor has zeros above the diagonal.  Lanes >= n shadow lanes 0..n-1.
+    const int jc = lane & (NN - 1);
+    const double inv = (double)Lsm[jc * NN + jc];
+    if (lane < NN) Lsm[jc * NN + jc] = S(0);
+    double l[NN];
+#pragma unroll
+    for (int r = 0; r < NN; ++r) l[r] = (double)Lsm[r * NN + jc];
+    double bb = (lane < NN) ? dv[t * NN + lane] : 0.0;
+    if (t < T - 1 && lane < NN) {
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int i = 0; i + 1 < NX; i += 2) {
+        s0 += (double)Ecur[i * NN + lane] * dv[(t + 1) * NN + i];
+        s1 += (double)Ecur[(i + 1) * NN + lane] * dv[(t + 1) * NN + i + 1];
+      }
+      bb -= s0 + s1;
+    }
+    __syncwarp();
+    if (t > 0) fetch(t - 1, true);
+    cp_async_commit();
+#pragma unroll
+    for (int r = NN - 1; r >= 0; --r) {
+      const double dr = __shfl_sync(FULL, bb * inv, r);  // x_r, final on lane r once the rows below are done
+      bb = fma(-l[r], dr, bb);                           // lanes j < r: L[r][j] x_r; l[r] = 0 on lanes j >= r
+    }
+    if (lane < NN) dv[t * NN + lane] = bb * inv;
+    S* tmp = Ecur; Ecur = Enext; Enext = tmp;
+  }
+  __syncwarp();
+  bool ok = true;
+  for (int i = lane; i < L.N; i += 32) ok = ok && finite_(dv[i]);
+  ok = __all_sync(FULL, ok);
+  for (int i = lane; i < L.N; i += 32) {
+    const S d = ok ? (S)(-dv[i]) : S(0);
+    d_g[pN + i] = d;
+    if (dbg) dbg[L.N + i] = d;
+  }
+  if (lane == 0) {
+    int status = (mode == MODE_FIRST) ? (ALMPC_STATUS_FINITE | ALMPC_STATUS_CHOL_OK) : status_g[prob];
+    if (!ok) status &= ~ALMPC_STATUS_CHOL_OK;
+    status_g[prob] = status;
+  }
+  if (ring_slot >= 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) ring_release(P, ring_slot);
+  }
+}
+
+}  // namespace almpc

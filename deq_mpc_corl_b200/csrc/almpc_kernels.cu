@@ -29,6 +29,7 @@
 #include "almpc_common.cuh"
 #include "almpc_dynamics_kernels.cuh"
 #include "almpc_factor.cuh"
+#include "almpc_factor_mma.cuh"
 #include "almpc_linesearch.cuh"
 #include "almpc_fused.cuh"
 #include "almpc_kkt.cuh"
@@ -199,6 +200,13 @@ static auto pair_kernel() -> decltype(&k_factor_solve<NX, NU, S, kWPB, V>) {
   if constexpr (NX + NU <= 16 && NX + 1 <= 16 && V != 1) return &k_factor_solve_pair<NX, NU, S, kWPP, V>;
   else return nullptr;
 }
+// the fragment-layout factor kernel (almpc_factor_mma.cuh) is written for 16-wide blocks (quadrotor)
+constexpr int kWPM = 4;  // warps = problems per CTA
+template <int NX, int NU, typename S, int V>
+static auto mma_kernel() -> decltype(&k_factor_solve<NX, NU, S, kWPB, V>) {
+  if constexpr (NX + NU == 16 && NX >= 8 && NX < 16 && NX % 4 == 0 && V != 1) return &k_factor_solve_mma<NX, NU, S, kWPM, V>;
+  else return nullptr;
+}
 template <typename S>
 using FusedFn = void (*)(const KParams<S>, const S*, const S*, const S*, S*, S*, S*, S*, const S*, const S*, S*, int*, int*,
                          S*, Ctl*, double*);
@@ -214,7 +222,7 @@ static FusedFn<S> fused_kernel() {
 struct Plan {
   int dev = -1, T = 0, n_obs = -1, select = -1;
   int n_sm = 0;
-  bool use_pair = false, fused = false;
+  bool use_pair = false, fused = false, use_mma = false;
   size_t smem_fac = 0, smem_ls = 0, smem_fin = 0, smem_fused = 0;
   int fac_threads = 0, fac_per_cta = 0, fin_ppw = 1, ls_grid_cap = 0;
   LsWarpCfg lw{nullptr, 0, 0, 1};
@@ -245,8 +253,21 @@ static int make_plan(Plan& pl, int dev, int T, int n_obs, int select) {
     return set_err(-11, "horizon too long for the shared-memory layout");
   auto kfac = &k_factor_solve<NX, NU, S, kWPB, V>;
   pl.fac_threads = kWPB * 32; pl.fac_per_cta = kWPB;
-  pl.use_pair = pl.fused = false;
-  if (auto kp = pair_kernel<NX, NU, S, V>(); kp && !(select & ALMPC_SELECT_FAC_SINGLE)) {
+  pl.use_pair = pl.fused = pl.use_mma = false;
+  if (auto km = mma_kernel<NX, NU, S, V>(); km && (select & ALMPC_SELECT_FAC_MMA) && !(select & ALMPC_SELECT_FAC_SINGLE)) {
+    if constexpr (NX + NU == 16) {
+      const size_t smem_mma = (size_t)kWPM * MmaLayout<NX, NU, S>(T, SE).total;
+      if (smem_mma + 1024 <= 227 * 1024 && allow_max_smem(km, optin) == cudaSuccess) {
+        pl.use_mma = true;
+        pl.fac_threads = kWPM * 32;
+        pl.fac_per_cta = kWPM;
+        pl.smem_fac = smem_mma;
+      } else {
+        (void)cudaGetLastError();
+      }
+    }
+  }
+  if (auto kp = pair_kernel<NX, NU, S, V>(); kp && !pl.use_mma && !(select & ALMPC_SELECT_FAC_SINGLE)) {
     // Both kernels are bound by (latency of one problem) / (problems resident per SM): take the pair kernel
     // unless its larger shared-memory footprint (long horizons) leaves it with clearly fewer resident problems.
     const size_t smem_pair = (size_t)2 * kWPP * Layout<NX, NU>(T, 0, SE, true).total * sizeof(S);
@@ -280,7 +301,7 @@ static int make_plan(Plan& pl, int dev, int T, int n_obs, int select) {
       }
     }
   }
-  if (!pl.use_pair) {
+  if (!pl.use_pair && !pl.use_mma) {
     e = allow_max_smem(kfac, optin);
     if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(factor_solve)");
   }
@@ -352,6 +373,7 @@ static int forward_impl(const almpc_desc* d, const S* x0, const S* Qd, const S* 
   auto kjac = k_jacobian<M, S, V>;
   auto kfac = &k_factor_solve<NX, NU, S, kWPB, V>;
   if (pl.use_pair) kfac = pair_kernel<NX, NU, S, V>();
+  if (pl.use_mma) kfac = mma_kernel<NX, NU, S, V>();
   auto kfused = fused_kernel<M, S, V>();
   auto kls = k_line_search<M, S, V>;
   auto kfin = k_final_dual<M, S, kWPB, V>;
