@@ -309,14 +309,16 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
         Dt[2][0] -= sy[2][0]; Dt[2][1] -= sy[2][1];
       }
     }
-    // ---- blocked elimination, panel width 4
+    // ---- blocked elimination, panel width 4.  Look-ahead: as soon as a panel's solve is done, the tile holding the
+    // NEXT diagonal block is updated and that block is published, so that its shared-memory round trip runs under
+    // the remaining trailing updates and the write-outs of this panel.
+    if (!odd) bc[r4 * 4 + q] = Dt[0][0];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const int tc = p >> 1, pp = p & 1;
       const int dti = tc ? 2 : 0;
       double* bcb = bc + pp * 32;
-      if (odd == pp) bcb[r4 * 4 + q] = Dt[dti][pp];
-      __syncwarp();
+      __syncwarp();  // the diagonal block of this panel was published by the previous panel (look-ahead)
       const double a00 = bcb[0];
       const Vec2<double> r1 = *reinterpret_cast<const Vec2<double>*>(bcb + 4);
       const Vec2<double> r2 = *reinterpret_cast<const Vec2<double>*>(bcb + 8);
@@ -360,6 +362,36 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
       if (p == 2) { junk = 0.0; dmma884(P1, junk, Dt[2][0], wb); }
       junk = 0.0; dmma884(PX0, junk, X[0][tc][pp], wb);
       junk = 0.0; dmma884(PX1, junk, X[1][tc][pp], wb);
+      // trailing update A22 -= P P^T (columns inside the panel's own tile half are masked out of the B fragment):
+      // first the tile with the next diagonal block, which is published at once
+      const double nbm = odd ? -((p == 0) ? P0 : P1) : 0.0, nb1 = -P1;
+      if (p < 3) {
+        double* bnx = bc + ((p + 1) & 1) * 32;
+        if (p == 0) {
+          dmma884(Dt[0][0], Dt[0][1], P0, nbm);
+          if (odd) bnx[r4 * 4 + q] = Dt[0][1];
+        } else if (p == 1) {
+          dmma884(Dt[2][0], Dt[2][1], P1, nb1);
+          if (!odd) bnx[r4 * 4 + q] = Dt[2][0];
+        } else {
+          dmma884(Dt[2][0], Dt[2][1], P1, nbm);
+          if (odd) bnx[r4 * 4 + q] = Dt[2][1];
+        }
+      }
+      if (p == 0) {
+        dmma884(Dt[1][0], Dt[1][1], P1, nbm);
+        dmma884(X[0][0][0], X[0][0][1], PX0, nbm);
+        dmma884(X[1][0][0], X[1][0][1], PX1, nbm);
+        dmma884(Dt[2][0], Dt[2][1], P1, nb1);
+        dmma884(X[0][1][0], X[0][1][1], PX0, nb1);
+        dmma884(X[1][1][0], X[1][1][1], PX1, nb1);
+      } else if (p == 1) {
+        dmma884(X[0][1][0], X[0][1][1], PX0, nb1);
+        dmma884(X[1][1][0], X[1][1][1], PX1, nb1);
+      } else if (p == 2) {
+        dmma884(X[0][1][0], X[0][1][1], PX0, nbm);
+        dmma884(X[1][1][0], X[1][1][1], PX1, nbm);
+      }
       // write-outs: L rows (zeros above the diagonal, 1/L_ii on it), E_t rows, y_t
       {
         double v0, v1;
@@ -377,27 +409,6 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
       }
       Ep[p][0] = PX0;
       Ep[p][1] = PX1;
-      // trailing update A22 -= P P^T (columns inside the panel's own tile half are masked out of the B fragment)
-      if (p == 0) {
-        const double nb = odd ? -P0 : 0.0, nb1 = -P1;
-        dmma884(Dt[0][0], Dt[0][1], P0, nb);
-        dmma884(Dt[1][0], Dt[1][1], P1, nb);
-        dmma884(X[0][0][0], X[0][0][1], PX0, nb);
-        dmma884(X[1][0][0], X[1][0][1], PX1, nb);
-        dmma884(Dt[2][0], Dt[2][1], P1, nb1);
-        dmma884(X[0][1][0], X[0][1][1], PX0, nb1);
-        dmma884(X[1][1][0], X[1][1][1], PX1, nb1);
-      } else if (p == 1) {
-        const double nb1 = -P1;
-        dmma884(Dt[2][0], Dt[2][1], P1, nb1);
-        dmma884(X[0][1][0], X[0][1][1], PX0, nb1);
-        dmma884(X[1][1][0], X[1][1][1], PX1, nb1);
-      } else if (p == 2) {
-        const double nb = odd ? -P1 : 0.0;
-        dmma884(Dt[2][0], Dt[2][1], P1, nb);
-        dmma884(X[0][1][0], X[0][1][1], PX0, nb);
-        dmma884(X[1][1][0], X[1][1][1], PX1, nb);
-      }
     }
     S* tmp = Gc; Gc = Gn; Gn = tmp;
   }

@@ -254,7 +254,7 @@ static int make_plan(Plan& pl, int dev, int T, int n_obs, int select) {
   auto kfac = &k_factor_solve<NX, NU, S, kWPB, V>;
   pl.fac_threads = kWPB * 32; pl.fac_per_cta = kWPB;
   pl.use_pair = pl.fused = pl.use_mma = false;
-  if (auto km = mma_kernel<NX, NU, S, V>(); km && (select & ALMPC_SELECT_FAC_MMA) && !(select & ALMPC_SELECT_FAC_SINGLE)) {
+  if (auto km = mma_kernel<NX, NU, S, V>(); km && !(select & (ALMPC_SELECT_FAC_PAIR | ALMPC_SELECT_FAC_SINGLE | ALMPC_SELECT_FUSE))) {
     if constexpr (NX + NU == 16) {
       const size_t smem_mma = (size_t)kWPM * MmaLayout<NX, NU, S>(T, SE).total;
       if (smem_mma + 1024 <= 227 * 1024 && allow_max_smem(km, optin) == cudaSuccess) {

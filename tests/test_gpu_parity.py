@@ -704,6 +704,8 @@ def test_fused_newton_tail_equals_three_kernel_path(model, T, B, se, monkeypatch
     dyn = make_dyn(model, dt=spec["dt"])
 
     def chain(fuse):
+        # the fused kernel continues the half-warp-per-problem factor phase: compare with THAT three-kernel path
+        monkeypatch.setenv("ALMPC_FAC_PAIR", "1")
         if fuse:
             monkeypatch.setenv("ALMPC_FUSE", "1")
         else:
@@ -727,6 +729,47 @@ def test_fused_newton_tail_equals_three_kernel_path(model, T, B, se, monkeypatch
         assert a[5] == b[5]
         for ta, tb in zip(a[:5], b[:5]):
             assert torch.equal(ta, tb)
+
+
+@pytest.mark.parametrize("T,B,se,dtype", [(5, 131, False, torch.float64), (2, 1, False, torch.float64),
+                                          (9, 67, True, torch.float64), (17, 40, False, torch.float64),
+                                          (5, 257, False, torch.float32), (4, 33, True, torch.float32)])
+def test_fragment_layout_factor_kernel_matches_half_warp_kernel(T, B, se, dtype, monkeypatch):
+    """k_factor_solve_mma (blocked Cholesky in FP64-MMA fragment layout, the default for the 16-wide quadrotor blocks)
+    against k_factor_solve_pair (ALMPC_SELECT_FAC_PAIR: right-looking, one row per lane) over two chained calls (the
+    second runs the fused dual update): same Newton-step counts and status, iterates / multipliers / gradients equal to
+    rounding.  The two kernels order their floating-point operations differently, so bit-identity is not expected."""
+    model = "rex_quadrotor"
+    spec = MODEL_SPECS[model]
+    inp = make_inputs(model, T, B, 909 + T)
+    dyn = make_dyn(model, dt=spec["dt"])
+
+    def chain(pair):
+        if pair:
+            monkeypatch.setenv("ALMPC_FAC_PAIR", "1")
+        else:
+            monkeypatch.delenv("ALMPC_FAC_PAIR", raising=False)
+        ctrl = MPC(spec["nx"], spec["nu"], T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B, state_estimator=se)
+        ctrl.reinitialize(inp["x_ref"].to(DEV).to(dtype))
+        ctrl.x_init, ctrl.u_init = inp["x_ref"].to(DEV), inp["u_ref"].to(DEV)
+        out, x_ref = [], inp["x_ref"]
+        for _ in range(2):
+            Qd, q, _ = tracking_cost(inp["Qd"], x_ref, inp["u_ref"], dtype)
+            ql = q.to(dtype).to(DEV).requires_grad_(True)
+            x, u, _ = ctrl(inp["x0"].to(DEV).to(dtype), QuadCost(Qd.to(dtype).to(DEV), ql, None), dyn, dyn)
+            g, = torch.autograd.grad((x, u), ql, (torch.ones_like(x), torch.ones_like(u)))
+            out.append((ctrl.last_xu.clone(), ctrl.lamda_prev.clone(), g.clone(), ctrl.last_status.clone(), ctrl.newton_steps()))
+            x_ref = 0.7 * x_ref + 0.3 * x.detach().cpu()
+            x_ref[:, 0] = inp["x0"]
+        return out
+
+    tol = 1e-9 if dtype == torch.float64 else 2e-3
+    for ci, (a, b) in enumerate(zip(chain(False), chain(True))):
+        assert a[4] == b[4], (ci, a[4], b[4])
+        assert torch.equal(a[3], b[3])
+        for k, (ta, tb) in enumerate(zip(a[:3], b[:3])):
+            if tb.numel():
+                assert rel_err(ta.cpu().double(), tb.cpu().double()) < tol, (ci, k)
 
 
 def test_c_abi_used_directly_like_integration_md():
@@ -934,9 +977,16 @@ def test_deq_chain_without_resync_matches_oracle():
     assert float(ctrl.rho_prev.max()) == float(torch.tensor(1e12, dtype=torch.float32))
 
 
-def test_fp32_high_penalty_flags_instead_of_failing():
+@pytest.mark.parametrize("pair", [True, False])
+def test_fp32_high_penalty_flags_instead_of_failing(pair, monkeypatch):
     """fp32 loses positive definiteness from rho ~ 1e4 on.  The solver must keep running, keep the
-    iterate finite and report the broken pivots per problem (ALMPC_STATUS_CHOL_OK cleared) — never hang or NaN."""
+    iterate finite and report the broken pivots per problem (ALMPC_STATUS_CHOL_OK cleared) — never hang or NaN.
+    pair=True: the half-warp-per-problem kernel, which factors in fp32 and does lose pivots; pair=False: the default
+    fragment-layout kernel keeps the blocks in FP64 accumulators (fp32 only at the interface), so its pivots survive."""
+    if pair:
+        monkeypatch.setenv("ALMPC_FAC_PAIR", "1")
+    else:
+        monkeypatch.delenv("ALMPC_FAC_PAIR", raising=False)
     model, T, B = "rex_quadrotor", 5, 256
     inp = make_inputs(model, T, B, 5)
     Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"], torch.float32)
@@ -951,7 +1001,8 @@ def test_fp32_high_penalty_flags_instead_of_failing():
         assert torch.isfinite(x).all() and torch.isfinite(u).all()
         assert ((st & _lib.STATUS_FINITE) == _lib.STATUS_FINITE).all()
         flagged = int(((st & _lib.STATUS_CHOL_OK) == 0).sum())
-    assert flagged > 0  # at rho = 1e6..1e7 fp32 pivots do go non-positive for some problems
+    if pair:
+        assert flagged > 0  # at rho = 1e6..1e7 fp32 pivots do go non-positive for some problems
 
 
 def test_nan_propagation_and_dual_shape_check():
