@@ -53,17 +53,17 @@ class Desc(ctypes.Structure):
 # int (*almpc_stop_reduce_fn)(double* stats_dev, void* stream, void* user)
 STOP_REDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
 
-SELECT_FAC_SINGLE, SELECT_FUSE, SELECT_LS_CTA, SELECT_PDL, SELECT_NO_RING, SELECT_NO_PDL, SELECT_FAC_PAIR = 1, 2, 4, 8, 16, 32, 64
+SELECT_FAC_SINGLE, SELECT_FUSE, SELECT_LS_CTA, SELECT_PDL, SELECT_NO_RING, SELECT_NO_PDL, SELECT_FAC_PAIR, SELECT_FAC_MMA = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 def env_select():
     """desc.select from the environment (A/B measurements, differential tests): ALMPC_FAC_SINGLE, ALMPC_FUSE,
-    ALMPC_LS_CTA, ALMPC_PDL, ALMPC_NO_PDL, ALMPC_NO_RING, ALMPC_FAC_PAIR.  Read per call on the host side; the library itself has no global state."""
+    ALMPC_LS_CTA, ALMPC_PDL, ALMPC_NO_PDL, ALMPC_NO_RING, ALMPC_FAC_PAIR, ALMPC_FAC_MMA.  Read per call on the host side; the library itself has no global state."""
     e = os.environ
     return ((SELECT_FAC_SINGLE if e.get("ALMPC_FAC_SINGLE") else 0) | (SELECT_FUSE if e.get("ALMPC_FUSE") else 0)
             | (SELECT_LS_CTA if e.get("ALMPC_LS_CTA") else 0) | (SELECT_PDL if e.get("ALMPC_PDL") else 0)
             | (SELECT_NO_RING if e.get("ALMPC_NO_RING") else 0) | (SELECT_NO_PDL if e.get("ALMPC_NO_PDL") else 0)
-            | (SELECT_FAC_PAIR if e.get("ALMPC_FAC_PAIR") else 0))
+            | (SELECT_FAC_PAIR if e.get("ALMPC_FAC_PAIR") else 0) | (SELECT_FAC_MMA if e.get("ALMPC_FAC_MMA") else 0))
 
 
 FLAG_SKIP_FINAL_DUAL = 1

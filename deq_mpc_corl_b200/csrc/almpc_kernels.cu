@@ -254,7 +254,11 @@ static int make_plan(Plan& pl, int dev, int T, int n_obs, int select) {
   auto kfac = &k_factor_solve<NX, NU, S, kWPB, V>;
   pl.fac_threads = kWPB * 32; pl.fac_per_cta = kWPB;
   pl.use_pair = pl.fused = pl.use_mma = false;
-  if (auto km = mma_kernel<NX, NU, S, V>(); km && !(select & (ALMPC_SELECT_FAC_PAIR | ALMPC_SELECT_FAC_SINGLE | ALMPC_SELECT_FUSE))) {
+  if (auto km = mma_kernel<NX, NU, S, V>(); km && !(select & (ALMPC_SELECT_FAC_PAIR | ALMPC_SELECT_FAC_SINGLE | ALMPC_SELECT_FUSE)) &&
+                                               (sizeof(S) == 8 || (select & ALMPC_SELECT_FAC_MMA))) {
+    // fp64: 0.64 vs 0.88 ms per launch at 64K quadrotor problems (0.095 vs 0.137 ms at 8K).  fp32 problems keep the
+    // half-warp kernel by default: it factors in fp32 registers at 10 CTAs/SM (0.553 ms) while this kernel keeps its
+    // blocks in FP64 accumulators whatever the interface type (0.620 ms) — selectable for its accuracy (no lost pivots)
     if constexpr (NX + NU == 16) {
       const size_t smem_mma = (size_t)kWPM * MmaLayout<NX, NU, S>(T, SE).total;
       if (smem_mma + 1024 <= 227 * 1024 && allow_max_smem(km, optin) == cudaSuccess) {

@@ -72,6 +72,7 @@ enum almpc_dyn_id {
 #define ALMPC_SELECT_PDL 8        /* launch the step kernels with programmatic stream serialization (default for B <= 16384) */
 #define ALMPC_SELECT_NO_PDL 32    /* ... never */
 #define ALMPC_SELECT_FAC_PAIR 64  /* half-warp-per-problem factor kernel even where the fragment-layout one (k_factor_solve_mma: blocked Cholesky on FP64 MMAs, the default for 16-wide blocks) applies */
+#define ALMPC_SELECT_FAC_MMA 128  /* the fragment-layout factor kernel for fp32 problems too (blocks kept in FP64 accumulators) */
 #define ALMPC_SELECT_NO_RING 16   /* every Newton step streams its block factor to `factor` (no L2-resident scratch ring) */
 
 /* Hook for the reference's batch-GLOBAL decisions under batch sharding (qpth/al_utils.py:486,552,560-564: the

@@ -745,10 +745,9 @@ def test_fragment_layout_factor_kernel_matches_half_warp_kernel(T, B, se, dtype,
     dyn = make_dyn(model, dt=spec["dt"])
 
     def chain(pair):
-        if pair:
-            monkeypatch.setenv("ALMPC_FAC_PAIR", "1")
-        else:
-            monkeypatch.delenv("ALMPC_FAC_PAIR", raising=False)
+        monkeypatch.delenv("ALMPC_FAC_PAIR", raising=False)
+        monkeypatch.delenv("ALMPC_FAC_MMA", raising=False)
+        monkeypatch.setenv("ALMPC_FAC_PAIR" if pair else "ALMPC_FAC_MMA", "1")  # (fp32 defaults to the half-warp kernel)
         ctrl = MPC(spec["nx"], spec["nu"], T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B, state_estimator=se)
         ctrl.reinitialize(inp["x_ref"].to(DEV).to(dtype))
         ctrl.x_init, ctrl.u_init = inp["x_ref"].to(DEV), inp["u_ref"].to(DEV)
@@ -981,12 +980,9 @@ def test_deq_chain_without_resync_matches_oracle():
 def test_fp32_high_penalty_flags_instead_of_failing(pair, monkeypatch):
     """fp32 loses positive definiteness from rho ~ 1e4 on.  The solver must keep running, keep the
     iterate finite and report the broken pivots per problem (ALMPC_STATUS_CHOL_OK cleared) — never hang or NaN.
-    pair=True: the half-warp-per-problem kernel, which factors in fp32 and does lose pivots; pair=False: the default
-    fragment-layout kernel keeps the blocks in FP64 accumulators (fp32 only at the interface), so its pivots survive."""
-    if pair:
-        monkeypatch.setenv("ALMPC_FAC_PAIR", "1")
-    else:
-        monkeypatch.delenv("ALMPC_FAC_PAIR", raising=False)
+    pair=True: the half-warp-per-problem kernel (the fp32 default), which factors in fp32 and does lose pivots;
+    pair=False: the fragment-layout kernel (ALMPC_SELECT_FAC_MMA) keeps the blocks in FP64 accumulators (fp32 only at the interface), so its pivots survive."""
+    monkeypatch.setenv("ALMPC_FAC_PAIR" if pair else "ALMPC_FAC_MMA", "1")
     model, T, B = "rex_quadrotor", 5, 256
     inp = make_inputs(model, T, B, 5)
     Qd, q, _ = tracking_cost(inp["Qd"], inp["x_ref"], inp["u_ref"], torch.float32)
