@@ -68,11 +68,11 @@ __device__ __forceinline__ void warp_copy_rows16_async(S* dst, const S* src, int
 }
 
 #ifndef ALMPC_MMA_MINB
-#define ALMPC_MMA_MINB 5
+#define ALMPC_MMA_MINB 5  // CTAs of 4 warps per SM the kernel is compiled for (96 registers)
 #endif
 
 template <int NX, int NU, typename S, int WPB, int V>
-__global__ void __launch_bounds__(WPB * 32, ALMPC_MMA_MINB)
+__global__ void __launch_bounds__(WPB * 32, ALMPC_MMA_MINB * 4 / WPB)
 k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restrict__ q_g, const S* __restrict__ xu_g,
                    S* __restrict__ lam_g, S* __restrict__ rho_g, S* fac_g, const S* __restrict__ G_g,
                    const S* __restrict__ c_g, S* __restrict__ d_g, S* __restrict__ merit_g,

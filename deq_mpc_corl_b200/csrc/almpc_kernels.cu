@@ -201,7 +201,10 @@ static auto pair_kernel() -> decltype(&k_factor_solve<NX, NU, S, kWPB, V>) {
   else return nullptr;
 }
 // the fragment-layout factor kernel (almpc_factor_mma.cuh) is written for 16-wide blocks (quadrotor)
-constexpr int kWPM = 4;  // warps = problems per CTA
+#ifndef ALMPC_MMA_WPB
+#define ALMPC_MMA_WPB 4
+#endif
+constexpr int kWPM = ALMPC_MMA_WPB;  // warps = problems per CTA of the fragment-layout factor kernel
 template <int NX, int NU, typename S, int V>
 static auto mma_kernel() -> decltype(&k_factor_solve<NX, NU, S, kWPB, V>) {
   if constexpr (NX + NU == 16 && NX >= 8 && NX < 16 && NX % 4 == 0 && V != 1) return &k_factor_solve_mma<NX, NU, S, kWPM, V>;

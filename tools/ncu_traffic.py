@@ -40,7 +40,7 @@ for (_, name), m in launches.items():
         continue
     per.setdefault(name, []).append((byts, m.get("dram__bytes_read.sum", 0.0), m.get("dram__bytes_write.sum", 0.0), m.get("gpu__time_duration.sum", 0.0)))
     total += byts
-alias = {"k_factor_solve_pair": "k_factor_solve", "k_line_search_warp": "k_line_search"}
+alias = {"k_factor_solve_pair": "k_factor_solve", "k_factor_solve_mma": "k_factor_solve", "k_line_search_warp": "k_line_search"}
 out = {"source": path, "solve_dram_bytes_per_problem": total / B, "solve_dram_bytes": total}
 for name, v in per.items():
     out[alias.get(name, name)] = statistics.median(x[0] for x in v)
