@@ -23,7 +23,8 @@ namespace almpc {
 template <int NX, int NU, typename S>
 struct MmaLayout {
   static constexpr int NN = NX + NU;
-  static constexpr int LDG = NN + 16 / (int)sizeof(S);  // staged G rows stay 16-byte multiples
+  static constexpr bool COPY16 = (NN * sizeof(S)) % 16 == 0;  // rows of G are 16-byte multiples: chunked copies
+  static constexpr int LDG = COPY16 ? NN + 16 / (int)sizeof(S) : NN + 1;  // padded row stride of the staged G block
   int N, neq, nin, m;
   int dv, dg, bc, gs0, gs1, lsm, total;  // byte offsets (every region 16-byte aligned)
   int xu, w, lin;                        // prologue-only arrays (double), aliased with lsm
@@ -45,47 +46,75 @@ struct MmaLayout {
   }
 };
 
-// [ROWS][NN] block, contiguous in global memory -> shared rows of stride LD (16-byte chunks)
+#ifndef ALMPC_MMA_MINB
+#define ALMPC_MMA_MINB 5  // 16-wide blocks: 5 CTAs x 4 warps per SM (96 registers)
+#endif
+// [ROWS][NN] block, contiguous in global memory -> shared rows of stride LD: 16-byte chunks where the rows are 16-byte
+// multiples, element-wise otherwise
 template <int ROWS, int NN, int LD, typename S>
-__device__ __forceinline__ void warp_copy_rows16_async(S* dst, const S* src, int lane) {
-  constexpr int CPR = NN * (int)sizeof(S) / 16;
-  static_assert((NN * sizeof(S)) % 16 == 0 && (LD * sizeof(S)) % 16 == 0, "rows must be 16-byte multiples");
-  constexpr int CH = ROWS * CPR;
-  if constexpr (LD == NN) {  // contiguous on both sides
+__device__ __forceinline__ void warp_copy_rows_async(S* dst, const S* src, int lane) {
+  if constexpr ((NN * sizeof(S)) % 16 == 0 && (LD * sizeof(S)) % 16 == 0) {
+    constexpr int CPR = NN * (int)sizeof(S) / 16;
+    constexpr int CH = ROWS * CPR;
+    if constexpr (32 % CPR == 0) {  // a lane keeps its chunk column: one address computation, then constant steps
+      const int r0 = lane / CPR, c = lane % CPR;
+      char* d0 = (char*)(dst + r0 * LD) + c * 16;
+      const char* s0 = (const char*)(src + r0 * NN) + c * 16;
 #pragma unroll
-    for (int k = 0; k < (CH + 31) / 32; ++k)
-      if (CH % 32 == 0 || lane + 32 * k < CH) cp_async16((char*)dst + (lane + 32 * k) * 16, (const char*)src + (lane + 32 * k) * 16);
+      for (int k = 0; k < (CH + 31) / 32; ++k)
+        if (CH % 32 == 0 || lane + 32 * k < CH)
+          cp_async16(d0 + k * (32 / CPR) * LD * (int)sizeof(S), s0 + k * (32 / CPR) * NN * (int)sizeof(S));
+    } else {
+#pragma unroll
+      for (int k = 0; k < (CH + 31) / 32; ++k) {
+        const int ch = lane + 32 * k, r = ch / CPR, c = ch - r * CPR;
+        if (ch < CH) cp_async16((char*)(dst + r * LD) + c * 16, (const char*)(src + r * NN) + c * 16);
+      }
+    }
   } else {
-    static_assert(32 % CPR == 0, "a lane keeps its chunk column");
-    const int r0 = lane / CPR, c = lane % CPR;
-    char* d0 = (char*)(dst + r0 * LD) + c * 16;
-    const char* s0 = (const char*)(src + r0 * NN) + c * 16;
+    warp_copy_block_async<ROWS, NN, LD>(dst, src, lane);
+  }
+}
+// COUNT contiguous scalars, copy width W bytes (CopyWidth: the widest size that divides every block of the factor)
+template <int COUNT, int W, typename S>
+__device__ __forceinline__ void warp_copy_contig_async(S* dst, const S* src, int lane) {
+  constexpr int CH = COUNT * (int)sizeof(S) / W;
+  static_assert((COUNT * sizeof(S)) % W == 0, "copy width must divide the block");
 #pragma unroll
-    for (int k = 0; k < (CH + 31) / 32; ++k)
-      if (CH % 32 == 0 || lane + 32 * k < CH)
-        cp_async16(d0 + k * (32 / CPR) * LD * (int)sizeof(S), s0 + k * (32 / CPR) * NN * (int)sizeof(S));
+  for (int k = 0; k < (CH + 31) / 32; ++k) {
+    const int o = (lane + 32 * k) * W;
+    if (CH % 32 == 0 || lane + 32 * k < CH) {
+      if constexpr (W == 16) cp_async16((char*)dst + o, (const char*)src + o);
+      else if constexpr (W == 8) cp_async8((char*)dst + o, (const char*)src + o);
+      else cp_async4((char*)dst + o, (const char*)src + o);
+    }
   }
 }
 
-#ifndef ALMPC_MMA_MINB
-#define ALMPC_MMA_MINB 5  // CTAs of 4 warps per SM the kernel is compiled for (96 registers)
-#endif
+constexpr __host__ __device__ int mma_dt(int rt, int ct) { return rt * (rt + 1) / 2 + ct; }  // lower tile (rt, ct) of D_t
+// CTAs (of 4 warps) per SM the kernel is compiled for, by the number of 8-column tiles of a block
+constexpr int mma_minb(int nt) { return nt == 1 ? 6 : (nt == 2 ? ALMPC_MMA_MINB : 3); }
 
 template <int NX, int NU, typename S, int WPB, int V>
-__global__ void __launch_bounds__(WPB * 32, ALMPC_MMA_MINB * 4 / WPB)
+__global__ void __launch_bounds__(WPB * 32, mma_minb((NX + NU + 7) / 8) * 4 / WPB)
 k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __restrict__ q_g, const S* __restrict__ xu_g,
                    S* __restrict__ lam_g, S* __restrict__ rho_g, S* fac_g, const S* __restrict__ G_g,
                    const S* __restrict__ c_g, S* __restrict__ d_g, S* __restrict__ merit_g,
                    double* __restrict__ rentry_g, int* __restrict__ status_g, S* __restrict__ debug_g,
                    const Ctl* __restrict__ ctl) {
   constexpr int NN = NX + NU;
-  static_assert(NN == 16 && NX >= 8 && NX < 16 && NX % 4 == 0, "tile mapping written for n = 16, 8 <= nx <= 12");
+  constexpr int NT = (NN + 7) / 8;     // 8-column tiles of a block (padding: identity)
+  constexpr int NP = (NN + 3) / 4;     // panels of the elimination = k-chunks of a contraction over the columns
+  constexpr int KG = (NX + 3) / 4;     // k-chunks of the contraction over the rows of G_t
+  constexpr int NTE = (NX + 8) / 8;    // row tiles of the extra rows: nx rows of -rho G_t, then the right-hand side
+  constexpr int NTX = (NX + 7) / 8;    // tiles of the x-x part of D_t (what E E^T touches)
+  constexpr int XR = NX / 8, RHS = NX % 8;  // extra tile / logical in-tile row of the right-hand side
+  static_assert(NT <= 3 && NTE <= 2 && NTE <= NT, "tile mapping: n <= 24, nx + 1 <= 16");
   static_assert(V != 1, "obstacle rows are compiled for the row-per-lane kernel only");
   constexpr bool SE = (V == 2);
   constexpr int SI = 2 * NU;
-  constexpr int KG = NX / 4;                    // k-chunks of the contraction over the rows of G_t
   constexpr int LDG = MmaLayout<NX, NU, S>::LDG;
-  constexpr int RHS = NX & 7;                   // logical in-tile row of the right-hand side (extra row NX, tile 1)
+  constexpr int CW = CopyWidth<NX, NU, S>::W;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_ring;
   grid_dep_wait();
@@ -122,7 +151,7 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
                             : fac_g + (size_t)prob * factor_elems<NX, NU>(T);
   S* dbg = debug_g ? debug_g + (size_t)prob * (2 * L.N + 24) : nullptr;
 
-  if (T > 1) warp_copy_rows16_async<NX, NN, LDG>(Gs0, Gp, lane);
+  if (T > 1) warp_copy_rows_async<NX, NN, LDG>(Gs0, Gp, lane);
   cp_async_commit();
   S rho_s = rho_g[prob];
   // ---- prologue: dual / penalty update of the previous AL iteration (AL_mpc.py:316-317,325), entry residual
@@ -227,9 +256,11 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
   __syncwarp();
 
   // ---- forward sweep over the stages
-  double Ep[4][2];  // E_{t-1} (+ y_{t-1} in the right-hand-side row): [k-chunk][extra tile], A/B fragments
+  double Ep[NP][NTE];  // E_{t-1} (+ y_{t-1} in the right-hand-side row): [k-chunk][extra tile], A/B fragments
 #pragma unroll
-  for (int p = 0; p < 4; ++p) Ep[p][0] = Ep[p][1] = 0.0;
+  for (int p = 0; p < NP; ++p)
+#pragma unroll
+    for (int xt = 0; xt < NTE; ++xt) Ep[p][xt] = 0.0;
   S* Gc = Gs0;
   S* Gn = Gs1;
   const bool isdiag = (q == r4);
@@ -240,83 +271,99 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
     const bool has_G = t < T - 1, has_E = t > 0;
     cp_async_wait_all();
     __syncwarp();
-    double Dt[3][2];     // tiles (0,0) (1,0) (1,1) of D_t
-    double X[2][2][2];   // extra rows: [extra tile][column tile][reg]: -rho G_t | rhs | 0
+    double Dt[NT * (NT + 1) / 2][2];  // lower tiles of D_t
+    double X[NTE][NT][2];             // extra rows: [extra tile][column tile][reg]: -rho G_t | rhs | 0
 #pragma unroll
-    for (int i = 0; i < 3; ++i) Dt[i][0] = Dt[i][1] = 0.0;
-    double rw[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // w^T G_t in the right-hand-side row
+    for (int i = 0; i < NT * (NT + 1) / 2; ++i) Dt[i][0] = Dt[i][1] = 0.0;
+    double rw[NT][2];  // w^T G_t in the right-hand-side row
+#pragma unroll
+    for (int ct = 0; ct < NT; ++ct) rw[ct][0] = rw[ct][1] = 0.0;
     if (has_G) {
-      double f[2][KG];
+      double f[NT][KG];
 #pragma unroll
-      for (int tl = 0; tl < 2; ++tl)
+      for (int tl = 0; tl < NT; ++tl)
 #pragma unroll
-        for (int kk = 0; kk < KG; ++kk) f[tl][kk] = (double)Gc[(4 * kk + q) * LDG + 8 * tl + pg];
+        for (int kk = 0; kk < KG; ++kk) {
+          const int row = 4 * kk + q, col = 8 * tl + pg;
+          f[tl][kk] = ((NX % 4 == 0 || row < NX) && (NN % 8 == 0 || col < NN)) ? (double)Gc[row * LDG + col] : 0.0;
+        }
 #pragma unroll
       for (int kk = 0; kk < KG; ++kk) {
-        dmma884(Dt[0][0], Dt[0][1], f[0][kk], f[0][kk]);
-        dmma884(Dt[1][0], Dt[1][1], f[1][kk], f[0][kk]);
-        dmma884(Dt[2][0], Dt[2][1], f[1][kk], f[1][kk]);
-        const double wa = rhs_lane ? wv[t * NX + 4 * kk + q] : 0.0;
-        dmma884(rw[0][0], rw[0][1], wa, f[0][kk]);
-        dmma884(rw[1][0], rw[1][1], wa, f[1][kk]);
+#pragma unroll
+        for (int rt = 0; rt < NT; ++rt)
+#pragma unroll
+          for (int ct = 0; ct <= rt; ++ct) dmma884(Dt[mma_dt(rt, ct)][0], Dt[mma_dt(rt, ct)][1], f[rt][kk], f[ct][kk]);
+        const double wa = (rhs_lane && (NX % 4 == 0 || 4 * kk + q < NX)) ? wv[t * NX + 4 * kk + q] : 0.0;
+#pragma unroll
+        for (int ct = 0; ct < NT; ++ct) dmma884(rw[ct][0], rw[ct][1], wa, f[ct][kk]);
       }
     }
-    {
-      const double d0 = dg[t * NN + pg], d1 = dg[t * NN + 8 + pg];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) { Dt[i][0] *= rho; Dt[i][1] *= rho; }
+    for (int i = 0; i < NT * (NT + 1) / 2; ++i) { Dt[i][0] *= rho; Dt[i][1] *= rho; }
+#pragma unroll
+    for (int rt = 0; rt < NT; ++rt) {
+      const double dd = (NN % 8 == 0 || 8 * rt + pg < NN) ? dg[t * NN + 8 * rt + pg] : 1.0;  // padding: identity
       if (isdiag) {
-        if (odd) { Dt[0][1] += d0; Dt[2][1] += d1; }
-        else { Dt[0][0] += d0; Dt[2][0] += d1; }
+        if (odd) Dt[mma_dt(rt, rt)][1] += dd;
+        else Dt[mma_dt(rt, rt)][0] += dd;
       }
     }
 #pragma unroll
-    for (int xt = 0; xt < 2; ++xt)
+    for (int xt = 0; xt < NTE; ++xt)
 #pragma unroll
-      for (int ct = 0; ct < 2; ++ct)
+      for (int ct = 0; ct < NT; ++ct)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int row = 8 * xt + pg, col = 8 * ct + q + 4 * e;
+          const bool cok = (NN % 8 == 0 || col < NN);
           double v = 0.0;
-          if (has_G && row < NX) v = -rho * (double)Gc[row * LDG + col];
-          if (xt == 1 && rhs_lane) {
-            v = dv[t * NN + col] - rw[ct][e];
-            if (dbg) dbg[t * NN + col] = (S)v;
+          if (has_G && row < NX && cok) v = -rho * (double)Gc[row * LDG + col];
+          if (xt == XR && rhs_lane) {
+            v = cok ? dv[t * NN + col] - rw[ct][e] : 0.0;
+            if (dbg && cok) dbg[t * NN + col] = (S)v;
           }
           X[xt][ct][e] = v;
         }
     __syncwarp();  // G_t has no reader left: prefetch G_{t+1} behind the factorisation
-    if (t + 1 < T - 1) warp_copy_rows16_async<NX, NN, LDG>(Gn, Gp + (size_t)(t + 1) * NX * NN, lane);
+    if (t + 1 < T - 1) warp_copy_rows_async<NX, NN, LDG>(Gn, Gp + (size_t)(t + 1) * NX * NN, lane);
     cp_async_commit();
     if (has_E) {
-      double sy[3][2];
+      double sy[NTE][NTX][2];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) sy[i][0] = sy[i][1] = 0.0;
+      for (int rt = 0; rt < NTE; ++rt)
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const double a0 = Ep[p][0], a1 = Ep[p][1];
-        const double b1 = (8 + pg < NX) ? a1 : 0.0;  // the y row (and the padding) is no column of E E^T
-        dmma884(sy[0][0], sy[0][1], a0, a0);
-        dmma884(sy[1][0], sy[1][1], a1, a0);
-        dmma884(sy[2][0], sy[2][1], a1, b1);
+        for (int ct = 0; ct < NTX; ++ct) sy[rt][ct][0] = sy[rt][ct][1] = 0.0;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        double bfr[NTX];
+#pragma unroll
+        for (int ct = 0; ct < NTX; ++ct) bfr[ct] = (8 * ct + pg < NX) ? Ep[p][ct] : 0.0;  // the y row (and the padding) is no column of E E^T
+#pragma unroll
+        for (int rt = 0; rt < NTE; ++rt)
+#pragma unroll
+          for (int ct = 0; ct < NTX; ++ct)
+            if (ct <= rt) dmma884(sy[rt][ct][0], sy[rt][ct][1], Ep[p][rt], bfr[ct]);
       }
-      Dt[0][0] -= sy[0][0]; Dt[0][1] -= sy[0][1];
-      if (rhs_lane) {  // row NX of the product is y_{t-1} E_{t-1}^T: the coupling of the right-hand side
-        X[1][0][0] -= sy[1][0]; X[1][0][1] -= sy[1][1];
-        X[1][1][0] -= sy[2][0]; X[1][1][1] -= sy[2][1];
-      } else {
-        Dt[1][0] -= sy[1][0]; Dt[1][1] -= sy[1][1];
-        Dt[2][0] -= sy[2][0]; Dt[2][1] -= sy[2][1];
-      }
+#pragma unroll
+      for (int rt = 0; rt < NTE; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < NTX; ++ct)
+          if (ct <= rt) {
+            if (rt == XR && rhs_lane) {  // row NX of the product is y_{t-1} E_{t-1}^T: the coupling of the right-hand side
+              X[XR][ct][0] -= sy[rt][ct][0]; X[XR][ct][1] -= sy[rt][ct][1];
+            } else {
+              Dt[mma_dt(rt, ct)][0] -= sy[rt][ct][0]; Dt[mma_dt(rt, ct)][1] -= sy[rt][ct][1];
+            }
+          }
     }
     // ---- blocked elimination, panel width 4.  Look-ahead: as soon as a panel's solve is done, the tile holding the
     // NEXT diagonal block is updated and that block is published, so that its shared-memory round trip runs under
     // the remaining trailing updates and the write-outs of this panel.
     if (!odd) bc[r4 * 4 + q] = Dt[0][0];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
+    for (int p = 0; p < NP; ++p) {
       const int tc = p >> 1, pp = p & 1;
-      const int dti = tc ? 2 : 0;
+      const bool second_half = 4 * p + 4 < NN;  // the panel's tile has real columns behind the panel
       double* bcb = bc + pp * 32;
       __syncwarp();  // the diagonal block of this panel was published by the previous panel (look-ahead)
       const double a00 = bcb[0];
@@ -356,59 +403,64 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
       const double lsel = (q <= r4) ? lraw : 0.0;
       const double wb = (odd || q > r4) ? 0.0 : wsel;
       // panel solve P = A W^T per row tile: c0 of the output is P[row][q], i.e. already the A/B fragment of the update
-      double P0 = 0.0, P1 = 0.0, PX0 = 0.0, PX1 = 0.0, junk;
-      if (p == 0) { junk = 0.0; dmma884(P0, junk, Dt[0][0], wb); }
-      if (p <= 1) { junk = 0.0; dmma884(P1, junk, Dt[1][pp], wb); }
-      if (p == 2) { junk = 0.0; dmma884(P1, junk, Dt[2][0], wb); }
-      junk = 0.0; dmma884(PX0, junk, X[0][tc][pp], wb);
-      junk = 0.0; dmma884(PX1, junk, X[1][tc][pp], wb);
+      double Pd[NT], PX[NTE], junk;
+#pragma unroll
+      for (int rt = 0; rt < NT; ++rt) {
+        Pd[rt] = 0.0;
+        if (rt > tc || (rt == tc && pp == 0 && second_half)) { junk = 0.0; dmma884(Pd[rt], junk, Dt[mma_dt(rt, tc)][pp], wb); }
+      }
+#pragma unroll
+      for (int xt = 0; xt < NTE; ++xt) { PX[xt] = 0.0; junk = 0.0; dmma884(PX[xt], junk, X[xt][tc][pp], wb); }
       // trailing update A22 -= P P^T (columns inside the panel's own tile half are masked out of the B fragment):
       // first the tile with the next diagonal block, which is published at once
-      const double nbm = odd ? -((p == 0) ? P0 : P1) : 0.0, nb1 = -P1;
-      if (p < 3) {
+      const double nbm = odd ? -Pd[tc] : 0.0;
+      if (p + 1 < NP) {
         double* bnx = bc + ((p + 1) & 1) * 32;
-        if (p == 0) {
-          dmma884(Dt[0][0], Dt[0][1], P0, nbm);
-          if (odd) bnx[r4 * 4 + q] = Dt[0][1];
-        } else if (p == 1) {
-          dmma884(Dt[2][0], Dt[2][1], P1, nb1);
-          if (!odd) bnx[r4 * 4 + q] = Dt[2][0];
+        if (pp == 0) {
+          dmma884(Dt[mma_dt(tc, tc)][0], Dt[mma_dt(tc, tc)][1], Pd[tc], nbm);
+          if (odd) bnx[r4 * 4 + q] = Dt[mma_dt(tc, tc)][1];
         } else {
-          dmma884(Dt[2][0], Dt[2][1], P1, nbm);
-          if (odd) bnx[r4 * 4 + q] = Dt[2][1];
+          const int tn = tc + 1 < NT ? tc + 1 : tc;
+          dmma884(Dt[mma_dt(tn, tn)][0], Dt[mma_dt(tn, tn)][1], Pd[tn], -Pd[tn]);
+          if (!odd) bnx[r4 * 4 + q] = Dt[mma_dt(tn, tn)][0];
         }
       }
-      if (p == 0) {
-        dmma884(Dt[1][0], Dt[1][1], P1, nbm);
-        dmma884(X[0][0][0], X[0][0][1], PX0, nbm);
-        dmma884(X[1][0][0], X[1][0][1], PX1, nbm);
-        dmma884(Dt[2][0], Dt[2][1], P1, nb1);
-        dmma884(X[0][1][0], X[0][1][1], PX0, nb1);
-        dmma884(X[1][1][0], X[1][1][1], PX1, nb1);
-      } else if (p == 1) {
-        dmma884(X[0][1][0], X[0][1][1], PX0, nb1);
-        dmma884(X[1][1][0], X[1][1][1], PX1, nb1);
-      } else if (p == 2) {
-        dmma884(X[0][1][0], X[0][1][1], PX0, nbm);
-        dmma884(X[1][1][0], X[1][1][1], PX1, nbm);
+      if (pp == 0 && second_half) {
+#pragma unroll
+        for (int rt = 0; rt < NT; ++rt)
+          if (rt > tc) dmma884(Dt[mma_dt(rt, tc)][0], Dt[mma_dt(rt, tc)][1], Pd[rt], nbm);
+#pragma unroll
+        for (int xt = 0; xt < NTE; ++xt) dmma884(X[xt][tc][0], X[xt][tc][1], PX[xt], nbm);
       }
+#pragma unroll
+      for (int ct = 0; ct < NT; ++ct)
+        if (ct > tc) {
+          const double nb = -Pd[ct];
+#pragma unroll
+          for (int rt = 0; rt < NT; ++rt)
+            if (rt >= ct && !(pp == 1 && rt == tc + 1 && ct == tc + 1))  // (that tile went first)
+              dmma884(Dt[mma_dt(rt, ct)][0], Dt[mma_dt(rt, ct)][1], Pd[rt], nb);
+#pragma unroll
+          for (int xt = 0; xt < NTE; ++xt) dmma884(X[xt][ct][0], X[xt][ct][1], PX[xt], nb);
+        }
       // write-outs: L rows (zeros above the diagonal, 1/L_ii on it), E_t rows, y_t
-      {
-        double v0, v1;
-        if (p == 0) { v0 = odd ? P0 : lsel; v1 = P1; }
-        else if (p == 1) { v0 = odd ? lsel : 0.0; v1 = P1; }
-        else if (p == 2) { v0 = 0.0; v1 = odd ? P1 : lsel; }
-        else { v0 = 0.0; v1 = odd ? lsel : 0.0; }
-        Lg[pg * NN + 4 * p + q] = (S)v0;
-        Lg[(8 + pg) * NN + 4 * p + q] = (S)v1;
-        if (has_G) {
-          Eg[pg * NN + 4 * p + q] = (S)PX0;
-          if (8 + pg < NX) Eg[(8 + pg) * NN + 4 * p + q] = (S)PX1;
-        }
-        if (rhs_lane) dv[t * NN + 4 * p + q] = PX1;
+      const bool pcol = (NN % 4 == 0 || 4 * p + q < NN);
+#pragma unroll
+      for (int rt = 0; rt < NT; ++rt) {
+        double v;
+        if (rt < tc) v = 0.0;
+        else if (rt == tc) v = (pp == 0) ? (odd ? Pd[tc] : lsel) : (odd ? lsel : 0.0);
+        else v = Pd[rt];
+        if (pcol && (NN % 8 == 0 || 8 * rt + pg < NN)) Lg[(8 * rt + pg) * NN + 4 * p + q] = (S)v;
       }
-      Ep[p][0] = PX0;
-      Ep[p][1] = PX1;
+      if (has_G) {
+#pragma unroll
+        for (int xt = 0; xt < NTE; ++xt)
+          if (pcol && 8 * xt + pg < NX) Eg[(8 * xt + pg) * NN + 4 * p + q] = (S)PX[xt];
+      }
+      if (rhs_lane && pcol) dv[t * NN + 4 * p + q] = PX[XR];
+#pragma unroll
+      for (int xt = 0; xt < NTE; ++xt) Ep[p][xt] = PX[xt];
     }
     S* tmp = Gc; Gc = Gn; Gn = tmp;
   }
@@ -419,8 +471,8 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
   S* Ecur = Gc;
   S* Enext = Gn;
   auto fetch = [&](int t, bool with_E) {
-    warp_copy_rows16_async<NN, NN, NN>(Lsm, fac + (size_t)t * NN * NN, lane);
-    if (with_E) warp_copy_rows16_async<NX, NN, NN>(Enext, fac + (size_t)T * NN * NN + (size_t)t * NX * NN, lane);
+    warp_copy_contig_async<NN * NN, CW>(Lsm, fac + (size_t)t * NN * NN, lane);
+    if (with_E) warp_copy_contig_async<NX * NN, CW>(Enext, fac + (size_t)T * NN * NN + (size_t)t * NX * NN, lane);
   };
   fetch(T - 1, false);
   cp_async_commit();
@@ -428,8 +480,8 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
     cp_async_wait_all();
     __syncwarp();
     // lane j < n owns column j of L^T.  Its own 1/L_jj is taken out of the staged block (and replaced by 0), so the
-    // column needs no masks: the stored factor has zeros above the diagonal.  Lanes >= n shadow lanes 0..n-1.
-    const int jc = lane & (NN - 1);
+    // column needs no masks: the stored factor has zeros above the diagonal.  Lanes >= n shadow column 0.
+    const int jc = (lane < NN) ? lane : 0;
     const double inv = (double)Lsm[jc * NN + jc];
     if (lane < NN) Lsm[jc * NN + jc] = S(0);
     double l[NN];
@@ -443,6 +495,7 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
         s0 += (double)Ecur[i * NN + lane] * dv[(t + 1) * NN + i];
         s1 += (double)Ecur[(i + 1) * NN + lane] * dv[(t + 1) * NN + i + 1];
       }
+      if (NX & 1) s0 += (double)Ecur[(NX - 1) * NN + lane] * dv[(t + 1) * NN + NX - 1];
       bb -= s0 + s1;
     }
     __syncwarp();

@@ -200,14 +200,16 @@ static auto pair_kernel() -> decltype(&k_factor_solve<NX, NU, S, kWPB, V>) {
   if constexpr (NX + NU <= 16 && NX + 1 <= 16 && V != 1) return &k_factor_solve_pair<NX, NU, S, kWPP, V>;
   else return nullptr;
 }
-// the fragment-layout factor kernel (almpc_factor_mma.cuh) is written for 16-wide blocks (quadrotor)
+// the fragment-layout factor kernel (almpc_factor_mma.cuh): blocks up to 24 wide, nx + 1 <= 16, no obstacle rows
 #ifndef ALMPC_MMA_WPB
 #define ALMPC_MMA_WPB 4
 #endif
 constexpr int kWPM = ALMPC_MMA_WPB;  // warps = problems per CTA of the fragment-layout factor kernel
+template <int NX, int NU>
+constexpr bool mma_applies(int V) { return NX + NU <= 24 && NX + 1 <= 16 && V != 1; }
 template <int NX, int NU, typename S, int V>
 static auto mma_kernel() -> decltype(&k_factor_solve<NX, NU, S, kWPB, V>) {
-  if constexpr (NX + NU == 16 && NX >= 8 && NX < 16 && NX % 4 == 0 && V != 1) return &k_factor_solve_mma<NX, NU, S, kWPM, V>;
+  if constexpr (mma_applies<NX, NU>(V)) return &k_factor_solve_mma<NX, NU, S, kWPM, V>;
   else return nullptr;
 }
 template <typename S>
@@ -258,11 +260,13 @@ static int make_plan(Plan& pl, int dev, int T, int n_obs, int select) {
   pl.fac_threads = kWPB * 32; pl.fac_per_cta = kWPB;
   pl.use_pair = pl.fused = pl.use_mma = false;
   if (auto km = mma_kernel<NX, NU, S, V>(); km && !(select & (ALMPC_SELECT_FAC_PAIR | ALMPC_SELECT_FAC_SINGLE | ALMPC_SELECT_FUSE)) &&
-                                               (sizeof(S) == 8 || (select & ALMPC_SELECT_FAC_MMA))) {
-    // fp64: 0.64 vs 0.88 ms per launch at 64K quadrotor problems (0.095 vs 0.137 ms at 8K).  fp32 problems keep the
-    // half-warp kernel by default: it factors in fp32 registers at 10 CTAs/SM (0.553 ms) while this kernel keeps its
-    // blocks in FP64 accumulators whatever the interface type (0.620 ms) — selectable for its accuracy (no lost pivots)
-    if constexpr (NX + NU == 16) {
+                                               ((sizeof(S) == 8 && NX + NU > 8) || (select & ALMPC_SELECT_FAC_MMA))) {
+    // Default for fp64 problems with blocks wider than 8 (measured per launch, B200): quadrotor 64K 0.63 vs 0.88 ms (8K:
+    // 0.095 vs 0.137 ms), flying cartpole T=10 16K 0.61 vs 0.95 ms.  Blocks that fit one 8x8 tile (pendulum, cartpoles)
+    // keep the half-warp kernel (64K problems: 0.170 / 0.226 / 0.297 ms against 0.184 / 0.271 / 0.311 ms), and so do
+    // fp32 problems: it factors in fp32 registers at 10 CTAs/SM (quadrotor 0.553 ms) while this kernel keeps its blocks
+    // in FP64 accumulators whatever the interface type (0.620 ms) — selectable for its accuracy (no lost pivots).
+    if constexpr (mma_applies<NX, NU>(V)) {
       const size_t smem_mma = (size_t)kWPM * MmaLayout<NX, NU, S>(T, SE).total;
       if (smem_mma + 1024 <= 227 * 1024 && allow_max_smem(km, optin) == cudaSuccess) {
         pl.use_mma = true;

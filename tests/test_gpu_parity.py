@@ -731,15 +731,21 @@ def test_fused_newton_tail_equals_three_kernel_path(model, T, B, se, monkeypatch
             assert torch.equal(ta, tb)
 
 
-@pytest.mark.parametrize("T,B,se,dtype", [(5, 131, False, torch.float64), (2, 1, False, torch.float64),
-                                          (9, 67, True, torch.float64), (17, 40, False, torch.float64),
-                                          (5, 257, False, torch.float32), (4, 33, True, torch.float32)])
-def test_fragment_layout_factor_kernel_matches_half_warp_kernel(T, B, se, dtype, monkeypatch):
-    """k_factor_solve_mma (blocked Cholesky in FP64-MMA fragment layout, the default for the 16-wide quadrotor blocks)
-    against k_factor_solve_pair (ALMPC_SELECT_FAC_PAIR: right-looking, one row per lane) over two chained calls (the
-    second runs the fused dual update): same Newton-step counts and status, iterates / multipliers / gradients equal to
-    rounding.  The two kernels order their floating-point operations differently, so bit-identity is not expected."""
-    model = "rex_quadrotor"
+@pytest.mark.parametrize("model,T,B,se,dtype", [
+    ("rex_quadrotor", 5, 131, False, torch.float64), ("rex_quadrotor", 2, 1, False, torch.float64),
+    ("rex_quadrotor", 9, 67, True, torch.float64), ("rex_quadrotor", 17, 40, False, torch.float64),
+    ("rex_quadrotor", 5, 257, False, torch.float32), ("rex_quadrotor", 4, 33, True, torch.float32),
+    ("flying_cartpole", 10, 65, False, torch.float64), ("flying_cartpole", 3, 7, True, torch.float64),
+    ("flying_cartpole", 6, 33, False, torch.float32), ("pendulum", 5, 77, False, torch.float64),
+    ("cartpole1l", 12, 31, False, torch.float64), ("cartpole2l", 7, 19, True, torch.float64),
+    ("cartpole1l", 5, 40, False, torch.float32)])
+def test_fragment_layout_factor_kernel_matches_half_warp_kernel(model, T, B, se, dtype, monkeypatch):
+    """k_factor_solve_mma (blocked Cholesky in FP64-MMA fragment layout: the default for fp64 blocks wider than 8 —
+    quadrotor, flying cartpole — and selectable everywhere, ALMPC_SELECT_FAC_MMA: 1, 2 and 3 column tiles, padded
+    blocks) against the right-looking row-per-lane kernels (ALMPC_SELECT_FAC_PAIR, which falls back to k_factor_solve
+    where the half-warp mapping does not apply) over two chained calls (the second runs the fused dual update): same
+    Newton-step counts and status, iterates / multipliers / gradients equal to rounding.  The kernels order their
+    floating-point operations differently, so bit-identity is not expected."""
     spec = MODEL_SPECS[model]
     inp = make_inputs(model, T, B, 909 + T)
     dyn = make_dyn(model, dt=spec["dt"])
@@ -762,7 +768,8 @@ def test_fragment_layout_factor_kernel_matches_half_warp_kernel(T, B, se, dtype,
             x_ref[:, 0] = inp["x0"]
         return out
 
-    tol = 1e-9 if dtype == torch.float64 else 2e-3
+    # (rounding differences grow with the conditioning of H: 2e-8 in the multipliers of the pendulum's second call)
+    tol = 1e-6 if dtype == torch.float64 else 2e-3
     for ci, (a, b) in enumerate(zip(chain(False), chain(True))):
         assert a[4] == b[4], (ci, a[4], b[4])
         assert torch.equal(a[3], b[3])

@@ -1,6 +1,8 @@
-"""Differential stress test: the half-warp-per-problem and the row-per-lane factor kernels on random (model, T, B,
-variant) draws, two chained calls each (the second runs the fused dual update): same Newton-step counts, iterates /
-multipliers / gradients equal to rounding.  python tools/diff_kernels.py [n_draws]"""
+"""Differential stress test: the default factor kernel (fragment layout, k_factor_solve_mma, where it applies) against
+the row-per-lane kernel (ALMPC_FAC_SINGLE) — or, with a second argument `pair`, against the half-warp-per-problem
+kernel (ALMPC_FAC_PAIR) — on random (model, T, B, variant) draws, two chained calls each (the second runs the fused
+dual update): same Newton-step counts and status, iterates / multipliers / gradients equal to rounding.
+python tools/diff_kernels.py [n_draws [pair]]"""
 import os, random, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
@@ -14,8 +16,9 @@ dev = "cuda:0"
 
 def run(model, T, B, seed, se, single):
     os.environ.pop("ALMPC_FAC_SINGLE", None)
+    os.environ.pop("ALMPC_FAC_PAIR", None)
     if single:
-        os.environ["ALMPC_FAC_SINGLE"] = "1"
+        os.environ[OTHER] = "1"
     spec = MODEL_SPECS[model]
     inp = make_inputs(model, T, B, seed)
     dyn = make_dyn(model, dt=spec["dt"])
@@ -40,10 +43,11 @@ def rel(a, b):
 
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+OTHER = "ALMPC_FAC_PAIR" if len(sys.argv) > 2 and sys.argv[2] == "pair" else "ALMPC_FAC_SINGLE"
 rng = random.Random(2024)
 worst = 0.0
 for i in range(n):
-    model = rng.choice(["pendulum", "cartpole1l", "cartpole2l", "rex_quadrotor"])
+    model = rng.choice(["pendulum", "cartpole1l", "cartpole2l", "rex_quadrotor", "flying_cartpole"])
     T = rng.choice([2, 3, 4, 5, 6, 7, 9, 12, 17, 24])
     B = rng.choice([1, 2, 3, 5, 31, 64, 127, 500, 1025])
     se = rng.random() < 0.25
