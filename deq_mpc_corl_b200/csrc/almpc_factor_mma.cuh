@@ -46,6 +46,9 @@ struct MmaLayout {
   }
 };
 
+#ifndef ALMPC_MMA3_MINB
+#define ALMPC_MMA3_MINB 4  // 17..24-wide blocks (flying cartpole): 128 registers; 3 CTAs (164 registers) 0.606 vs 0.541 ms
+#endif
 #ifndef ALMPC_MMA_MINB
 #define ALMPC_MMA_MINB 5  // 16-wide blocks: 5 CTAs x 4 warps per SM (96 registers)
 #endif
@@ -93,7 +96,7 @@ __device__ __forceinline__ void warp_copy_contig_async(S* dst, const S* src, int
 
 constexpr __host__ __device__ int mma_dt(int rt, int ct) { return rt * (rt + 1) / 2 + ct; }  // lower tile (rt, ct) of D_t
 // CTAs (of 4 warps) per SM the kernel is compiled for, by the number of 8-column tiles of a block
-constexpr int mma_minb(int nt) { return nt == 1 ? 6 : (nt == 2 ? ALMPC_MMA_MINB : 3); }
+constexpr int mma_minb(int nt) { return nt == 1 ? 6 : (nt == 2 ? ALMPC_MMA_MINB : ALMPC_MMA3_MINB); }
 
 template <int NX, int NU, typename S, int WPB, int V>
 __global__ void __launch_bounds__(WPB * 32, mma_minb((NX + NU + 7) / 8) * 4 / WPB)
