@@ -94,6 +94,18 @@ __device__ __forceinline__ void warp_copy_contig_async(S* dst, const S* src, int
   }
 }
 
+// D = A B with a zero accumulator (the first MMA of a chain: no registers to clear first)
+__device__ __forceinline__ void dmma884z(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+               : "=d"(d0), "=d"(d1)
+               : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+// first MMA of a chain (compile-time flag after unrolling) or accumulation
+__device__ __forceinline__ void dmma884f(bool first, double& c0, double& c1, double a, double b) {
+  if (first) dmma884z(c0, c1, a, b);
+  else dmma884(c0, c1, a, b);
+}
+
 constexpr __host__ __device__ int mma_dt(int rt, int ct) { return rt * (rt + 1) / 2 + ct; }  // lower tile (rt, ct) of D_t
 // CTAs (of 4 warps) per SM the kernel is compiled for, by the number of 8-column tiles of a block
 constexpr int mma_minb(int nt) { return nt == 1 ? 6 : (nt == 2 ? ALMPC_MMA_MINB : ALMPC_MMA3_MINB); }
@@ -295,10 +307,10 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
 #pragma unroll
         for (int rt = 0; rt < NT; ++rt)
 #pragma unroll
-          for (int ct = 0; ct <= rt; ++ct) dmma884(Dt[mma_dt(rt, ct)][0], Dt[mma_dt(rt, ct)][1], f[rt][kk], f[ct][kk]);
+          for (int ct = 0; ct <= rt; ++ct) dmma884f(kk == 0, Dt[mma_dt(rt, ct)][0], Dt[mma_dt(rt, ct)][1], f[rt][kk], f[ct][kk]);
         const double wa = (rhs_lane && (NX % 4 == 0 || 4 * kk + q < NX)) ? wv[t * NX + 4 * kk + q] : 0.0;
 #pragma unroll
-        for (int ct = 0; ct < NT; ++ct) dmma884(rw[ct][0], rw[ct][1], wa, f[ct][kk]);
+        for (int ct = 0; ct < NT; ++ct) dmma884f(kk == 0, rw[ct][0], rw[ct][1], wa, f[ct][kk]);
       }
     }
 #pragma unroll
@@ -345,7 +357,7 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
         for (int rt = 0; rt < NTE; ++rt)
 #pragma unroll
           for (int ct = 0; ct < NTX; ++ct)
-            if (ct <= rt) dmma884(sy[rt][ct][0], sy[rt][ct][1], Ep[p][rt], bfr[ct]);
+            if (ct <= rt) dmma884f(p == 0, sy[rt][ct][0], sy[rt][ct][1], Ep[p][rt], bfr[ct]);
       }
 #pragma unroll
       for (int rt = 0; rt < NTE; ++rt)
@@ -410,10 +422,10 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
 #pragma unroll
       for (int rt = 0; rt < NT; ++rt) {
         Pd[rt] = 0.0;
-        if (rt > tc || (rt == tc && pp == 0 && second_half)) { junk = 0.0; dmma884(Pd[rt], junk, Dt[mma_dt(rt, tc)][pp], wb); }
+        if (rt > tc || (rt == tc && pp == 0 && second_half)) dmma884z(Pd[rt], junk, Dt[mma_dt(rt, tc)][pp], wb);
       }
 #pragma unroll
-      for (int xt = 0; xt < NTE; ++xt) { PX[xt] = 0.0; junk = 0.0; dmma884(PX[xt], junk, X[xt][tc][pp], wb); }
+      for (int xt = 0; xt < NTE; ++xt) dmma884z(PX[xt], junk, X[xt][tc][pp], wb);
       // trailing update A22 -= P P^T (columns inside the panel's own tile half are masked out of the B fragment):
       // first the tile with the next diagonal block, which is published at once
       const double nbm = odd ? -Pd[tc] : 0.0;
