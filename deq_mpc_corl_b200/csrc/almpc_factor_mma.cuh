@@ -495,13 +495,15 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
     cp_async_wait_all();
     __syncwarp();
     // lane j < n owns column j of L^T.  Its own 1/L_jj is taken out of the staged block (and replaced by 0), so the
-    // column needs no masks: the stored factor has zeros above the diagonal.  Lanes >= n shadow column 0.
-    const int jc = (lane < NN) ? lane : 0;
-    const double inv = (double)Lsm[jc * NN + jc];
-    if (lane < NN) Lsm[jc * NN + jc] = S(0);
+    // column needs no masks: the stored factor has zeros above the diagonal.  Lanes >= n idle (no loads: a warp-wide
+    // 8-byte load is two shared-memory wavefronts, one per half-warp).
+    const bool act = lane < NN;
+    const int jc = act ? lane : 0;
+    const double inv = act ? (double)Lsm[jc * NN + jc] : 0.0;
+    if (act) Lsm[jc * NN + jc] = S(0);
     double l[NN];
 #pragma unroll
-    for (int r = 0; r < NN; ++r) l[r] = (double)Lsm[r * NN + jc];
+    for (int r = 0; r < NN; ++r) l[r] = act ? (double)Lsm[r * NN + jc] : 0.0;
     double bb = (lane < NN) ? dv[t * NN + lane] : 0.0;
     if (t < T - 1 && lane < NN) {
       double s0 = 0.0, s1 = 0.0;
