@@ -825,13 +825,18 @@ def main():
     pipelined_ms(e2e_solve, h, out_h, 6)  # warm-up: the caching allocator needs a few steps to reach steady state
     barrier()
     k_pipe = max(4, args.steps)
-    e2e_ms = pipelined_ms(e2e_solve, h, out_h, k_pipe)
+    # two passes like the device-timed value (a one-off stall of tens of ms halves a 20 ms pass at 8K problems per GPU)
+    e2e_passes = []
+    for _ in range(2):
+        e2e_passes.append(max_over_ranks(pipelined_ms(e2e_solve, h, out_h, k_pipe)))
+        barrier()
+    e2e_ms = min(e2e_passes)
     # the overlapped copies must deliver exactly what the serial path delivers (same inputs every step)
     e2e_verified = all(torch.equal(out_h[k], serial_out[k]) for k in out_h)
     if not e2e_verified:
         raise RuntimeError("pipelined e2e results differ from the serial e2e results")
     barrier()
-    e2e_ms, e2e_serial_ms = max_over_ranks(e2e_ms), max_over_ranks(e2e_serial_ms)
+    e2e_serial_ms = max_over_ranks(e2e_serial_ms)
 
     # ---- e2e one level up: Tracking_MPC (the reference's actual caller, policies.py:1117-1315): host inputs are
     # the fp32 network outputs (x0, x_ref, u_ref) + output grads; the cost build and its chain rule run fused
@@ -899,6 +904,7 @@ def main():
             "value_passes_ms": [round(p[0], 3) for p in passes],  # both K-step passes (max over ranks); value = the faster
             "e2e": {"value": k_pipe * GB / (e2e_ms * 1e-3), "unit": "solves/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms / k_pipe, "steps": k_pipe, "matches_serial": e2e_verified,
+                    "passes_ms": [round(v, 3) for v in e2e_passes],  # both passes of `steps` end-to-end steps; value = the faster
                     "api": "deq_mpc_corl_b200.al_mpc.MPC.forward + autograd backward; every step copies its inputs "
                            "from pinned host buffers and its results back, double-buffered: the H2D of step j+1 and the "
                            "D2H of step j-1 run on copy streams under the solve of step j",

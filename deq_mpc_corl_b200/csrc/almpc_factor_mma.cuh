@@ -27,9 +27,9 @@ struct MmaLayout {
   static constexpr int LDG = COPY16 ? NN + 16 / (int)sizeof(S) : NN + 1;  // padded row stride of the staged G block
   int N, neq, nin, m;
   int dv, dg, bc, gs0, gs1, lsm, total;  // byte offsets (every region 16-byte aligned)
-  int xu, w, lin;                        // prologue-only arrays (double), aliased with lsm
-  __host__ __device__ MmaLayout(int T, bool se) {
-    const int SI = se ? 0 : 2 * NU;
+  int xu, w, lin, obv, hob;              // arrays the forward sweep is done with before lsm is written (double)
+  __host__ __device__ MmaLayout(int T, bool se, int nobs = 0) {
+    const int SI = se ? 0 : 2 * NU + nobs;
     N = T * NN; neq = se ? (T - 1) * NX : T * NX; nin = T * SI; m = neq + nin;
     int o = 0;
     auto take = [&](int bytes) { int at = o; o += (bytes + 15) & ~15; return at; };
@@ -38,10 +38,14 @@ struct MmaLayout {
     bc = take(64 * 8);  // per panel parity: the 4x4 diagonal block, then the table of W / L11 entries
     gs0 = take(NX * LDG * (int)sizeof(S));
     gs1 = take(NX * LDG * (int)sizeof(S));
-    const int pro = (((N + 1) & ~1) + ((neq + 1) & ~1) + ((nin + 1) & ~1)) * 8;
+    // obstacle rows (Obstacle_MPC): per (stage, obstacle) J[3], lam + rho c+, active penalty; per stage the lower 3x3
+    // of sum_k active_k rho J_k^T J_k
+    const int nov = T * nobs * 5, nho = nobs ? T * 8 : 0;
+    const int pro = (((N + 1) & ~1) + ((neq + 1) & ~1) + ((nin + 1) & ~1) + ((nov + 1) & ~1) + nho) * 8;
     const int lb = NN * NN * (int)sizeof(S);
     lsm = take(pro > lb ? pro : lb);
     xu = lsm; w = xu + ((N + 1) & ~1) * 8; lin = w + ((neq + 1) & ~1) * 8;
+    obv = lin + ((nin + 1) & ~1) * 8; hob = obv + ((nov + 1) & ~1) * 8;
     total = o;
   }
 };
@@ -125,9 +129,7 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
   constexpr int NTX = (NX + 7) / 8;    // tiles of the x-x part of D_t (what E E^T touches)
   constexpr int XR = NX / 8, RHS = NX % 8;  // extra tile / logical in-tile row of the right-hand side
   static_assert(NT <= 3 && NTE <= 2 && NTE <= NT, "tile mapping: n <= 24, nx + 1 <= 16");
-  static_assert(V != 1, "obstacle rows are compiled for the row-per-lane kernel only");
-  constexpr bool SE = (V == 2);
-  constexpr int SI = 2 * NU;
+  constexpr bool OBS = (V == 1), SE = (V == 2);  // variant: 0 plain, 1 obstacle rows, 2 state estimator
   constexpr int LDG = MmaLayout<NX, NU, S>::LDG;
   constexpr int CW = CopyWidth<NX, NU, S>::W;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -139,7 +141,9 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
   __syncthreads();
   const int ring_slot = s_ring;
   const int T = P.T;
-  const MmaLayout<NX, NU, S> L(T, SE);
+  const int n_obs = OBS ? P.n_obs : 0;
+  const int SI = OBS ? 2 * NU + n_obs : 2 * NU;  // inequality rows per stage (a compile-time constant without obstacle rows)
+  const MmaLayout<NX, NU, S> L(T, SE, n_obs);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int prob = blockIdx.x * WPB + warp;
   if (prob >= P.B) return;  // (warp 0 always has a problem, so the release below is reached)
@@ -156,6 +160,9 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
   double* xu = reinterpret_cast<double*>(sm + L.xu);
   double* wv = reinterpret_cast<double*>(sm + L.w);
   double* lin = reinterpret_cast<double*>(sm + L.lin);
+  double* obv = reinterpret_cast<double*>(sm + L.obv);
+  double* hob = reinterpret_cast<double*>(sm + L.hob);
+  const S* obs = OBS ? P.obs + (size_t)prob * T * n_obs * 3 : nullptr;
   const size_t pN = (size_t)prob * L.N;
   const S* Qd = Qd_g + pN;
   const S* qv = q_g + pN;
@@ -219,17 +226,41 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
         if (i < L.nin) {
           const int t = i / SI, sidx = i - t * SI;
           const double* z_t = xu + t * NN;
-          const S ci = (sidx < NU) ? (S)z_t[NX + sidx] - P.uhi[sidx] : P.ulo[sidx - NU] - (S)z_t[NX + sidx - NU];
+          S ci, J[3];
+          if (OBS && sidx >= 2 * NU) {  // obstacle row k of stage t: c = r^2 - |p - c_k|^2, J = -2 (p - c_k)^T
+            const S pos[3] = {(S)z_t[0], (S)z_t[1], (S)z_t[2]};
+            ci = obstacle_res<S>(pos, obs + ((size_t)t * n_obs + (sidx - 2 * NU)) * 3, P.obs_r2, J);
+          } else {
+            ci = (sidx < NU) ? (S)z_t[NX + sidx] - P.uhi[sidx] : P.ulo[sidx - NU] - (S)z_t[NX + sidx - NU];
+          }
           S li = (base == 0) ? p_li[u] : lam[L.neq + i];
           if (dual) { li = fmax0(li + rho_old * ci); lam[L.neq + i] = li; }
           lin[i] = (double)li;
           const S cp = fmax0(ci);
+          if (OBS && sidx >= 2 * NU) {
+            double* ov = obv + (t * n_obs + (sidx - 2 * NU)) * 5;
+            ov[0] = (double)J[0]; ov[1] = (double)J[1]; ov[2] = (double)J[2];
+            ov[3] = (double)(li + rho_s * cp);                   // multiplies J in the gradient (al_utils.py:113-117)
+            ov[4] = (ci >= S(0)) ? (double)rho_s : 0.0;          // multiplies J^T J in the Hessian (active rows only)
+          }
           s2 += cp * cp;
           sl += li * ci;
         }
       }
     }
     __syncwarp();
+    if constexpr (OBS) {  // + sum_k active_k rho J_k^T J_k on the position block (lower part), per stage
+      for (int e = lane; e < T * 6; e += 32) {
+        const int t = e / 6, w6 = e - t * 6;
+        const int r = (w6 < 1) ? 0 : (w6 < 3 ? 1 : 2), c = w6 - (r * (r + 1)) / 2;
+        double acc = 0.0;
+        for (int k = 0; k < n_obs; ++k) {
+          const double* ov = obv + (t * n_obs + k) * 5;
+          acc += ov[4] * ov[r] * ov[c];
+        }
+        hob[t * 8 + w6] = acc;
+      }
+    }
     for (int base = 0; base < L.N; base += 32 * U) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -254,6 +285,8 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
             gv += (lu - ll) + rho_s * (fmax0(cu) - fmax0(cl));
             dd += rho_s * ((cu >= S(0) ? S(1) : S(0)) + (cl >= S(0) ? S(1) : S(0)));
           }
+          if (OBS && j < 3)
+            for (int k = 0; k < n_obs; ++k) gv += (S)(obv[(t * n_obs + k) * 5 + 3] * obv[(t * n_obs + k) * 5 + j]);
           dv[i] = (double)gv;
           dg[i] = (double)dd;
         }
@@ -322,6 +355,9 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
         if (odd) Dt[mma_dt(rt, rt)][1] += dd;
         else Dt[mma_dt(rt, rt)][0] += dd;
       }
+    }
+    if constexpr (OBS) {  // (the 3x3 position block sits inside the first 4x4 diagonal block, whose lower part is what is read)
+      if (!odd && r4 < 3 && q <= r4) Dt[0][0] += hob[t * 8 + (r4 * (r4 + 1)) / 2 + q];
     }
 #pragma unroll
     for (int xt = 0; xt < NTE; ++xt)

@@ -200,13 +200,13 @@ static auto pair_kernel() -> decltype(&k_factor_solve<NX, NU, S, kWPB, V>) {
   if constexpr (NX + NU <= 16 && NX + 1 <= 16 && V != 1) return &k_factor_solve_pair<NX, NU, S, kWPP, V>;
   else return nullptr;
 }
-// the fragment-layout factor kernel (almpc_factor_mma.cuh): blocks up to 24 wide, nx + 1 <= 16, no obstacle rows
+// the fragment-layout factor kernel (almpc_factor_mma.cuh): blocks up to 24 wide, nx + 1 <= 16
 #ifndef ALMPC_MMA_WPB
 #define ALMPC_MMA_WPB 4
 #endif
 constexpr int kWPM = ALMPC_MMA_WPB;  // warps = problems per CTA of the fragment-layout factor kernel
 template <int NX, int NU>
-constexpr bool mma_applies(int V) { return NX + NU <= 24 && NX + 1 <= 16 && V != 1; }
+constexpr bool mma_applies(int) { return NX + NU <= 24 && NX + 1 <= 16; }
 template <int NX, int NU, typename S, int V>
 static auto mma_kernel() -> decltype(&k_factor_solve<NX, NU, S, kWPB, V>) {
   if constexpr (mma_applies<NX, NU>(V)) return &k_factor_solve_mma<NX, NU, S, kWPM, V>;
@@ -267,7 +267,7 @@ static int make_plan(Plan& pl, int dev, int T, int n_obs, int select) {
     // fp32 problems: it factors in fp32 registers at 10 CTAs/SM (quadrotor 0.553 ms) while this kernel keeps its blocks
     // in FP64 accumulators whatever the interface type (0.620 ms) — selectable for its accuracy (no lost pivots).
     if constexpr (mma_applies<NX, NU>(V)) {
-      const size_t smem_mma = (size_t)kWPM * MmaLayout<NX, NU, S>(T, SE).total;
+      const size_t smem_mma = (size_t)kWPM * MmaLayout<NX, NU, S>(T, SE, n_obs).total;
       if (smem_mma + 1024 <= 227 * 1024 && allow_max_smem(km, optin) == cudaSuccess) {
         pl.use_mma = true;
         pl.fac_threads = kWPM * 32;
