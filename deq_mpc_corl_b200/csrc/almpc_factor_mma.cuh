@@ -20,11 +20,22 @@
 
 namespace almpc {
 
+#ifndef ALMPC_MMA_NO_SWZ
+#define ALMPC_MMA_NO_SWZ 0
+#endif
+// chunk swizzle of a staged 128-byte row: a bit permutation (bit0 -> bit2, bit1 -> bit0, bit2 -> bit1), i.e. linear
+// over XOR, so a lane's constant part and the compile-time part of a row index swizzle separately
+__host__ __device__ constexpr int mma_swz(int r) { return 4 * (r & 1) + ((r >> 1) & 1) + 2 * ((r >> 2) & 1); }
+
 template <int NX, int NU, typename S>
 struct MmaLayout {
   static constexpr int NN = NX + NU;
   static constexpr bool COPY16 = (NN * sizeof(S)) % 16 == 0;  // rows of G are 16-byte multiples: chunked copies
-  static constexpr int LDG = COPY16 ? NN + 16 / (int)sizeof(S) : NN + 1;  // padded row stride of the staged G block
+  // 128-byte rows (16 doubles): staged UNPADDED with the 16-byte chunks of row r XOR-swizzled by swz(r mod 8) — both
+  // fragment access patterns of the kernel and the cp.async writes are then bank-conflict free (with padded 144-byte
+  // rows they are 2- to 3-way conflicts: 240 of 1260 shared wavefronts per problem)
+  static constexpr bool SWZ = (NN * sizeof(S)) == 128 && !ALMPC_MMA_NO_SWZ;
+  static constexpr int LDG = SWZ ? NN : (COPY16 ? NN + 16 / (int)sizeof(S) : NN + 1);  // row stride of the staged G block
   int N, neq, nin, m;
   int dv, dg, bc, gs0, gs1, lsm, total;  // byte offsets (every region 16-byte aligned)
   int xu, w, lin, obv, hob;              // arrays the forward sweep is done with before lsm is written (double)
@@ -82,6 +93,18 @@ __device__ __forceinline__ void warp_copy_rows_async(S* dst, const S* src, int l
     warp_copy_block_async<ROWS, NN, LD>(dst, src, lane);
   }
 }
+// [ROWS][16 doubles] block -> unpadded shared rows with swizzled 16-byte chunks (MmaLayout::SWZ)
+template <int ROWS, typename S>
+__device__ __forceinline__ void warp_copy_rows_swz_async(S* dst, const S* src, int lane) {
+  constexpr int CH = ROWS * 8;
+  const int r0 = lane >> 3, c = lane & 7;
+  const int cb = c ^ mma_swz(r0);  // rows r0 + 4k: swz(r) = swz(r0) ^ 2 (k & 1)
+  char* d0 = (char*)dst + r0 * 128;
+  const char* s0 = (const char*)src + lane * 16;
+#pragma unroll
+  for (int k = 0; k < (CH + 31) / 32; ++k)
+    if (CH % 32 == 0 || lane + 32 * k < CH) cp_async16(d0 + k * 512 + ((cb ^ (2 * (k & 1))) << 4), s0 + k * 512);
+}
 // COUNT contiguous scalars, copy width W bytes (CopyWidth: the widest size that divides every block of the factor)
 template <int COUNT, int W, typename S>
 __device__ __forceinline__ void warp_copy_contig_async(S* dst, const S* src, int lane) {
@@ -131,6 +154,7 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
   static_assert(NT <= 3 && NTE <= 2 && NTE <= NT, "tile mapping: n <= 24, nx + 1 <= 16");
   constexpr bool OBS = (V == 1), SE = (V == 2);  // variant: 0 plain, 1 obstacle rows, 2 state estimator
   constexpr int LDG = MmaLayout<NX, NU, S>::LDG;
+  constexpr bool SWZ = MmaLayout<NX, NU, S>::SWZ;
   constexpr int CW = CopyWidth<NX, NU, S>::W;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_ring;
@@ -173,7 +197,10 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
                             : fac_g + (size_t)prob * factor_elems<NX, NU>(T);
   S* dbg = debug_g ? debug_g + (size_t)prob * (2 * L.N + 24) : nullptr;
 
-  if (T > 1) warp_copy_rows_async<NX, NN, LDG>(Gs0, Gp, lane);
+  if (T > 1) {
+    if constexpr (SWZ) warp_copy_rows_swz_async<NX>(Gs0, Gp, lane);
+    else warp_copy_rows_async<NX, NN, LDG>(Gs0, Gp, lane);
+  }
   cp_async_commit();
   S rho_s = rho_g[prob];
   // ---- prologue: dual / penalty update of the previous AL iteration (AL_mpc.py:316-317,325), entry residual
@@ -312,6 +339,9 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
   S* Gc = Gs0;
   S* Gn = Gs1;
   const bool isdiag = (q == r4);
+  // lane-constant parts of the swizzled addresses of G_t (in scalars): fragment loads / accumulator-layout loads
+  const int swz_f = q * 16 + (pg & 1) + 2 * ((pg >> 1) ^ mma_swz(q));
+  const int swz_x = pg * 16 + (q & 1) + 2 * ((q >> 1) ^ mma_swz(pg));
   const int tl_idx = (q < r4) ? q * 4 + r4 : r4 * 5;  // table slot of L11[r4][q]
   for (int t = 0; t < T; ++t) {
     S* Lg = fac + (size_t)t * NN * NN;
@@ -333,7 +363,9 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
 #pragma unroll
         for (int kk = 0; kk < KG; ++kk) {
           const int row = 4 * kk + q, col = 8 * tl + pg;
-          f[tl][kk] = ((NX % 4 == 0 || row < NX) && (NN % 8 == 0 || col < NN)) ? (double)Gc[row * LDG + col] : 0.0;
+          // swizzled rows: element (row, col) sits in chunk (col / 2) ^ swz(row mod 8); row = 4 kk + q, col = 8 tl + pg
+          const int at = SWZ ? (swz_f ^ (2 * ((4 * tl) ^ (2 * (kk & 1))))) + 64 * kk : row * LDG + col;
+          f[tl][kk] = ((NX % 4 == 0 || row < NX) && (NN % 8 == 0 || col < NN)) ? (double)Gc[at] : 0.0;
         }
 #pragma unroll
       for (int kk = 0; kk < KG; ++kk) {
@@ -368,7 +400,9 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
           const int row = 8 * xt + pg, col = 8 * ct + q + 4 * e;
           const bool cok = (NN % 8 == 0 || col < NN);
           double v = 0.0;
-          if (has_G && row < NX && cok) v = -rho * (double)Gc[row * LDG + col];
+          // (swizzled rows: row = 8 xt + pg, col = 8 ct + 4 e + q)
+          const int at = SWZ ? (swz_x ^ (2 * ((2 * e) ^ (4 * ct)))) + 128 * xt : row * LDG + col;
+          if (has_G && row < NX && cok) v = -rho * (double)Gc[at];
           if (xt == XR && rhs_lane) {
             v = cok ? dv[t * NN + col] - rw[ct][e] : 0.0;
             if (dbg && cok) dbg[t * NN + col] = (S)v;
@@ -376,7 +410,10 @@ k_factor_solve_mma(const KParams<S> P, const S* __restrict__ Qd_g, const S* __re
           X[xt][ct][e] = v;
         }
     __syncwarp();  // G_t has no reader left: prefetch G_{t+1} behind the factorisation
-    if (t + 1 < T - 1) warp_copy_rows_async<NX, NN, LDG>(Gn, Gp + (size_t)(t + 1) * NX * NN, lane);
+    if (t + 1 < T - 1) {
+      if constexpr (SWZ) warp_copy_rows_swz_async<NX>(Gn, Gp + (size_t)(t + 1) * NX * NN, lane);
+      else warp_copy_rows_async<NX, NN, LDG>(Gn, Gp + (size_t)(t + 1) * NX * NN, lane);
+    }
     cp_async_commit();
     if (has_E) {
       double sy[NTE][NTX][2];
