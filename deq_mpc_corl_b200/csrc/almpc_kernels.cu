@@ -8,8 +8,10 @@
 //
 //   k_jacobian      1 thread = 1 (problem, stage t, tangent column j): dynamics + Jacobians G_t=[A_t B_t]
 //                   by forward-mode duals, residuals c_t                                       al_utils.py:233-265
-//   k_factor_solve(_pair)  1 warp = 1 problem (row per lane), or for blocks up to 16 wide 1 half-warp = 1 problem
-//                   (two rows per lane, the default for pendulum / cartpoles / quadrotor): residual statistics,
+//   k_factor_solve(_mma|_pair)  1 warp = 1 problem.  Default for fp64 blocks wider than 8 (quadrotor, flying
+//                   cartpole): k_factor_solve_mma, the blocked Cholesky kept in FP64 tensor-core fragment layout
+//                   (almpc_factor_mma.cuh); for the small models and fp32 1 half-warp = 1 problem, two matrix rows
+//                   per lane (_pair); the row-per-lane kernel is the fallback.  All three: residual statistics,
 //                   (optional) dual/penalty update of
 //                   the previous AL iteration (AL_mpc.py:315-325), merit (al_utils.py:52-77), gradient
 //                   (:113-117), block-tridiagonal Cholesky of H = diag(Qd) + rho Jc^T Jc and both triangular
@@ -263,7 +265,10 @@ static int make_plan(Plan& pl, int dev, int T, int n_obs, int select) {
                                                ((sizeof(S) == 8 && NX + NU > 8) || (select & ALMPC_SELECT_FAC_MMA))) {
     // Default for fp64 problems with blocks wider than 8 (measured per launch, B200): quadrotor 64K 0.63 vs 0.88 ms (8K:
     // 0.095 vs 0.137 ms), flying cartpole T=10 16K 0.61 vs 0.95 ms.  Blocks that fit one 8x8 tile (pendulum, cartpoles)
-    // keep the half-warp kernel (64K problems: 0.170 / 0.226 / 0.297 ms against 0.184 / 0.271 / 0.311 ms), and so do
+    // keep the half-warp kernel (64K problems: 0.170 / 0.226 / 0.297 ms against 0.184 / 0.271 / 0.311 ms; for single-wave
+    // batches this kernel is faster, 13 vs 17 us per launch at 200 pendulum problems, but the last iteration of the pendulum
+    // DEQ chain (rho = 1e12, cond(H) beyond 1e12) then sits 4.4e-5 from the oracle instead of 7e-6, outside the budget of
+    // test_deq_chain_without_resync_matches_oracle; tools/chain_accuracy.py), and so do
     // fp32 problems: it factors in fp32 registers at 10 CTAs/SM (quadrotor 0.553 ms) while this kernel keeps its blocks
     // in FP64 accumulators whatever the interface type (0.620 ms) — selectable for its accuracy (no lost pivots).
     if constexpr (mma_applies<NX, NU>(V)) {
