@@ -947,18 +947,19 @@ def test_mpc_cuda_graph_mode_equals_eager():
         assert a[5] == b[5]
 
 
-def test_deq_chain_without_resync_matches_oracle():
+@pytest.mark.parametrize("model,T,B", [("pendulum", 5, 200), ("rex_quadrotor", 5, 48)])
+def test_deq_chain_without_resync_matches_oracle(model, T, B):
     """BASELINE config 1 shape (pendulum, T=5, B=200, fp64, 6 DEQ iterations of al_iter=2 with lam / rho and the
-    warm start carried across calls, rho 1 -> 1e12): the CUDA module and the oracle run the whole chain from the
-    same inputs with NO re-synchronisation; the synthetic "network" pulls x_ref towards each side's own solution."""
+    warm start carried across calls, rho 1 -> 1e12) and the headline model (quadrotor, through the fragment-layout factor
+    kernel): the CUDA module and the oracle run the whole chain from the same inputs with NO re-synchronisation; the
+    synthetic "network" pulls x_ref towards each side's own solution."""
     from oracle import almpc_oracle as orc
     from oracle.problem_gen import make_oracle_model
 
-    model, T, B = "pendulum", 5, 200
     spec = MODEL_SPECS[model]
     inp = make_inputs(model, T, B, 1000)
     dyn = make_dyn(model)
-    ctrl = MPC(2, 1, T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B)
+    ctrl = MPC(spec["nx"], spec["nu"], T, u_lower=inp["u_lower"], u_upper=inp["u_upper"], n_batch=B)
     ompc = orc.OracleMPC(make_oracle_model(model), T, inp["u_lower"], inp["u_upper"], B)
     xr_c, xr_o = inp["x_ref"].to(DEV), inp["x_ref"].clone()
     ctrl.reinitialize(xr_c, None)
