@@ -2,7 +2,7 @@
 the row-per-lane kernel (ALMPC_FAC_SINGLE) — or, with a second argument `pair`, against the half-warp-per-problem
 kernel (ALMPC_FAC_PAIR) — on random (model, T, B, variant) draws, two chained calls each (the second runs the fused
 dual update): same Newton-step counts and status, iterates / multipliers / gradients equal to rounding.
-python tools/diff_kernels.py [n_draws [pair]]"""
+python tools/diff_kernels.py [n_draws [pair|single] [mma]]   (mma: force the fragment-layout kernel everywhere)"""
 import os, random, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
@@ -15,10 +15,12 @@ dev = "cuda:0"
 
 
 def run(model, T, B, seed, se, single):
-    os.environ.pop("ALMPC_FAC_SINGLE", None)
-    os.environ.pop("ALMPC_FAC_PAIR", None)
+    for k in ("ALMPC_FAC_SINGLE", "ALMPC_FAC_PAIR", "ALMPC_FAC_MMA"):
+        os.environ.pop(k, None)
     if single:
         os.environ[OTHER] = "1"
+    elif FORCE_MMA:  # the fragment-layout kernel also where it is not the default (one-tile models)
+        os.environ["ALMPC_FAC_MMA"] = "1"
     spec = MODEL_SPECS[model]
     inp = make_inputs(model, T, B, seed)
     dyn = make_dyn(model, dt=spec["dt"])
@@ -44,6 +46,7 @@ def rel(a, b):
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 OTHER = "ALMPC_FAC_PAIR" if len(sys.argv) > 2 and sys.argv[2] == "pair" else "ALMPC_FAC_SINGLE"
+FORCE_MMA = "mma" in sys.argv[2:]
 rng = random.Random(2024)
 worst = 0.0
 for i in range(n):
